@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the contrast-maximization inner loop (BASELINE.json metric): events/s per CM iteration
+(warp + IWE + variance cost + gradient w.r.t. the dense flow) at 346x260.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            the B200 path (one rank per GPU under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]       the reference algorithm on the host cores
+
+A step = one CM iteration over the resident event batch with a fresh flow field.  Workload = BASELINE config 2
+(5 M synthetic events per GPU, 260x346 dense flow, variance cost + gradient); for N > 1 every rank holds its own
+5 M-event contiguous shard (weak scaling) and the partial IWE / gradient are all-reduced over NCCL each step.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 260, 346
+EVENTS_PER_GPU = 5_000_000
+MAX_FLOW = 10.0          # px of displacement over the normalised window
+N_FLOWS = 8              # distinct pre-generated flow fields cycled through the steps
+L2_FLUSH_BYTES = 512 << 20
+METRIC = "events/sec per CM iteration (warp+IWE+cost+grad) @346x260"
+UNIT = "events/s"
+
+
+def synth_events(n: int, seed: int) -> np.ndarray:
+    """The reference's own fixture (src/utils/event_utils.py:18-47), seeded: integer pixel coordinates, sorted
+    uniform timestamps in [0, 0.05), random polarity; fp32 [n,4] = (x=row, y=col, t, p)."""
+    rng = np.random.default_rng(seed)
+    ev = np.empty((n, 4), dtype=np.float32)
+    ev[:, 0] = rng.integers(0, H, n)
+    ev[:, 1] = rng.integers(0, W, n)
+    ev[:, 2] = np.sort(rng.uniform(0.0, 0.05, n))
+    ev[:, 3] = rng.integers(0, 2, n)
+    return ev
+
+
+def synth_flows(k: int, seed: int) -> np.ndarray:
+    """Smooth flows as the pyramid produces at its finest scale: a 16x16 patch grid, bilinearly up-sampled
+    (SURVEY.md section 8d), |flow| <= MAX_FLOW."""
+    import torch
+    rng = np.random.default_rng(seed)
+    grid = torch.from_numpy(rng.uniform(-MAX_FLOW, MAX_FLOW, (k, 2, 16, 16)).astype(np.float32))
+    return torch.nn.functional.interpolate(grid, size=(H, W), mode="bilinear", align_corners=False).numpy()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Polls SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+                nv.nvmlClocksThrottleReasonApplicationsClocksSetting: "applications_clocks_setting",
+            }
+            while not self._stop_evt.is_set():
+                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
+                mhz = int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                if util > 0:
+                    self.samples.append(mhz)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing -> report, do not fake
+            self.error = repr(e)
+
+    def finish(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=2.0)
+        out = {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.error:
+            out["error"] = self.error
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_steps(ev_np: np.ndarray, flows_np: np.ndarray, steps: int, warmup: int):
+    """The reference's algorithm for this path (torch CPU branch: warp -> bilinear vote -> variance -> autograd
+    gradient), restated in oracle/cm_oracle.py and pinned to the reference's outputs by tests/test_oracle_golden.py.
+    fp32, all host threads.  Returns (seconds per step list, threads)."""
+    import torch
+    from oracle import cm_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ev = torch.from_numpy(ev_np)
+    times = []
+    for i in range(warmup + steps):
+        flow = torch.from_numpy(flows_np[i % len(flows_np)])
+        t0 = time.perf_counter()
+        val, grad = O.objective_value_and_grad(ev, flow, (H, W), motion_model="dense-flow", cost="image_variance")
+        float(val)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, threads
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = EVENTS_PER_GPU
+    ev = synth_events(n, seed=0)
+    flows = synth_flows(N_FLOWS, seed=100)
+    times, threads = cpu_reference_steps(ev, flows, args.steps, args.warmup)
+    sec = float(np.mean(times))
+    value = n / sec
+    sample = f"{n} events (one full config-2 batch) per step, fp32, torch CPU ops, {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: 5M events, 260x346 dense flow, variance cost+grad", "events": n, "image": [H, W]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from event_based_optical_flow_b200 import ContrastObjective, _lib
+    from event_based_optical_flow_b200.distributed import global_time_range
+    _lib.load()
+
+    n = EVENTS_PER_GPU
+    ev_np = synth_events(n, seed=rank)            # rank r's contiguous shard of the N*5M-event stream
+    ev_np[:, 2] = (ev_np[:, 2] + 0.05 * rank)     # shards are consecutive in time
+    flows_np = synth_flows(N_FLOWS, seed=100)     # identical on every rank (the flow is replicated)
+    ev = torch.from_numpy(ev_np).to(dev)
+    flows = torch.from_numpy(flows_np).to(dev)
+    group = dist.group.WORLD if world > 1 else None
+    t_range = global_time_range(ev, group)
+    obj = ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow", sigma=0.0, order=args.order,
+                            process_group=group, t_range=t_range)
+    obj.plan.set_variant(args.vote_variant, args.grad_variant)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    cost_buf = torch.zeros(1, dtype=torch.float64, device=dev)
+    grad_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
+    flow_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
+
+    # one CM iteration; single GPU: captured once in a CUDA graph (7 nodes), multi GPU: eager (NCCL in between)
+    graph = None
+    if world == 1 and not args.no_graph:
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            obj.step_into(flow_buf, cost_buf, grad_buf)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            obj.step_into(flow_buf, cost_buf, grad_buf)
+
+    def step(i: int):
+        if graph is not None:
+            flow_buf.copy_(flows[i % N_FLOWS])  # outside the timed bracket: the flow is "already resident"
+            return None
+        return flows[i % N_FLOWS]
+
+    def run_steps(count: int, first: int):
+        """-> per-step device milliseconds (CUDA events on the launching stream), L2 flushed before every step."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
+        for k in range(count):
+            f = step(first + k)
+            flush.zero_()
+            evs[k][0].record()
+            if graph is not None:
+                graph.replay()
+            else:
+                c, g = obj.value_and_grad(f)
+            evs[k][1].record()
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs]
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    run_steps(args.warmup, 0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = run_steps(args.steps, args.warmup)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = float(np.sum(ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: per step the motion comes from pinned host memory (what scipy hands
+    # over, scipy_autograd/torch_wrapper.py:33-36) and cost + gradient go back to the host (:46-49).  Events stay
+    # resident, as in the reference (patch_contrast_pyramid.py:186 moves them once per optimize()).
+    host_flows = [torch.from_numpy(flows_np[i]).pin_memory() for i in range(N_FLOWS)]
+    host_grad = torch.empty(2, H, W, dtype=torch.float32).pin_memory()
+    host_cost = torch.empty(1, dtype=torch.float64).pin_memory()
+
+    def e2e_steps(count: int):
+        t0 = time.perf_counter()
+        for k in range(count):
+            flush.zero_()
+            f = host_flows[k % N_FLOWS].to(dev, non_blocking=True)
+            c, g = obj.value_and_grad(f)
+            host_grad.copy_(g, non_blocking=True)
+            host_cost.copy_(c.reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    def flush_only(count: int):
+        t0 = time.perf_counter()
+        for k in range(count):
+            flush.zero_()
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_steps(max(3, args.warmup))
+    if world > 1:
+        dist.barrier()
+    e2e_s = e2e_steps(args.steps) - flush_only(args.steps)   # the L2 flush is hygiene, not part of the step
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * n * args.steps / e2e_s
+    h2d = int(host_flows[0].numel() * 4)
+    d2h = int(host_grad.numel() * 4 + 8)
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernels, each timed alone with CUDA events (stage mask = event kernel only)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        HWp = H * W
+        kernels = {}
+        if world == 1:
+            from event_based_optical_flow_b200 import _lib as L
+            import ctypes as C
+            obj.value_and_grad(flows[0])  # leave a consistent workspace behind
+            obj.plan.set_stage_mask(2)
+            stream = torch.cuda.current_stream().cuda_stream
+            m = flows[1].contiguous()
+
+            def time_kernel(fn, reps=20):
+                out = []
+                for _ in range(reps + 3):
+                    flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    fn()
+                    b.record()
+                    torch.cuda.synchronize()
+                    out.append(a.elapsed_time(b))
+                return float(np.mean(out[3:]))
+
+            k1 = time_kernel(lambda: L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, None, None, None, stream))
+            k3 = time_kernel(lambda: L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), stream))
+            obj.plan.set_stage_mask(7)
+            # algorithmic bytes per launch (DESIGN.md "Kernels"): K1 = 16 B/event + flow read 8 HW + IWE write 4 HW;
+            # K3 = 16 B/event + flow read 8 HW + dL/dIWE read 4 HW + gradient write 8 HW
+            kernels = {"vote_fused_kernel(K1)": {"ms": k1, "bytes": 16 * n + 12 * HWp},
+                       "grad_fused_kernel(K3)": {"ms": k3, "bytes": 16 * n + 20 * HWp}}
+            for v in kernels.values():
+                v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        step_bytes = 32 * n + 32 * HWp  # per CM iteration, single reference time, dense flow
+        step_gbps = step_bytes / (ms_per_step * 1e-3) / 1e9
+        if kernels:
+            dom = max(kernels, key=lambda k: kernels[k]["ms"])
+            roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                    "kernels": kernels, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
+        else:
+            roof = {"bound": "hbm", "kernel": "whole CM iteration (per GPU)", "achieved": step_gbps, "peak": peak, "unit": "GB/s",
+                    "frac": step_gbps / peak, "traffic": None, "peak_source": peak_src}
+
+        # ---- CPU baseline: the oracle port of the reference algorithm on this box's host cores, bounded sample
+        cpu = None
+        if world == 1 and not args.skip_cpu:
+            times, threads = cpu_reference_steps(synth_events(n, seed=0), flows_np, steps=5, warmup=1)
+            cpu = {"value": n / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"5 timed + 1 warm-up CM iterations over the full {n}-event config-2 batch, fp32 torch CPU ops"}
+
+        clocks = sampler.finish() if sampler else None
+        per_step_kernels = 5  # K1 vote, fold(+variance), combine, gq_build, K3 grad  (+ 2 memset nodes, not counted)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "config2: 5M events per GPU, 260x346 dense flow, variance cost+grad", "events_per_gpu": n,
+                       "image": [H, W], "flow": "smooth (16x16 grid upsampled), |f|<=10px, fresh per step",
+                       "event_order": args.order, "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
+                       "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset)",
+                       "parallelism": f"events sharded x{world}, allreduce(IWE)+allreduce(grad)" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "host pinned flow -> device, value_and_grad through the Python API, cost+grad -> host, sync; events resident"},
+            "gpu_launches": per_step_kernels * args.steps,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--order", choices=("asis", "tile", "pixel"), default="pixel")
+    ap.add_argument("--vote-variant", type=int, default=0)
+    ap.add_argument("--grad-variant", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,408 @@
+// Event-batch preparation: error plumbing, time range / reference-time parameters, and the resident plan
+// (validation + stable tile sort).  Everything here runs once per solver.optimize(), not per CM iteration.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "cmax_plan.cuh"
+
+namespace cmax {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return CMAX_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------ time range
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void init_minmax_kernel(float* mm) {
+  mm[0] = INFINITY;
+  mm[1] = -INFINITY;
+}
+
+// min/max over column 2.                                     src/warp.py:217-224, 256-257 (nt_min / nt_max)
+__global__ void __launch_bounds__(256) time_range_kernel(const float* __restrict__ ev, int64_t n, int stride,
+                                                         float* __restrict__ mm) {
+  float lo = INFINITY, hi = -INFINITY;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const float t = (stride == 4) ? ld_event(ev, i).z : __ldg(ev + i * stride + 2);
+    lo = fminf(lo, t);
+    hi = fmaxf(hi, t);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomic_min_float(mm + 0, lo);
+    atomic_max_float(mm + 1, hi);
+  }
+}
+
+// One thread restates the reference's scalar arithmetic: fp32 for ref/period (0-dim tensor ops), float64 for the
+// bin edges (numpy on the host), then the edge is rounded to fp32 because torch compares `scalar <= fp32 tensor`
+// in fp32.                                                  src/warp.py:201-233, 254-258, 342-345
+__global__ void time_params_kernel(const float* __restrict__ mm, cmax_time_params_t* __restrict__ out, int n_ref,
+                                   int n_bins, int normalize_t, cmax_ref r0, cmax_ref r1, cmax_ref r2, cmax_ref r3) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const cmax_ref refs[CMAX_MAX_REFS] = {r0, r1, r2, r3};
+  const float tmin = mm[0], tmax = mm[1];
+  out->n_ref = n_ref;
+  out->n_bins = n_bins;
+  out->normalize_t = normalize_t;
+  out->pad_ = 0;
+  for (int r = 0; r < n_ref; ++r) {
+    float ref;
+    if (refs[r].mode == 0) ref = tmin;
+    else if (refs[r].mode == 1) ref = tmax;
+    else ref = __fadd_rn(tmin, __fmul_rn(__fsub_rn(tmax, tmin), refs[r].fraction));
+    const float dlo = __fsub_rn(tmin, ref), dhi = __fsub_rn(tmax, ref);
+    const float period = __fsub_rn(dhi, dlo);
+    const float lo = normalize_t ? __fdiv_rn(dlo, period) : dlo;
+    const float hi = normalize_t ? __fdiv_rn(dhi, period) : dhi;
+    out->ref[r] = ref;
+    out->period[r] = period;
+    out->dt_min[r] = lo;
+    out->dt_max[r] = hi;
+    const double span = __dsub_rn((double)hi, (double)lo);
+    for (int b = 0; b < n_bins; ++b) {
+      const double e = __dadd_rn(__dmul_rn(__ddiv_rn((double)b, (double)n_bins), span), (double)lo);
+      out->edges[r][b] = (float)e;
+    }
+    out->edges[r][n_bins] = (float)__dadd_rn((double)hi, 1000.0);
+    for (int b = n_bins + 1; b <= CMAX_MAX_BINS; ++b) out->edges[r][b] = INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ plan kernels
+// Source pixel of an event: .long() truncation of the un-warped coordinates, src/warp.py:305
+__device__ __forceinline__ bool source_pixel(float x, float y, int H, int W, int* r, int* c) {
+  *r = __float2int_rz(x);
+  *c = __float2int_rz(y);
+  return (*r >= 0) && (*r < H) && (*c >= 0) && (*c < W) && (x == x) && (y == y);
+}
+
+__global__ void __launch_bounds__(256) validate_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
+                                                       int32_t* __restrict__ status) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    int r, c;
+    bad |= !source_pixel(__ldg(ev + i * stride), __ldg(ev + i * stride + 1), H, W, &r, &c);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+}
+
+// Sort key: tile id (TILE order: events of a tile keep their time order) or tile id * 1024 + pixel inside the tile
+// (PIXEL order).  Also counts events per tile for the chunk list of the privatised kernels.
+__global__ void __launch_bounds__(256) sort_keys_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
+                                                        int tiles_x, int by_pixel, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ idx, uint32_t* __restrict__ tile_counts) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    int r, c;
+    source_pixel(__ldg(ev + i * stride), __ldg(ev + i * stride + 1), H, W, &r, &c);  // validated before
+    const uint32_t tile = (uint32_t)((r / kTile) * tiles_x + (c / kTile));
+    keys[i] = by_pixel ? (tile * (uint32_t)(kTile * kTile) + (uint32_t)((r % kTile) * kTile + (c % kTile))) : tile;
+    idx[i] = (uint32_t)i;
+    atomicAdd(&tile_counts[tile], 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_events_kernel(const float* __restrict__ ev, int64_t n, int stride,
+                                                            const uint32_t* __restrict__ idx, float4* __restrict__ out) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += step) {
+    const float* e = ev + (int64_t)idx[j] * stride;
+    out[j] = make_float4(__ldg(e), __ldg(e + 1), __ldg(e + 2), stride >= 4 ? __ldg(e + 3) : 0.f);
+  }
+}
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int bits_for(uint64_t v) {
+  int b = 1;
+  while (b < 32 && (1ull << b) < v) ++b;
+  return b;
+}
+
+struct PlanLayout {
+  size_t off_params, off_minmax, off_status, off_events, off_keys[2], off_idx[2], off_counts, off_chunks, off_temp, temp_bytes, total;
+  int tiles_x, tiles_y, n_tiles, max_chunks, key_bits;
+};
+
+// Returns false (message set) when the CUB temp-storage query fails, e.g. without a device.
+static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
+  PlanLayout L;
+  memset(&L, 0, sizeof(L));
+  L.tiles_x = (W + kTile - 1) / kTile;
+  L.tiles_y = (H + kTile - 1) / kTile;
+  L.n_tiles = L.tiles_x * L.tiles_y;
+  size_t off = 0;
+  L.off_params = off; off = align_up(off + sizeof(cmax_time_params_t), 256);
+  L.off_minmax = off; off = align_up(off + 2 * sizeof(float), 256);
+  L.off_status = off; off = align_up(off + sizeof(int32_t), 256);
+  if (order != CMAX_ORDER_ASIS) {
+    L.key_bits = bits_for((uint64_t)L.n_tiles * (order == CMAX_ORDER_PIXEL ? kTile * kTile : 1));
+    L.max_chunks = (int)(n / kChunk) + L.n_tiles + 1;
+    L.off_events = off; off = align_up(off + (size_t)n * sizeof(float4), 256);
+    L.off_counts = off; off = align_up(off + (size_t)L.n_tiles * sizeof(uint32_t), 256);
+    L.off_chunks = off; off = align_up(off + (size_t)L.max_chunks * sizeof(Chunk), 256);
+    for (int k = 0; k < 2; ++k) {
+      L.off_keys[k] = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
+      L.off_idx[k] = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
+    }
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+    size_t temp = 0;
+    const cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp, dk, dv, (int)n, 0, L.key_bits, (cudaStream_t)0);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "cub::DeviceRadixSort::SortPairs (temp-storage query)");
+      return false;
+    }
+    L.temp_bytes = temp;
+    L.off_temp = off; off = align_up(off + temp + 256, 256);
+  }
+  L.total = off;
+  *out = L;
+  return true;
+}
+
+}  // namespace cmax
+
+using namespace cmax;
+
+extern "C" {
+
+int cmax_abi_version(void) { return CMAX_ABI_VERSION; }
+const char* cmax_last_error(void) { return g_last_error.c_str(); }
+const char* cmax_build_arch(void) { return "sm_100a"; }
+
+int cmax_time_range(const float* events, int64_t n, int ev_stride, float* d_minmax, cmax_stream_t stream) {
+  CMAX_REQUIRE(d_minmax != nullptr, "cmax_time_range: d_minmax is NULL");
+  CMAX_REQUIRE(n >= 0 && ev_stride >= 3, "cmax_time_range: need n >= 0 and ev_stride >= 3 (got %lld, %d)", (long long)n, ev_stride);
+  CMAX_REQUIRE(n == 0 || events != nullptr, "cmax_time_range: events is NULL");
+  cudaStream_t s = as_stream(stream);
+  init_minmax_kernel<<<1, 1, 0, s>>>(d_minmax);
+  if (n > 0) {
+    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
+    time_range_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, d_minmax);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
+}
+
+int cmax_time_params(const float* d_minmax, const cmax_ref* h_refs, int n_ref, int n_bins, int normalize_t,
+                     cmax_time_params_t* d_params, cmax_stream_t stream) {
+  CMAX_REQUIRE(d_minmax && h_refs && d_params, "cmax_time_params: NULL argument");
+  CMAX_REQUIRE(n_ref >= 1 && n_ref <= CMAX_MAX_REFS, "cmax_time_params: n_ref must be in [1,%d], got %d", CMAX_MAX_REFS, n_ref);
+  CMAX_REQUIRE(n_bins >= 0 && n_bins <= CMAX_MAX_BINS, "cmax_time_params: n_bins must be in [0,%d], got %d", CMAX_MAX_BINS, n_bins);
+  cmax_ref r[CMAX_MAX_REFS];
+  for (int i = 0; i < CMAX_MAX_REFS; ++i) r[i] = h_refs[i < n_ref ? i : 0];
+  for (int i = 0; i < n_ref; ++i)
+    CMAX_REQUIRE(r[i].mode >= 0 && r[i].mode <= 2, "cmax_time_params: ref %d has mode %d (0 first, 1 last, 2 fraction)", i, r[i].mode);
+  time_params_kernel<<<1, 1, 0, as_stream(stream)>>>(d_minmax, d_params, n_ref, n_bins, normalize_t ? 1 : 0, r[0], r[1], r[2], r[3]);
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
+}
+
+size_t cmax_plan_workspace_bytes(int64_t n, int H, int W, int order) {
+  if (n < 0 || n >= ((int64_t)1 << 31) || H <= 0 || W <= 0 || order < CMAX_ORDER_ASIS || order > CMAX_ORDER_PIXEL) {
+    set_error("cmax_plan_workspace_bytes: bad argument (n=%lld, %dx%d, order %d)", (long long)n, H, W, order);
+    return 0;
+  }
+  PlanLayout L;
+  if (!plan_layout(n, H, W, order, &L)) return 0;
+  return L.total;
+}
+
+int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_stride, int H, int W, int pad_h,
+                     int pad_w, float t_min, float t_max, int order, void* workspace, size_t workspace_bytes,
+                     cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_create: plan is NULL");
+  *plan = nullptr;
+  CMAX_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "cmax_plan_create: n must be in [0, 2^31), got %lld", (long long)n);
+  CMAX_REQUIRE(H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "cmax_plan_create: bad image size %dx%d pad %d,%d", H, W, pad_h, pad_w);
+  CMAX_REQUIRE((int64_t)(H + 2 * pad_h + 1) * (W + 2 * pad_w + 1) < (int64_t)1 << 28, "cmax_plan_create: image too large");
+  CMAX_REQUIRE(ev_stride >= 3, "cmax_plan_create: ev_stride must be >= 3");
+  CMAX_REQUIRE(n == 0 || events != nullptr, "cmax_plan_create: events is NULL");
+  CMAX_REQUIRE(order >= CMAX_ORDER_ASIS && order <= CMAX_ORDER_PIXEL, "cmax_plan_create: unknown event order %d", order);
+  const bool sort = order != CMAX_ORDER_ASIS;
+  CMAX_REQUIRE(sort || ev_stride == 4, "cmax_plan_create: un-sorted plans borrow the caller's array and need ev_stride == 4");
+  CMAX_REQUIRE(sort || (reinterpret_cast<uintptr_t>(events) & 15) == 0, "cmax_plan_create: events must be 16-byte aligned");
+  PlanLayout L;
+  if (!plan_layout(n, H, W, order, &L)) return CMAX_ERR_CUDA;
+  if (workspace == nullptr || workspace_bytes < L.total) {
+    set_error("cmax_plan_create: workspace of %zu bytes needed, %zu given", L.total, workspace_bytes);
+    return CMAX_ERR_WORKSPACE;
+  }
+  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_plan_create: workspace must be 256-byte aligned");
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+
+  cmax_plan* p = new (std::nothrow) cmax_plan();
+  CMAX_REQUIRE(p != nullptr, "cmax_plan_create: out of host memory");
+  memset(p, 0, sizeof(*p));
+  p->n = n; p->H = H; p->W = W; p->pad_h = pad_h; p->pad_w = pad_w;
+  p->Hp = H + 2 * pad_h; p->Wp = W + 2 * pad_w;
+  p->tiles_x = L.tiles_x; p->tiles_y = L.tiles_y; p->n_tiles = L.n_tiles;
+  p->d_params = reinterpret_cast<cmax_time_params_t*>(ws + L.off_params);
+  p->d_minmax = reinterpret_cast<float*>(ws + L.off_minmax);
+  p->d_status = reinterpret_cast<int32_t*>(ws + L.off_status);
+  p->events = events;
+  p->order = CMAX_ORDER_ASIS;
+  p->stage_mask = 7;
+
+  int rc = CMAX_OK;
+  std::vector<uint32_t> h_counts;
+  std::vector<Chunk> h_chunks;
+  float h_mm[2] = {t_min, t_max};
+  int32_t h_status = 0;
+#define PLAN_CHECK(call)                                      \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call); goto fail; } \
+  } while (0)
+
+  PLAN_CHECK(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t), s));
+  if (n > 0) {
+    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
+    validate_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, p->d_status);
+  }
+  if (t_min != t_min || t_max != t_max) {  // NaN -> compute from this batch
+    rc = cmax_time_range(events, n, ev_stride, p->d_minmax, stream);
+    if (rc != CMAX_OK) goto fail;
+    PLAN_CHECK(cudaMemcpyAsync(h_mm, p->d_minmax, sizeof(h_mm), cudaMemcpyDeviceToHost, s));
+  } else {
+    PLAN_CHECK(cudaMemcpyAsync(p->d_minmax, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, s));
+  }
+  PLAN_CHECK(cudaMemcpyAsync(&h_status, p->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PLAN_CHECK(cudaStreamSynchronize(s));
+  if (h_status != 0) {
+    set_error("cmax_plan_create: an event's pixel (x=row, y=col) lies outside the %dx%d image (or is NaN); "
+              "the reference's torch.gather raises here (src/warp.py:305-307)", H, W);
+    rc = CMAX_ERR_SOURCE_OOB;
+    goto fail;
+  }
+  p->t_min = h_mm[0];
+  p->t_max = h_mm[1];
+
+  if (sort && n > 0) {
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + L.off_counts);
+    float4* sorted = reinterpret_cast<float4*>(ws + L.off_events);
+    cub::DoubleBuffer<uint32_t> dk(reinterpret_cast<uint32_t*>(ws + L.off_keys[0]), reinterpret_cast<uint32_t*>(ws + L.off_keys[1]));
+    cub::DoubleBuffer<uint32_t> dv(reinterpret_cast<uint32_t*>(ws + L.off_idx[0]), reinterpret_cast<uint32_t*>(ws + L.off_idx[1]));
+    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
+    PLAN_CHECK(cudaMemsetAsync(counts, 0, (size_t)L.n_tiles * sizeof(uint32_t), s));
+    sort_keys_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, L.tiles_x, order == CMAX_ORDER_PIXEL, dk.Current(),
+                                          dv.Current(), counts);
+    size_t temp = L.temp_bytes + 256;
+    PLAN_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.off_temp, temp, dk, dv, (int)n, 0, L.key_bits, s));  // stable
+    gather_events_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, dv.Current(), sorted);
+    PLAN_CHECK(cudaGetLastError());
+    h_counts.resize(L.n_tiles);
+    PLAN_CHECK(cudaMemcpyAsync(h_counts.data(), counts, (size_t)L.n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    PLAN_CHECK(cudaStreamSynchronize(s));
+    uint32_t begin = 0;
+    for (int t = 0; t < L.n_tiles; ++t) {
+      for (uint32_t b = 0; b < h_counts[t]; b += kChunk) {
+        Chunk c;
+        c.tile = t;
+        c.begin = (int32_t)(begin + b);
+        c.count = (int32_t)std::min<uint32_t>(kChunk, h_counts[t] - b);
+        c.pad_ = 0;
+        h_chunks.push_back(c);
+      }
+      begin += h_counts[t];
+    }
+    if ((int)h_chunks.size() > L.max_chunks || begin != (uint32_t)n) {
+      set_error("cmax_plan_create: internal error, %zu chunks (max %d), %u of %lld events binned", h_chunks.size(),
+                L.max_chunks, begin, (long long)n);
+      rc = CMAX_ERR_WORKSPACE;
+      goto fail;
+    }
+    Chunk* d_chunks = reinterpret_cast<Chunk*>(ws + L.off_chunks);
+    PLAN_CHECK(cudaMemcpyAsync(d_chunks, h_chunks.data(), h_chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, s));
+    PLAN_CHECK(cudaStreamSynchronize(s));
+    p->events = reinterpret_cast<const float*>(sorted);
+    p->chunks = d_chunks;
+    p->n_chunks = (int)h_chunks.size();
+    p->order = order;
+  }
+#undef PLAN_CHECK
+  {
+    const cmax_ref first = {0, 0.0f};
+    rc = cmax_plan_set_refs(p, &first, 1, 0, stream);
+    if (rc != CMAX_OK) goto fail;
+  }
+  *plan = p;
+  return CMAX_OK;
+fail:
+  delete p;
+  return rc;
+}
+
+void cmax_plan_destroy(cmax_plan_t* plan) { delete plan; }
+
+int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_t* h_n, int32_t* h_order) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_info: plan is NULL");
+  if (h_tmin) *h_tmin = plan->t_min;
+  if (h_tmax) *h_tmax = plan->t_max;
+  if (h_n) *h_n = plan->n;
+  if (h_order) *h_order = plan->order;
+  return CMAX_OK;
+}
+
+int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
+  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 2, "cmax_plan_set_variant: vote_variant must be 0, 1 or 2");
+  CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 1, "cmax_plan_set_variant: grad_variant must be 0 or 1");
+  CMAX_REQUIRE(vote_variant != 2 || plan->order != CMAX_ORDER_ASIS, "cmax_plan_set_variant: the privatised vote needs tile- or pixel-ordered events");
+  plan->vote_variant = vote_variant;
+  plan->grad_variant = grad_variant;
+  return CMAX_OK;
+}
+
+int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_stage_mask: plan is NULL");
+  CMAX_REQUIRE(mask >= 1 && mask <= 7, "cmax_plan_set_stage_mask: mask must be in [1,7]");
+  plan->stage_mask = mask;
+  return CMAX_OK;
+}
+
+int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_refs: plan is NULL");
+  const int rc = cmax_time_params(plan->d_minmax, h_refs, n_ref, n_bins, 1, plan->d_params, stream);
+  if (rc == CMAX_OK) {
+    plan->n_ref = n_ref;
+    plan->n_bins = n_bins;
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,543 @@
+// The per-iteration hot path: K1 (warp + bilinear vote of every event, all reference times in one pass),
+// the fold (per-corner accumulators -> IWE, with the variance sums fused in), K2 glue (blur / statistics / scalar
+// cost / per-corner gradient pictures) and K3 (re-warp, gather dL/dIWE, chain to dL/dmotion).
+//
+// Data layout in HBM / L2 (everything image-sized is L2 resident; only the event stream comes from HBM):
+//   events   float4[n]                       one 16-byte streamed load per event per pass
+//   acc      float4[n_ref][(Hp+1)*(Wp+1)]    per-corner accumulators: cell (i,j), i in [-1,Hp-1], j in [-1,Wp-1] holds
+//                                            the four bilinear weights of all events whose floor pixel is (i,j), so an
+//                                            event issues ONE 16-byte vector reduction (red.global.add.v4.f32)
+//                                            instead of four scalar ones;  IWE[r,c] = acc[r,c].x + acc[r-1,c].y +
+//                                            acc[r,c-1].z + acc[r-1,c-1].w  applies the reference's per-corner masks
+//                                            by construction (src/event_image_converter.py:355-372)
+//   gq       float4[n_ref][(Hp+1)*(Wp+1)]    the adjoint of that fold: cell (i,j) = dL/dIWE at the four (masked)
+//                                            corners, so K3 gathers ONE float4 per event per reference time
+#include "cmax_plan.cuh"
+#include "cmax_stats.cuh"
+
+namespace cmax {
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct ObjLayout {
+  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_gxy, off_g, off_g2, off_gq, total;
+  int64_t cells, HW;
+};
+
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+static ObjLayout obj_layout(int Hp, int Wp) {
+  ObjLayout L;
+  const int R = CMAX_MAX_REFS;
+  L.cells = (int64_t)(Hp + 1) * (Wp + 1);
+  L.HW = (int64_t)Hp * Wp;
+  size_t off = 0;
+  L.off_acc = off;     off = align256(off + (size_t)R * L.cells * sizeof(float4));
+  L.off_iwe = off;     off = align256(off + (size_t)R * L.HW * sizeof(float));
+  L.off_blur = off;    off = align256(off + (size_t)R * L.HW * sizeof(float));
+  L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
+  L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
+  // [StatAcc block][Sobel pair] is exactly the workspace layout cmax_image_stats expects (cmax_cost.cu)
+  L.off_statacc = off; off = align256(off + (size_t)R * sizeof(StatAcc));
+  L.off_gxy = off;     off = align256(off + (size_t)R * 2 * L.HW * sizeof(float));
+  L.off_g = off;       off = align256(off + (size_t)R * L.HW * sizeof(float));
+  L.off_g2 = off;      off = align256(off + (size_t)R * L.HW * sizeof(float));
+  L.off_gq = off;      off = align256(off + (size_t)R * L.cells * sizeof(float4));
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------ per-event math
+struct FusedArgs {
+  const float4* ev;
+  int64_t n;
+  int H, W, Hp, Wp, pad_h, pad_w;
+  const float* motion;
+  const cmax_time_params_t* tp;
+  int64_t cells;  // (Hp+1)*(Wp+1)
+};
+
+// Time parameters one CTA needs, staged in shared memory once per CTA.
+struct TimeSmem {
+  float ref[CMAX_MAX_REFS], period[CMAX_MAX_REFS], dt_min[CMAX_MAX_REFS], inv_width[CMAX_MAX_REFS];
+  float edges[CMAX_MAX_REFS][CMAX_MAX_BINS + 1];
+  int n_bins, normalize_t;
+};
+
+template <int NREF, bool VOXEL>
+__device__ __forceinline__ void stage_time(const cmax_time_params_t* __restrict__ tp, TimeSmem& s) {
+  if (threadIdx.x < NREF) {
+    const int r = threadIdx.x;
+    s.ref[r] = tp->ref[r];
+    s.period[r] = tp->period[r];
+    s.dt_min[r] = tp->dt_min[r];
+    s.inv_width[r] = (float)tp->n_bins / (tp->dt_max[r] - tp->dt_min[r]);
+  }
+  if (threadIdx.x == 0) {
+    s.n_bins = tp->n_bins;
+    s.normalize_t = tp->normalize_t;
+  }
+  if (VOXEL) {
+    for (int k = threadIdx.x; k < NREF * (CMAX_MAX_BINS + 1); k += blockDim.x)
+      s.edges[k / (CMAX_MAX_BINS + 1)][k % (CMAX_MAX_BINS + 1)] = tp->edges[k / (CMAX_MAX_BINS + 1)][k % (CMAX_MAX_BINS + 1)];
+  }
+  __syncthreads();
+}
+
+// One event, one reference time: (x', y', dt, bin).        src/warp.py:254-258, 306-307, 346-357, 507-514
+template <int MODEL>
+__device__ __forceinline__ void warp_ref(const float4 e, int src, int HW, const float* __restrict__ motion, const TimeSmem& s,
+                                         int r, float f0, float f1, float& xw, float& yw, float& dt, int& bin) {
+  dt = normalised_dt(e.z, s.ref[r], s.period[r], s.normalize_t);
+  bin = 0;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    xw = warp_plus(e.x, dt, f0);
+    yw = warp_plus(e.y, dt, f1);
+  } else if (MODEL == CMAX_MOTION_DENSE) {
+    xw = warp_minus(e.x, dt, f0);
+    yw = warp_minus(e.y, dt, f1);
+  } else {
+    bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
+    xw = e.x;
+    yw = e.y;
+    if (bin >= 0) {
+      const float* f = motion + (int64_t)bin * 2 * HW;
+      xw = warp_minus(e.x, dt, __ldg(f + src));
+      yw = warp_minus(e.y, dt, __ldg(f + HW + src));
+    }
+  }
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ K1
+// VARIANT 0: one red.v4 per event per reference time into the per-corner accumulators.
+// VARIANT 1: four masked scalar red.f32 straight into the IWE (the textbook scatter; kept as the measured baseline).
+template <int MODEL, int NREF, int VARIANT>
+__global__ void __launch_bounds__(256) vote_fused_kernel(FusedArgs a, float4* __restrict__ acc, float* __restrict__ iwe) {
+  __shared__ TimeSmem s;
+  stage_time<NREF, MODEL == CMAX_MOTION_VOXEL>(a.tp, s);
+  const int HW = a.H * a.W;
+  const int64_t HWp = (int64_t)a.Hp * a.Wp;
+  float th0 = 0.f, th1 = 0.f;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    th0 = __ldg(a.motion);
+    th1 = __ldg(a.motion + 1);
+  }
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += step) {
+    const float4 e = __ldcs(a.ev + i);
+    int src = 0;
+    float f0 = th0, f1 = th1;
+    if (MODEL != CMAX_MOTION_2DOF) src = __float2int_rz(e.x) * a.W + __float2int_rz(e.y);  // validated by the plan
+    if (MODEL == CMAX_MOTION_DENSE) {
+      f0 = __ldg(a.motion + src);
+      f1 = __ldg(a.motion + HW + src);
+    }
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      float xw, yw, dt;
+      int bin;
+      warp_ref<MODEL>(e, src, HW, a.motion, s, r, f0, f1, xw, yw, dt, bin);
+      const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+      float w[4];
+      vote_weights(v, w);
+      if (VARIANT == 0) {
+        if (v.row >= -1 && v.row < a.Hp && v.col >= -1 && v.col < a.Wp)
+          red_add_v4(acc + r * a.cells + (int64_t)(v.row + 1) * (a.Wp + 1) + (v.col + 1), w[0], w[1], w[2], w[3]);
+      } else {
+        const bool r0 = v.row >= 0 && v.row < a.Hp, r1 = v.row >= -1 && v.row + 1 < a.Hp;
+        const bool c0 = v.col >= 0 && v.col < a.Wp, c1 = v.col >= -1 && v.col + 1 < a.Wp;
+        float* p = iwe + r * HWp + (int64_t)v.row * a.Wp + v.col;
+        if (r0 && c0) atomicAdd(p, w[0]);
+        if (r1 && c0) atomicAdd(p + a.Wp, w[1]);
+        if (r0 && c1) atomicAdd(p + 1, w[2]);
+        if (r1 && c1) atomicAdd(p + a.Wp + 1, w[3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fold
+// acc -> IWE; optionally the variance sums of the crop in the same pass (fp64 accumulators).
+__global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restrict__ acc, float* __restrict__ iwe, int Hp, int Wp,
+                                                          int64_t cells, int want_var, int omit, StatAcc* __restrict__ sacc,
+                                                          double* __restrict__ stats) {
+  __shared__ double red[kStatBlock / 32];
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)Hp * Wp;
+  const float4* A = acc + img * cells;
+  const int Wc = Wp + 1;
+  double s = 0.0, q = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(p / Wp), c = (int)(p % Wp);
+    const int64_t k = (int64_t)(r + 1) * Wc + (c + 1);
+    const float v = ((A[k].x + A[k - Wc].y) + A[k - 1].z) + A[k - Wc - 1].w;
+    iwe[img * HW + p] = v;
+    if (want_var && (!omit || (r >= 1 && r <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
+      s += (double)v;
+      q += (double)v * (double)v;
+    }
+  }
+  if (want_var) {
+    const int64_t M = omit ? (int64_t)(Hp - 2) * (Wp - 2) : HW;
+    variance_commit(s, q, M, gridDim.x, &sacc[img], stats + 4 * img, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gq
+// Per-corner gradient pictures.  G[p] = a * (src[p] - m) (inside the crop when `crop`, else everywhere), gathered at
+// the four corners of every accumulator cell with the per-corner in-bounds masks.
+__global__ void __launch_bounds__(256) gq_build_kernel(const float* __restrict__ src, const float* __restrict__ affine, int Hp, int Wp,
+                                                       int64_t cells, int crop, float4* __restrict__ gq) {
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)Hp * Wp;
+  const float* I = src + img * HW;
+  const float a = affine[2 * img], m = affine[2 * img + 1];
+  const int Wc = Wp + 1;
+  const int lo = crop ? 1 : 0, hi_r = crop ? Hp - 2 : Hp - 1, hi_c = crop ? Wp - 2 : Wp - 1;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cells; k += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(k / Wc) - 1, c = (int)(k % Wc) - 1;
+    auto g = [&](int rr, int cc) -> float {
+      return (rr >= lo && rr <= hi_r && cc >= lo && cc <= hi_c) ? a * (__ldg(I + (int64_t)rr * Wp + cc) - m) : 0.f;
+    };
+    gq[img * cells + k] = make_float4(g(r, c), g(r + 1, c), g(r, c + 1), g(r + 1, c + 1));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// GVAR 0: scalar red per event.  GVAR 1: events are ordered by source pixel, so equal source pixels are consecutive
+// lanes: segmented warp reduction, one red per run.
+template <int MODEL, int NREF, int GVAR>
+__global__ void __launch_bounds__(256) grad_fused_kernel(FusedArgs a, const float4* __restrict__ gq, float* __restrict__ gmotion) {
+  __shared__ TimeSmem s;
+  __shared__ double red2[2][8];
+  stage_time<NREF, MODEL == CMAX_MOTION_VOXEL>(a.tp, s);
+  const int HW = a.H * a.W;
+  float th0 = 0.f, th1 = 0.f;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    th0 = __ldg(a.motion);
+    th1 = __ldg(a.motion + 1);
+  }
+  double t0 = 0.0, t1 = 0.0;  // 2-dof: per-thread fp64 partial sums
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = (a.n + 31) / 32 * 32;  // whole warps stay in the loop for the shuffles
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += step) {
+    const bool live = i < a.n;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) e = __ldcs(a.ev + i);
+    int src = 0;
+    float f0 = th0, f1 = th1;
+    if (MODEL != CMAX_MOTION_2DOF) src = __float2int_rz(e.x) * a.W + __float2int_rz(e.y);
+    if (MODEL == CMAX_MOTION_DENSE && live) {
+      f0 = __ldg(a.motion + src);
+      f1 = __ldg(a.motion + HW + src);
+    }
+    float g0 = 0.f, g1 = 0.f;  // dense: sum over reference times of -dt * dL/dx'
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      float xw, yw, dt;
+      int bin;
+      warp_ref<MODEL>(e, src, HW, a.motion, s, r, f0, f1, xw, yw, dt, bin);
+      const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+      float dx = 0.f, dy = 0.f;
+      if (live && v.row >= -1 && v.row < a.Hp && v.col >= -1 && v.col < a.Wp) {
+        const float4 g = __ldg(gq + r * a.cells + (int64_t)(v.row + 1) * (a.Wp + 1) + (v.col + 1));
+        // d w / d x' = (-(1-fy), (1-fy), -fy, fy),  d w / d y' = (-(1-fx), -fx, (1-fx), fx)
+        dx = (1.0f - v.fy) * (g.y - g.x) + v.fy * (g.w - g.z);
+        dy = (1.0f - v.fx) * (g.z - g.x) + v.fx * (g.w - g.y);
+      }
+      if (MODEL == CMAX_MOTION_2DOF) {
+        t0 += (double)(dt * dx);
+        t1 += (double)(dt * dy);
+      } else if (MODEL == CMAX_MOTION_DENSE) {
+        g0 -= dt * dx;
+        g1 -= dt * dy;
+      } else if (live && bin >= 0) {
+        float* g = gmotion + (int64_t)bin * 2 * HW;
+        atomicAdd(g + src, -(dt * dx));
+        atomicAdd(g + HW + src, -(dt * dy));
+      }
+    }
+    if (MODEL == CMAX_MOTION_DENSE) {
+      if (GVAR == 0) {
+        if (live) {
+          atomicAdd(gmotion + src, g0);
+          atomicAdd(gmotion + HW + src, g1);
+        }
+      } else {
+        // segmented suffix sum over runs of equal `src` (dead lanes carry src = -1 and zeros)
+        const int key = live ? src : -1;
+        const int lane = threadIdx.x & 31;
+        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (prev != key);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float u0 = __shfl_down_sync(0xffffffffu, g0, o);
+          const float u1 = __shfl_down_sync(0xffffffffu, g1, o);
+          const int uk = __shfl_down_sync(0xffffffffu, key, o);
+          if (lane + o < 32 && uk == key) {
+            g0 += u0;
+            g1 += u1;
+          }
+        }
+        if (head && live) {
+          atomicAdd(gmotion + src, g0);
+          atomicAdd(gmotion + HW + src, g1);
+        }
+      }
+    }
+  }
+  if (MODEL == CMAX_MOTION_2DOF) {
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+      red2[0][wid] = t0;
+      red2[1][wid] = t1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red2[threadIdx.x][w];
+      atomicAdd(reinterpret_cast<double*>(gmotion) + threadIdx.x, tot);  // fp64 staging, narrowed by finish_2dof_kernel
+    }
+  }
+}
+
+// 2-dof gradient: the CTAs accumulate in two doubles (staged in the G2 scratch), narrowed here.
+__global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __restrict__ out) {
+  if (threadIdx.x < 2) out[threadIdx.x] = (float)acc2[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------------ dispatch
+template <int MODEL, int NREF>
+static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
+  if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
+  else vote_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, acc, iwe);
+}
+template <int MODEL>
+static void launch_vote_m(int n_ref, int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
+  switch (n_ref) {
+    case 1: launch_vote<MODEL, 1>(variant, grid, s, a, acc, iwe); break;
+    case 2: launch_vote<MODEL, 2>(variant, grid, s, a, acc, iwe); break;
+    case 3: launch_vote<MODEL, 3>(variant, grid, s, a, acc, iwe); break;
+    default: launch_vote<MODEL, 4>(variant, grid, s, a, acc, iwe); break;
+  }
+}
+template <int MODEL, int NREF>
+static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
+  if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
+  else grad_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, gq, gm);
+}
+template <int MODEL>
+static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
+  switch (n_ref) {
+    case 1: launch_grad<MODEL, 1>(gvar, grid, s, a, gq, gm); break;
+    case 2: launch_grad<MODEL, 2>(gvar, grid, s, a, gq, gm); break;
+    case 3: launch_grad<MODEL, 3>(gvar, grid, s, a, gq, gm); break;
+    default: launch_grad<MODEL, 4>(gvar, grid, s, a, gq, gm); break;
+  }
+}
+
+static inline int event_grid(int64_t n, int per_sm) {
+  const int64_t want = (n + 255) / 256;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * per_sm));
+}
+static inline int image_grid(int64_t n) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 4));
+}
+
+static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
+  FusedArgs a;
+  a.ev = reinterpret_cast<const float4*>(p->events);
+  a.n = p->n;
+  a.H = p->H; a.W = p->W; a.Hp = p->Hp; a.Wp = p->Wp; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
+  a.motion = motion;
+  a.tp = p->d_params;
+  a.cells = (int64_t)(p->Hp + 1) * (p->Wp + 1);
+  return a;
+}
+
+static int check_model(const char* fn, const cmax_plan* p, int model) {
+  CMAX_REQUIRE(p != nullptr, "%s: plan is NULL", fn);
+  CMAX_REQUIRE(model == CMAX_MOTION_DENSE || model == CMAX_MOTION_VOXEL || model == CMAX_MOTION_2DOF,
+               "%s: motion model %d not supported", fn, model);
+  CMAX_REQUIRE(model != CMAX_MOTION_VOXEL || p->n_bins >= 1, "%s: dense-flow-voxel needs cmax_plan_set_refs(..., n_bins >= 1)", fn);
+  return CMAX_OK;
+}
+
+static bool can_fuse_stats(const cmax_cost_spec* spec) {
+  return spec != nullptr && spec->stat == CMAX_STAT_VARIANCE && !(spec->sigma > 0.f);
+}
+
+static int check_spec(const char* fn, const cmax_cost_spec* spec, int n_ref) {
+  CMAX_REQUIRE(spec != nullptr, "%s: spec is NULL", fn);
+  CMAX_REQUIRE(spec->stat == CMAX_STAT_VARIANCE || spec->stat == CMAX_STAT_GRADMAG, "%s: unknown statistic %d", fn, spec->stat);
+  CMAX_REQUIRE(spec->form >= CMAX_COST_PLAIN && spec->form <= CMAX_COST_MULTIFOCAL, "%s: unknown cost form %d", fn, spec->form);
+  CMAX_REQUIRE(spec->direction_sign == 1 || spec->direction_sign == -1, "%s: direction_sign must be +1 or -1", fn);
+  CMAX_REQUIRE(spec->form != CMAX_COST_PLAIN || n_ref == 1, "%s: a plain cost takes exactly one reference time (plan has %d)", fn, n_ref);
+  CMAX_REQUIRE(spec->form != CMAX_COST_NORMALIZED || n_ref == 1, "%s: a normalised cost takes exactly one reference time (plan has %d)", fn, n_ref);
+  CMAX_REQUIRE(!(spec->sigma < 0.f), "%s: sigma must be >= 0", fn);
+  return CMAX_OK;
+}
+
+}  // namespace cmax
+
+using namespace cmax;
+
+extern "C" {
+
+size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_spec* spec) {
+  (void)spec;
+  if (plan == nullptr) {
+    set_error("cmax_objective_workspace_bytes: plan is NULL");
+    return 0;
+  }
+  return obj_layout(plan->Hp, plan->Wp).total;
+}
+
+int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float** iwe_out,
+                        const cmax_cost_spec* fuse_spec, int32_t* stats_fused, cmax_stream_t stream) {
+  int rc = check_model("cmax_objective_vote", plan, motion_model);
+  if (rc) return rc;
+  CMAX_REQUIRE(motion != nullptr && workspace != nullptr, "cmax_objective_vote: NULL motion/workspace");
+  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective_vote: workspace must be 256-byte aligned");
+  const cmax_plan* p = plan;
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+  float4* acc = reinterpret_cast<float4*>(ws + L.off_acc);
+  float* iwe = reinterpret_cast<float*>(ws + L.off_iwe);
+  StatAcc* sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
+  double* stats = reinterpret_cast<double*>(ws + L.off_stats);
+  const int n_ref = p->n_ref;
+  const FusedArgs a = fused_args(p, motion);
+  const int variant = p->vote_variant;
+  const bool fuse = can_fuse_stats(fuse_spec) && variant != 1;
+  const int mask = p->stage_mask;
+  if (mask & 1) {
+    if (variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(iwe, 0, (size_t)n_ref * L.HW * sizeof(float), s));
+    else CMAX_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_ref * L.cells * sizeof(float4), s));
+  }
+  if (p->n > 0 && (mask & 2)) {
+    const int grid = event_grid(p->n, 8);
+    if (motion_model == CMAX_MOTION_DENSE) launch_vote_m<CMAX_MOTION_DENSE>(n_ref, variant, grid, s, a, acc, iwe);
+    else if (motion_model == CMAX_MOTION_VOXEL) launch_vote_m<CMAX_MOTION_VOXEL>(n_ref, variant, grid, s, a, acc, iwe);
+    else launch_vote_m<CMAX_MOTION_2DOF>(n_ref, variant, grid, s, a, acc, iwe);
+  }
+  if (variant != 1 && (mask & 4)) {
+    if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(sacc, 0, (size_t)n_ref * sizeof(StatAcc), s));
+    dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), n_ref);
+    fold_kernel<<<grid, kStatBlock, 0, s>>>(acc, iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0, fuse ? fuse_spec->omit_boundary : 0, sacc, stats);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  if (iwe_out) *iwe_out = iwe;
+  if (stats_fused) *stats_fused = fuse ? 1 : 0;
+  return CMAX_OK;
+}
+
+int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
+                        int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost: NULL argument");
+  const cmax_plan* p = plan;
+  int rc = check_spec("cmax_objective_cost", spec, p->n_ref);
+  if (rc) return rc;
+  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_cost: normalised costs need d_orig_stat");
+  CMAX_REQUIRE(p->Hp >= 3 && p->Wp >= 3, "cmax_objective_cost: images must be at least 3x3");
+  CMAX_REQUIRE(!stats_fused || can_fuse_stats(spec), "cmax_objective_cost: stats_fused set for a spec that cannot fuse");
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+  float* iwe = reinterpret_cast<float*>(ws + L.off_iwe);
+  float* blur = reinterpret_cast<float*>(ws + L.off_blur);
+  double* stats = reinterpret_cast<double*>(ws + L.off_stats);
+  float* affine = reinterpret_cast<float*>(ws + L.off_affine);
+  float* G = reinterpret_cast<float*>(ws + L.off_g);
+  float* G2 = reinterpret_cast<float*>(ws + L.off_g2);
+  float4* gq = reinterpret_cast<float4*>(ws + L.off_gq);
+  const int n_ref = p->n_ref;
+  const bool blurred = spec->sigma > 0.f;
+  const float* img = iwe;
+  if (blurred) {
+    rc = cmax_blur3(iwe, blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
+    if (rc) return rc;
+    img = blur;
+  }
+  // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
+  const bool explicit_grad = want_grad && (blurred || spec->stat == CMAX_STAT_GRADMAG);
+  if (!stats_fused) {
+    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
+    rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, stats, explicit_grad ? G : nullptr,
+                          ws + L.off_statacc, stream);
+    if (rc) return rc;
+  } else if (explicit_grad) {
+    CMAX_REQUIRE(false, "cmax_objective_cost: internal error (fused statistics with explicit gradient)");
+  }
+  rc = cmax_combine_cost(stats, n_ref, spec->stat, spec->form, d_orig_stat, spec->weights, spec->direction_sign, explicit_grad ? 1 : 0,
+                         d_cost, affine, stream);
+  if (rc) return rc;
+  if (want_grad) {
+    const float* gsrc = img;
+    int crop = spec->omit_boundary ? 1 : 0;
+    if (explicit_grad) {
+      gsrc = G;
+      crop = 0;
+      if (blurred) {
+        rc = cmax_blur3(G, G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
+        if (rc) return rc;
+        gsrc = G2;
+      }
+    }
+    dim3 grid((unsigned)image_grid(L.cells), n_ref);
+    gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, affine, p->Hp, p->Wp, L.cells, crop, gq);
+    CMAX_CUDA_CHECK(cudaGetLastError());
+  }
+  return CMAX_OK;
+}
+
+int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float* grad_motion,
+                        cmax_stream_t stream) {
+  int rc = check_model("cmax_objective_grad", plan, motion_model);
+  if (rc) return rc;
+  CMAX_REQUIRE(motion != nullptr && workspace != nullptr && grad_motion != nullptr, "cmax_objective_grad: NULL argument");
+  const cmax_plan* p = plan;
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  cudaStream_t s = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+  const float4* gq = reinterpret_cast<const float4*>(ws + L.off_gq);
+  double* acc2 = reinterpret_cast<double*>(ws + L.off_g2);  // 2-dof fp64 staging
+  const FusedArgs a = fused_args(p, motion);
+  const int HW = p->H * p->W;
+  size_t bytes = 2 * sizeof(float);
+  if (motion_model == CMAX_MOTION_DENSE) bytes = 2 * (size_t)HW * sizeof(float);
+  if (motion_model == CMAX_MOTION_VOXEL) bytes = 2 * (size_t)p->n_bins * HW * sizeof(float);
+  if (p->stage_mask & 1) {
+    CMAX_CUDA_CHECK(cudaMemsetAsync(grad_motion, 0, bytes, s));
+    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s));
+  }
+  if (p->n > 0 && (p->stage_mask & 2)) {
+    const int grid = event_grid(p->n, 8);
+    const int gvar = (p->order == CMAX_ORDER_PIXEL) ? p->grad_variant : 0;
+    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, gq, grad_motion);
+    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, gq, grad_motion);
+    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, gq, reinterpret_cast<float*>(acc2));
+    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(acc2, grad_motion);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
+}
+
+int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
+                   const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion, cmax_stream_t stream) {
+  int32_t fused = 0;
+  int rc = cmax_objective_vote(plan, motion_model, motion, workspace, nullptr, spec, &fused, stream);
+  if (rc) return rc;
+  rc = cmax_objective_cost(plan, spec, d_orig_stat, workspace, fused, grad_motion != nullptr, d_cost, stream);
+  if (rc) return rc;
+  if (grad_motion != nullptr) rc = cmax_objective_grad(plan, motion_model, motion, workspace, grad_motion, stream);
+  return rc;
+}
+
+}  // extern "C"

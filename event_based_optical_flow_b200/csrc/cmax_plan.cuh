@@ -1,0 +1,39 @@
+// Host-side plan handle (opaque to C callers) + tile geometry shared by the fused kernels.
+#pragma once
+#include "cmax_common.cuh"
+
+namespace cmax {
+
+// Source tiles: events are grouped by the 32x32 tile their UN-warped pixel falls in.  A CTA privatises a
+// 64x64 window of the IWE (the tile plus a 16-pixel halo on every side) in shared memory as int32 fixed point.
+constexpr int kTile = 32;
+constexpr int kHalo = 16;
+constexpr int kWin = kTile + 2 * kHalo;  // 64
+constexpr int kChunk = 8192;             // events per CTA work item (bounds the fixed-point range, see cmax_fused.cu)
+
+struct Chunk {
+  int32_t tile;   // tile id (ty * tiles_x + tx)
+  int32_t begin;  // first event (index into the tile-sorted array)
+  int32_t count;  // <= kChunk
+  int32_t pad_;
+};
+
+}  // namespace cmax
+
+struct cmax_plan {
+  const float* events;  // float4 per event; tile-sorted copy (in the workspace) or the caller's array
+  int64_t n;
+  int H, W, pad_h, pad_w, Hp, Wp;
+  float t_min, t_max;
+  int order;         // cmax_order
+  int vote_variant;  // see cmax_plan_set_variant
+  int grad_variant;
+  int stage_mask;       // see cmax_plan_set_stage_mask (7 = everything)
+  int tiles_x, tiles_y, n_tiles;
+  const cmax::Chunk* chunks;  // device
+  int n_chunks;
+  cmax_time_params_t* d_params;  // device
+  float* d_minmax;               // device [2]
+  int32_t* d_status;             // device [1]
+  int n_ref, n_bins;
+};

@@ -1,0 +1,306 @@
+"""Fused contrast-maximization objective: one CM iteration = warp + IWE + cost + gradient on the GPU.
+
+This is the fast path behind the reference's per-iteration seam
+`PatchContrastMaximization.calculate_cost` / `get_arg_for_cost` (src/solver/patch_contrast_base.py:273-352):
+events are made resident once per `optimize()` (`EventPlan`), and every objective evaluation is three C-ABI calls
+(`cmax_objective_vote` -> [all-reduce IWE] -> `cmax_objective_cost` -> `cmax_objective_grad` -> [all-reduce grad])
+with no host synchronisation.  The gradient w.r.t. the motion is analytic; events never
+receive a gradient (the reference only ever asks for d cost / d motion, scipy_autograd/torch_wrapper.py:38-40).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+Direction = Union[str, float]
+
+# cost name -> (statistic, form, (arg-dict key, direction) per fused reference time, multi-focal weights)
+# src/costs/*.py and src/solver/patch_contrast_base.py:303-347: "iwe"/"backward_iwe" warp to the FIRST event,
+# "forward_iwe" to the LAST, "middle_iwe" to the middle; multi-focal = N(fwd) + N(bwd) + 2 N(mid).
+COST_TABLE = {
+    "image_variance": ("variance", "plain", (("iwe", "first"),), (1.0,)),
+    "gradient_magnitude": ("gradmag", "plain", (("iwe", "first"),), (1.0,)),
+    "normalized_image_variance": ("variance", "normalized", (("iwe", "first"),), (1.0,)),
+    "normalized_gradient_magnitude": ("gradmag", "normalized", (("iwe", "first"),), (1.0,)),
+    "multi_focal_normalized_image_variance": (
+        "variance", "multifocal", (("backward_iwe", "first"), ("forward_iwe", "last"), ("middle_iwe", "middle")), (1.0, 1.0, 2.0)),
+    "multi_focal_normalized_gradient_magnitude": (
+        "gradmag", "multifocal", (("backward_iwe", "first"), ("forward_iwe", "last"), ("middle_iwe", "middle")), (1.0, 1.0, 2.0)),
+}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the B200 contrast-maximization path has no CPU fallback")
+
+
+def _pad2(outer_padding) -> Tuple[int, int]:
+    if isinstance(outer_padding, (int, float)):
+        return int(outer_padding), int(outer_padding)
+    return int(outer_padding[0]), int(outer_padding[1])
+
+
+class EventPlan:
+    """Resident, validated (and optionally source-pixel-ordered) float4 copy of one event batch.
+
+    Events are constant during one `solver.optimize()` (src/solver/patch_contrast_pyramid.py:186), so the work the
+    reference redoes on every call -- dtype conversion, `clone`, four min/max reductions over t (src/warp.py:201-259)
+    -- is done once here.  `t_range` must be the GLOBAL (t_min, t_max) when the batch is one shard of a larger one.
+    """
+
+    def __init__(self, events: torch.Tensor, image_size: Tuple[int, int], outer_padding=0, order: str = "pixel",
+                 t_range: Optional[Tuple[float, float]] = None):
+        _require_cuda(events, "events")
+        if events.dim() != 2 or events.shape[1] < 3:
+            raise ValueError(f"events must be [n, >=3] (x=row, y=col, t, p); got {tuple(events.shape)}")
+        if order not in _lib.ORDER:
+            raise ValueError(f"order must be one of {list(_lib.ORDER)}, got {order}")
+        self.lib = _lib.load()
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        self.pad = _pad2(outer_padding)
+        self.padded_size = (self.image_size[0] + 2 * self.pad[0], self.image_size[1] + 2 * self.pad[1])
+        self.device = events.device
+        ev = events.detach()
+        if ev.shape[1] == 3:
+            ev = torch.cat([ev, ev.new_zeros(len(ev), 1)], dim=1)
+        # keep the fp32 [n,4] array alive: an un-sorted plan borrows it
+        self._events_f32 = ev[:, :4].to(torch.float32).contiguous()
+        self.n = int(self._events_f32.shape[0])
+        H, W = self.image_size
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.cmax_plan_workspace_bytes(self.n, H, W, _lib.ORDER[order])
+            if nbytes == 0:
+                _lib.check("cmax_plan_workspace_bytes", _lib.ERR_ARG if self.n >= 0 else _lib.ERR_CUDA)
+            self._workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+            ws_ptr = (self._workspace.data_ptr() + 255) // 256 * 256
+            tmin, tmax = (float("nan"), float("nan")) if t_range is None else (float(t_range[0]), float(t_range[1]))
+            handle = C.c_void_p()
+            _lib.call("cmax_plan_create", C.byref(handle), self._events_f32.data_ptr(), self.n, 4, H, W, self.pad[0], self.pad[1],
+                      tmin, tmax, _lib.ORDER[order], ws_ptr, nbytes, _stream_ptr())
+        self._handle = handle
+        a, b, n, o = C.c_float(), C.c_float(), C.c_int64(), C.c_int32()
+        _lib.call("cmax_plan_info", self._handle, C.byref(a), C.byref(b), C.byref(n), C.byref(o))
+        self.t_min, self.t_max = a.value, b.value
+        self.order = {v: k for k, v in _lib.ORDER.items()}[o.value]
+        self.refs: Tuple[Direction, ...] = ("first",)
+        self.n_bins = 0
+        if self.order != "asis":
+            self._events_f32 = None  # the plan owns a re-ordered copy inside its workspace
+
+    @property
+    def handle(self):
+        if self._handle is None:
+            raise RuntimeError("EventPlan already closed")
+        return self._handle
+
+    def set_refs(self, directions: Sequence[Direction], n_bins: int = 0) -> None:
+        directions = tuple(directions)
+        if (directions, n_bins) == (self.refs, self.n_bins):
+            return
+        arr = _lib.refs_array(directions)
+        with torch.cuda.device(self.device):
+            _lib.call("cmax_plan_set_refs", self.handle, arr, len(directions), int(n_bins), _stream_ptr())
+        self.refs, self.n_bins = directions, int(n_bins)
+
+    def set_variant(self, vote_variant: int = 0, grad_variant: int = 0) -> None:
+        _lib.call("cmax_plan_set_variant", self.handle, int(vote_variant), int(grad_variant))
+
+    def set_stage_mask(self, mask: int = 7) -> None:
+        """Measurement aid, see cmax_plan_set_stage_mask in include/cmax_b200.h."""
+        _lib.call("cmax_plan_set_stage_mask", self.handle, int(mask))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) is not None:
+            self.lib.cmax_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _motion_shape(model: str, image_size, n_bins: int) -> Tuple[int, ...]:
+    H, W = image_size
+    if model == "dense-flow":
+        return (2, H, W)
+    if model == "dense-flow-voxel":
+        return (n_bins, 2, H, W)
+    return (2,)
+
+
+class ContrastObjective:
+    """cost(motion) and d cost / d motion for one resident event batch.
+
+    Args mirror the reference's configuration vocabulary: `motion_model` as in `Warp.warp_event`
+    (src/warp.py:156-199), `cost` a key of `costs.functions` (src/costs/__init__.py:35), `sigma` = `iwe.blur_sigma`,
+    `direction` = the cost direction (src/costs/base.py:20-25), `outer_padding` as in `EventImageConverter`.
+    `process_group`: events are sharded over its ranks; the partial IWE and the partial gradient are summed with one
+    NCCL all-reduce each.
+    """
+
+    def __init__(self, events: Union[torch.Tensor, EventPlan], image_size: Tuple[int, int], *, cost: str = "image_variance",
+                 motion_model: str = "dense-flow", sigma: float = 0.0, omit_boundary: bool = True, direction: str = "minimize",
+                 outer_padding=0, n_bins: Optional[int] = None, order: str = "pixel", process_group=None,
+                 t_range: Optional[Tuple[float, float]] = None, orig_events: Optional[torch.Tensor] = None):
+        if cost not in COST_TABLE:
+            raise KeyError(f"cost {cost!r} has no fused CUDA form; available: {sorted(COST_TABLE)}")
+        if motion_model not in _lib.MOTION:
+            from .warp import MotionModelKeyError
+            raise MotionModelKeyError(motion_model)
+        if direction not in ("minimize", "maximize", "natural"):
+            raise ValueError(f"direction should be minimize, maximize, and natural. Got {direction}.")
+        self.cost = cost
+        self.motion_model = motion_model
+        stat, form, refs, weights = COST_TABLE[cost]
+        self.stat, self.form = stat, form
+        self.ref_keys = tuple(k for k, _ in refs)
+        self.group = process_group
+        if orig_events is None and isinstance(events, torch.Tensor):
+            orig_events = events
+        self.plan = events if isinstance(events, EventPlan) else EventPlan(events, image_size, outer_padding, order, t_range)
+        self.device = self.plan.device
+        self.image_size = self.plan.image_size
+        self.padded_size = self.plan.padded_size
+        self.n_bins = int(n_bins) if motion_model == "dense-flow-voxel" else 0
+        if motion_model == "dense-flow-voxel" and not (1 <= self.n_bins <= _lib.MAX_BINS):
+            raise ValueError(f"dense-flow-voxel needs 1 <= n_bins <= {_lib.MAX_BINS}")
+        self.directions = tuple(d for _, d in refs)
+        self.plan.set_refs(self.directions, self.n_bins)
+        # Sign conventions of src/costs/*.py.  plain: minimize -> -stat, maximize/natural -> +stat.
+        # normalised: minimize -> orig/warped, maximize/natural -> warped/orig.  multi-focal: minimize -> sum of
+        # orig/warped, maximize -> -(sum of warped/orig), natural -> +(sum of warped/orig) (the inner normalised cost
+        # is built with the same direction, multi_focal_normalized_*.py:36-38, :96-101).
+        sign = 1 if direction == "minimize" else -1
+        self._post_sign = -1.0 if (direction == "natural" and form == "multifocal") else 1.0
+        self.spec = _lib.CostSpec(_lib.STAT[stat], _lib.FORM[form], sign, 1 if omit_boundary else 0, float(sigma),
+                                  (C.c_float * _lib.MAX_REFS)(*(list(weights) + [0.0] * (_lib.MAX_REFS - len(weights)))))
+        self.sigma = float(sigma)
+        self.omit_boundary = bool(omit_boundary)
+        self.motion_shape = _motion_shape(motion_model, self.image_size, self.n_bins)
+        self.lib = _lib.load()
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.cmax_objective_workspace_bytes(self.plan.handle, C.byref(self.spec))
+            self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+        self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        self._cost = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._orig_stat = None
+        if form != "plain":
+            self._orig_stat = self._orig_statistic(orig_events)
+        self._iwe_view = None
+
+    # -- the statistic of the un-warped IWE (normalised costs); constant per optimize(), so computed once
+    #    (the reference recomputes it on every call, src/solver/patch_contrast_base.py:295-301)
+    def _orig_statistic(self, orig_events: Optional[torch.Tensor]) -> torch.Tensor:
+        from . import ops
+        Hp, Wp = self.padded_size
+        if orig_events is None:
+            raise ValueError("normalised / multi-focal costs need `orig_events` (the un-warped events of this rank)")
+        img = ops.vote(orig_events.detach().to(torch.float32), self.padded_size, self.plan.pad, None, "bilinear_vote")
+        if self.group is not None:
+            torch.distributed.all_reduce(img, group=self.group)
+        if self.sigma > 0:
+            img = ops.blur3(img[None], self.sigma)[0]
+        # NormalizedImageVariance crops iwe but NOT orig_iwe (src/costs/normalized_image_variance.py:38-41)
+        omit = self.omit_boundary and self.stat == "gradmag"
+        stats, _ = ops.image_stats(img[None], self.stat, omit, want_grad=False)
+        return stats[0, :1].clone()
+
+    # -- one evaluation
+    def _check_motion(self, motion: torch.Tensor) -> torch.Tensor:
+        _require_cuda(motion, "motion")
+        if tuple(motion.shape) != self.motion_shape:
+            raise ValueError(f"motion for {self.motion_model} must have shape {self.motion_shape}, got {tuple(motion.shape)}")
+        return motion.detach().to(torch.float32).contiguous()
+
+    def _vote(self, m: torch.Tensor, stream: int) -> int:
+        iwe_ptr = C.c_void_p()
+        fused = C.c_int32(0)
+        spec = C.byref(self.spec) if self.group is None else None
+        _lib.call("cmax_objective_vote", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr,
+                  C.byref(iwe_ptr), spec, C.byref(fused), stream)
+        if self._iwe_view is None:
+            off = iwe_ptr.value - self._ws.data_ptr()
+            Hp, Wp = self.padded_size
+            k = len(self.directions)
+            self._iwe_view = self._ws[off:off + 4 * k * Hp * Wp].view(torch.float32).view(k, Hp, Wp)
+        if self.group is not None:
+            torch.distributed.all_reduce(self._iwe_view, group=self.group)
+        return fused.value
+
+    def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
+        """-> (cost: 0-dim float64 CUDA tensor, grad: fp32 tensor shaped like motion or None).  No host sync."""
+        m = self._check_motion(motion)
+        with torch.cuda.device(self.device):
+            stream = _stream_ptr()
+            fused = self._vote(m, stream)
+            orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
+            cost = torch.empty(1, dtype=torch.float64, device=self.device)
+            _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, fused, 1 if want_grad else 0,
+                      cost.data_ptr(), stream)
+            grad = None
+            if want_grad:
+                grad = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device)
+                _lib.call("cmax_objective_grad", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr,
+                          grad.data_ptr(), stream)
+                if self.group is not None:
+                    torch.distributed.all_reduce(grad, group=self.group)
+        if self._post_sign < 0:
+            cost = -cost
+            grad = -grad if grad is not None else None
+        return cost[0], grad
+
+    def value(self, motion: torch.Tensor) -> torch.Tensor:
+        return self.value_and_grad(motion, want_grad=False)[0]
+
+    def iwe(self, motion: torch.Tensor) -> torch.Tensor:
+        """The (un-blurred) IWE stack [n_ref, Hp, Wp] for `motion` (a copy)."""
+        m = self._check_motion(motion)
+        with torch.cuda.device(self.device):
+            self._vote(m, _stream_ptr())
+        return self._iwe_view.clone()
+
+    def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
+        """Allocation-free evaluation into caller buffers (CUDA-graph capturable, single GPU only)."""
+        if self.group is not None or self._post_sign < 0:
+            raise RuntimeError("step_into is the single-GPU graph path (minimize / maximize directions)")
+        orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
+        _lib.call("cmax_objective", self.plan.handle, _lib.MOTION[self.motion_model], motion_f32.data_ptr(), C.byref(self.spec), orig,
+                  self._ws_ptr, cost_out.data_ptr(), grad_out.data_ptr(), _stream_ptr())
+
+    def __call__(self, motion: torch.Tensor) -> torch.Tensor:
+        """Autograd-aware scalar in motion's dtype: drop-in for the reference's `calculate_cost` result."""
+        return _ObjectiveFunction.apply(motion, self)
+
+
+class _ObjectiveFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, motion: torch.Tensor, obj: ContrastObjective):
+        need = ctx.needs_input_grad[0]
+        cost, grad = obj.value_and_grad(motion, want_grad=need)
+        ctx.grad = grad
+        ctx.dtype = motion.dtype
+        return cost.to(motion.dtype if motion.dtype.is_floating_point else torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grad is None:
+            return None, None
+        return (ctx.grad.to(ctx.dtype) * g.to(ctx.dtype)), None
+
+
+def cm_objective(events: torch.Tensor, motion: torch.Tensor, image_size: Tuple[int, int], **kw) -> torch.Tensor:
+    """One-shot functional form (builds a plan every call; prefer a cached `ContrastObjective` inside a solver)."""
+    kw.setdefault("orig_events", events)
+    obj = ContrastObjective(events, image_size, **kw)
+    return obj(motion)

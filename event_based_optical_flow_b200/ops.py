@@ -1,0 +1,199 @@
+"""Modular CUDA operators (one C-ABI call each) + their autograd wrappers.
+
+These sit behind the drop-in `Warp` / `EventImageConverter` / cost classes so that the reference's unchanged solver
+code (which composes warp -> IWE -> cost itself, src/solver/patch_contrast_base.py:289-352, and differentiates with
+torch autograd, scipy_autograd/torch_wrapper.py:30-73) runs on the hand-written kernels.  Everything computes in fp32
+on the current CUDA stream; callers convert dtypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("the B200 contrast-maximization operators need CUDA tensors (no CPU fallback)")
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ time
+def time_params(events: torch.Tensor, directions: Sequence, n_bins: int = 0, normalize_t: bool = True) -> torch.Tensor:
+    """Device-resident cmax_time_params_t for these events (min/max of t taken from THIS batch, as the reference
+    does on every warp call, src/warp.py:201-259)."""
+    ev = _f32c(events)
+    with torch.cuda.device(ev.device):
+        mm = torch.empty(2, dtype=torch.float32, device=ev.device)
+        _lib.call("cmax_time_range", ev.data_ptr(), ev.shape[0], ev.shape[1], mm.data_ptr(), _stream())
+        tp = torch.empty(_lib.TIME_PARAMS_BYTES, dtype=torch.uint8, device=ev.device)
+        _lib.call("cmax_time_params", mm.data_ptr(), _lib.refs_array(tuple(directions)), len(directions), int(n_bins),
+                  1 if normalize_t else 0, tp.data_ptr(), _stream())
+    return tp
+
+
+# ------------------------------------------------------------------------------------------------ warp
+def warp_events(events: torch.Tensor, motion: torch.Tensor, motion_model: str, image_size: Tuple[int, int], tp: torch.Tensor,
+                ref_index: int = 0) -> torch.Tensor:
+    """fp32 [n,C] -> fp32 [n,C] = (x', y', dt, p).  Raises IndexError on a source pixel outside the image."""
+    ev, m = _f32c(events), _f32c(motion)
+    H, W = image_size
+    out = torch.empty_like(ev)
+    with torch.cuda.device(ev.device):
+        status = torch.zeros(1, dtype=torch.int32, device=ev.device)
+        _lib.call("cmax_warp_events", ev.data_ptr(), ev.shape[0], ev.shape[1], H, W, _lib.MOTION[motion_model], m.data_ptr(),
+                  tp.data_ptr(), ref_index, out.data_ptr(), status.data_ptr(), _stream())
+    if motion_model in ("dense-flow", "dense-flow-voxel") and int(status.item()) != 0:
+        raise IndexError(f"an event's pixel lies outside the {H}x{W} flow field (the reference's torch.gather raises, src/warp.py:305-307)")
+    return out
+
+
+def warp_events_backward(events: torch.Tensor, motion_model: str, motion_shape, image_size, tp: torch.Tensor, ref_index: int,
+                         grad_out: torch.Tensor) -> torch.Tensor:
+    ev, g = _f32c(events), _f32c(grad_out)
+    H, W = image_size
+    n_bins = motion_shape[0] if motion_model == "dense-flow-voxel" else 0
+    gm = torch.empty(tuple(motion_shape), dtype=torch.float32, device=ev.device)
+    with torch.cuda.device(ev.device):
+        _lib.call("cmax_warp_events_backward", ev.data_ptr(), ev.shape[0], ev.shape[1], H, W, _lib.MOTION[motion_model], n_bins,
+                  tp.data_ptr(), ref_index, g.data_ptr(), gm.data_ptr(), _stream())
+    return gm
+
+
+class WarpFunction(torch.autograd.Function):
+    """Differentiable w.r.t. `motion` only (events never need a gradient: scipy_autograd/torch_wrapper.py:38-40)."""
+
+    @staticmethod
+    def forward(ctx, events, motion, motion_model, image_size, tp, ref_index):
+        out = warp_events(events, motion, motion_model, image_size, tp, ref_index)
+        ctx.save_for_backward(events.detach())
+        ctx.meta = (motion_model, tuple(motion.shape), tuple(image_size), tp, ref_index, motion.dtype)
+        return out.to(events.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (events,) = ctx.saved_tensors
+        motion_model, mshape, image_size, tp, ref_index, mdtype = ctx.meta
+        gm = warp_events_backward(events, motion_model, mshape, image_size, tp, ref_index, grad_out)
+        return None, gm.to(mdtype), None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ vote
+def vote(xy: torch.Tensor, padded_size: Tuple[int, int], pad: Tuple[int, int], weight: Optional[torch.Tensor],
+         method: str = "bilinear_vote") -> torch.Tensor:
+    """[n,>=2] -> fp32 [Hp,Wp].  src/event_image_converter.py:316-374 (bilinear_vote), :209-255 (count)."""
+    if method not in _lib.VOTE:
+        raise NotImplementedError(f"{method = } is not implemented")
+    x = _f32c(xy)
+    Hp, Wp = padded_size
+    img = torch.empty(Hp, Wp, dtype=torch.float32, device=x.device)
+    w = _f32c(weight) if weight is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("cmax_vote", x.data_ptr(), x.shape[0], x.shape[1], w.data_ptr() if w is not None else None, Hp, Wp, pad[0], pad[1],
+                  _lib.VOTE[method], img.data_ptr(), _stream())
+    return img
+
+
+def vote_backward(xy: torch.Tensor, padded_size, pad, weight: Optional[torch.Tensor], grad_image: torch.Tensor,
+                  want_weight_grad: bool = False):
+    x, g = _f32c(xy), _f32c(grad_image)
+    Hp, Wp = padded_size
+    gxy = torch.empty(x.shape[0], 2, dtype=torch.float32, device=x.device)
+    gw = torch.empty(x.shape[0], dtype=torch.float32, device=x.device) if want_weight_grad else None
+    w = _f32c(weight) if weight is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("cmax_vote_backward", x.data_ptr(), x.shape[0], x.shape[1], w.data_ptr() if w is not None else None, Hp, Wp,
+                  pad[0], pad[1], g.data_ptr(), gxy.data_ptr(), gw.data_ptr() if gw is not None else None, _stream())
+    return gxy, gw
+
+
+class VoteFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xy, weight, padded_size, pad, method):
+        img = vote(xy, padded_size, pad, weight, method)
+        ctx.save_for_backward(xy.detach(), weight.detach() if weight is not None else None)
+        ctx.meta = (tuple(padded_size), tuple(pad), method, xy.dtype, xy.shape, weight is not None and ctx.needs_input_grad[1])
+        return img.to(xy.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_image):
+        xy, weight = ctx.saved_tensors
+        padded_size, pad, method, dtype, shape, want_w = ctx.meta
+        if method != "bilinear_vote":  # the count image is piecewise constant in the coordinates
+            return torch.zeros(shape, dtype=dtype, device=xy.device), None, None, None, None
+        gxy, gw = vote_backward(xy, padded_size, pad, weight, grad_image, want_w)
+        full = torch.zeros(shape, dtype=dtype, device=xy.device)
+        full[:, :2] = gxy.to(dtype)
+        return full, (gw.to(weight.dtype) if gw is not None else None), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ blur
+def blur3(images: torch.Tensor, sigma: float, transpose: bool = False) -> torch.Tensor:
+    """[k,Hp,Wp] fp32 -> 3x3 Gaussian, reflect padding (torchvision gaussian_blur(kernel_size=3) at
+    src/event_image_converter.py:153-158); transpose=True applies the adjoint."""
+    x = _f32c(images)
+    k, Hp, Wp = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.call("cmax_blur3", x.data_ptr(), out.data_ptr(), k, Hp, Wp, float(sigma), 1 if transpose else 0, _stream())
+    return out
+
+
+class BlurFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, sigma):
+        ctx.sigma = sigma
+        ctx.dtype = image.dtype
+        return blur3(image[None], sigma)[0].to(image.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return blur3(g[None], ctx.sigma, transpose=True)[0].to(ctx.dtype), None
+
+
+# ------------------------------------------------------------------------------------------------ statistics
+def image_stats(images: torch.Tensor, stat: str, omit_boundary: bool, want_grad: bool = True):
+    """[k,Hp,Wp] -> (stats float64 [k,4] = {value, mean, M, 0}, d value / d image fp32 [k,Hp,Wp] or None).
+    value = unbiased variance of the crop (src/costs/image_variance.py:37-58) or mean (Sobel/8)^2 magnitude
+    (src/costs/gradient_magnitude.py:60-76)."""
+    x = _f32c(images)
+    k, Hp, Wp = x.shape
+    lib = _lib.load()
+    stats = torch.empty(k, 4, dtype=torch.float64, device=x.device)
+    grad = torch.empty_like(x) if want_grad else None
+    with torch.cuda.device(x.device):
+        ws = torch.empty(lib.cmax_stats_workspace_bytes(k, Hp, Wp) + 256, dtype=torch.uint8, device=x.device)
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        _lib.call("cmax_image_stats", x.data_ptr(), k, Hp, Wp, _lib.STAT[stat], 1 if omit_boundary else 0, stats.data_ptr(),
+                  grad.data_ptr() if grad is not None else None, ws_ptr, _stream())
+    return stats, grad
+
+
+class ImageStatFunction(torch.autograd.Function):
+    """0-dim statistic of one image, differentiable through the kernel's closed-form image gradient."""
+
+    @staticmethod
+    def forward(ctx, image, stat, omit_boundary):
+        stats, grad = image_stats(image[None], stat, omit_boundary, want_grad=ctx.needs_input_grad[0])
+        ctx.save_for_backward(grad)
+        ctx.dtype = image.dtype
+        return stats[0, 0].to(image.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None, None
+        return (grad[0] * g.to(torch.float32)).to(ctx.dtype), None, None

@@ -1,0 +1,209 @@
+/*
+ * cmax_b200.h -- C ABI of the B200-native contrast-maximization inner loop.
+ *
+ * The reference (tub-rip/event_based_optical_flow) is pure Python: it has NO FFI for this path.  The seams a
+ * replacement plugs into are the duck-typed Python objects the solver holds (src/solver/base.py:139-147,
+ * :185-204) and the composing method src/solver/patch_contrast_base.py:273-352.  This header is therefore the
+ * boundary the reference's maintainers would bind (ctypes): every entry point names the
+ * reference function (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (fp32 unless stated) unless the name starts with `h_`.
+ *   - An event is 4 consecutive floats (x, y, t, p); x = ROW (height), y = COLUMN (width)
+ *     (src/utils/event_utils.py:38, src/event_image_converter.py:344-345).  `ev_stride` = floats per event (>=3).
+ *   - Flow is [2,H,W] (channel 0 = row component), a flow voxel is [T,2,H,W]; flat pixel = x*W + y (src/warp.py:305).
+ *   - Images are [Hp,Wp] row-major with Hp = H + 2*pad_h, Wp = W + 2*pad_w (src/event_image_converter.py:23-28).
+ *   - Every function returns 0 on success, a cmax_status otherwise, and never throws or exits;
+ *     cmax_last_error() gives the message for the calling thread.
+ *   - Kernels are enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises unless stated.
+ *   - Buffers are BORROWED: the library never frees caller memory and allocates no device memory of its own;
+ *     scratch comes from the caller through the *_workspace_bytes()/workspace arguments.
+ */
+#ifndef CMAX_B200_H
+#define CMAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMAX_ABI_VERSION 1
+#define CMAX_MAX_REFS 4   /* reference times fused into one event pass (first / middle / last / one more) */
+#define CMAX_MAX_BINS 64  /* time bins of a flow voxel */
+
+typedef void* cmax_stream_t;
+
+typedef enum {
+  CMAX_OK = 0,
+  CMAX_ERR_ARG = 1,        /* bad argument (null pointer, size, enum) -> Python ValueError */
+  CMAX_ERR_CUDA = 2,       /* a CUDA runtime call failed; message holds cudaGetErrorString */
+  CMAX_ERR_SOURCE_OOB = 3, /* an event's un-warped pixel lies outside [0,H)x[0,W): the reference's torch.gather raises (src/warp.py:305-307) */
+  CMAX_ERR_WORKSPACE = 4   /* caller workspace too small */
+} cmax_status;
+
+typedef enum {
+  CMAX_MOTION_DENSE = 0, /* "dense-flow"        src/warp.py:263-313 */
+  CMAX_MOTION_VOXEL = 1, /* "dense-flow-voxel"  src/warp.py:315-365 */
+  CMAX_MOTION_2DOF = 2   /* "2d-translation" / "rigid-optical-flow"  src/warp.py:483-522 */
+} cmax_motion;
+
+typedef enum {
+  CMAX_VOTE_BILINEAR = 0, /* src/event_image_converter.py:316-374 */
+  CMAX_VOTE_COUNT = 1     /* src/event_image_converter.py:209-255 */
+} cmax_vote_method;
+
+typedef enum {
+  CMAX_STAT_VARIANCE = 0, /* unbiased variance          src/costs/image_variance.py:47-58 */
+  CMAX_STAT_GRADMAG = 1   /* mean (Sobel/8)^2 magnitude  src/costs/gradient_magnitude.py:60-76 */
+} cmax_stat;
+
+typedef enum {
+  CMAX_COST_PLAIN = 0,      /* -stat(iwe)                               image_variance.py:56-58, gradient_magnitude.py:73-76 */
+  CMAX_COST_NORMALIZED = 1, /* stat(orig)/stat(iwe)                     normalized_*.py:59-64 / 74-79 */
+  CMAX_COST_MULTIFOCAL = 2  /* sum_r w_r stat(orig)/stat(iwe_r)         multi_focal_normalized_*.py:73-101 */
+} cmax_cost_form;
+
+/* A reference time: ref = t_min + fraction*(t_max - t_min) in fp32; mode 0 = "first" (ref = t_min exactly),
+ * 1 = "last" (ref = t_max exactly), 2 = fraction ("middle" = 0.5, "before" = -1, "after" = 2).  src/warp.py:201-233 */
+typedef struct {
+  int32_t mode;
+  float fraction;
+} cmax_ref;
+
+/* Device-resident time parameters for up to CMAX_MAX_REFS reference times (written by cmax_time_params). */
+typedef struct {
+  float ref[CMAX_MAX_REFS];    /* reference time                               src/warp.py:217-224 */
+  float period[CMAX_MAX_REFS]; /* max(dt) - min(dt) of the batch, fp32          src/warp.py:256-257 */
+  float dt_min[CMAX_MAX_REFS]; /* normalised dt of the earliest event                                   */
+  float dt_max[CMAX_MAX_REFS];
+  float edges[CMAX_MAX_REFS][CMAX_MAX_BINS + 1]; /* fp32-rounded float64 bin edges, last = dt_max+1000  src/warp.py:342-345 */
+  int32_t n_ref;
+  int32_t n_bins;
+  int32_t normalize_t;
+  int32_t pad_;
+} cmax_time_params_t;
+
+typedef struct cmax_plan cmax_plan_t; /* host-side handle; see cmax_plan_create */
+
+/* ------------------------------------------------------------------ library */
+int cmax_abi_version(void);
+const char* cmax_last_error(void);
+/* Name of the first CUDA kernel image compiled into the library ("sm_100a"); lets a loader assert the build arch. */
+const char* cmax_build_arch(void);
+
+/* ------------------------------------------------------------------ time  (src/warp.py:201-259, 342-345) */
+/* min/max of column 2 of `events` into d_minmax[0..1].  Replaces the 4 full reductions per warp call. */
+int cmax_time_range(const float* events, int64_t n, int ev_stride, float* d_minmax, cmax_stream_t stream);
+/* (t_min,t_max) on device -> cmax_time_params_t on device, bit-exact with the reference's fp32/fp64 host arithmetic. */
+int cmax_time_params(const float* d_minmax, const cmax_ref* h_refs, int n_ref, int n_bins, int normalize_t,
+                     cmax_time_params_t* d_params, cmax_stream_t stream);
+
+/* ------------------------------------------------------------------ modular operators */
+/* Warp.warp_event (src/warp.py:156-199): out[n,ev_stride] = (x', y', dt, p) for reference time `ref_index`.
+ * motion: [2,H,W] | [n_bins,2,H,W] | [2].  d_status (int32, device, may be NULL) is set non-zero on a source pixel
+ * outside the image (such events are passed through un-warped). */
+int cmax_warp_events(const float* events, int64_t n, int ev_stride, int H, int W, int motion_model,
+                     const float* motion, const cmax_time_params_t* d_params, int ref_index, float* out,
+                     int32_t* d_status, cmax_stream_t stream);
+/* Adjoint of cmax_warp_events w.r.t. motion: grad_out[n,ev_stride] (columns 0,1 used) -> grad_motion (same shape as
+ * motion, ZEROED BY THE CALLEE, accumulated with atomics; n_bins = voxel depth, ignored for the other models).
+ * (autograd of src/warp.py:306-307 / 352-357 / 507-508) */
+int cmax_warp_events_backward(const float* events, int64_t n, int ev_stride, int H, int W, int motion_model,
+                              int n_bins, const cmax_time_params_t* d_params, int ref_index, const float* grad_out,
+                              float* grad_motion, cmax_stream_t stream);
+/* EventImageConverter.bilinear_vote_tensor / count_event_tensor (src/event_image_converter.py:316-374, 209-255).
+ * xy: [n,xy_stride] (columns 0,1 used); weight: [n] or NULL (=1); image [Hp,Wp] is ZEROED BY THE CALLEE. */
+int cmax_vote(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h, int pad_w,
+              int vote, float* image, cmax_stream_t stream);
+/* Adjoint of the bilinear vote: grad_image [Hp,Wp] -> grad_xy [n,2] (and grad_weight [n] if non-NULL). */
+int cmax_vote_backward(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h,
+                       int pad_w, const float* grad_image, float* grad_xy, float* grad_weight, cmax_stream_t stream);
+/* 3x3 Gaussian, reflect padding (torchvision gaussian_blur(kernel_size=3) at src/event_image_converter.py:153-158)
+ * and its transpose.  n_img images of [Hp,Wp]; in != out. */
+int cmax_blur3(const float* in, float* out, int n_img, int Hp, int Wp, float sigma, int transpose, cmax_stream_t stream);
+/* Contrast statistics of n_img images: d_stats[i*4 + {0,1,2,3}] (float64, device) = {value, mean, M, unused}.
+ * value = unbiased variance of the crop (VARIANCE) or mean (gx^2+gy^2) (GRADMAG); if grad != NULL also writes
+ * d value / d image [n_img,Hp,Wp].  omit_boundary crops [1:-1,1:-1] (src/costs/image_variance.py:37-38,
+ * src/costs/gradient_magnitude.py:67-72).  workspace: cmax_stats_workspace_bytes(n_img,Hp,Wp) bytes. */
+size_t cmax_stats_workspace_bytes(int n_img, int Hp, int Wp);
+int cmax_image_stats(const float* images, int n_img, int Hp, int Wp, int stat, int omit_boundary, double* d_stats,
+                     float* grad, void* workspace, cmax_stream_t stream);
+
+/* ------------------------------------------------------------------ fused hot path */
+/* Event order inside a plan.  The order never changes results beyond fp32 summation order; it changes locality. */
+typedef enum {
+  CMAX_ORDER_ASIS = 0,  /* borrow the caller's float4 array (time order)                                       */
+  CMAX_ORDER_TILE = 1,  /* stable sort by 32x32 source tile: flow / gradient accesses of a CTA stay in one tile */
+  CMAX_ORDER_PIXEL = 2  /* stable sort by source pixel (tile-major): runs of events share one flow vector       */
+} cmax_order;
+
+/* Resident, pre-processed event batch (events are constant over one solver.optimize()).  Validates source pixels,
+ * takes (t_min,t_max) (pass NaN to compute from this batch; multi-GPU callers pass the GLOBAL range), and -- for
+ * order != ASIS -- stably re-orders the events into the workspace as float4.  Synchronises `stream` once.
+ * `events` must stay alive and unchanged while the plan is used when order == CMAX_ORDER_ASIS. */
+size_t cmax_plan_workspace_bytes(int64_t n, int H, int W, int order);
+int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_stride, int H, int W, int pad_h,
+                     int pad_w, float t_min, float t_max, int order, void* workspace, size_t workspace_bytes,
+                     cmax_stream_t stream);
+void cmax_plan_destroy(cmax_plan_t* plan);
+/* (t_min, t_max, n, order) the plan uses. */
+int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_t* h_n, int32_t* h_order);
+/* Select reference times / voxel bins for subsequent calls (enqueues one tiny kernel). */
+int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream);
+/* Kernel variant knobs for experiments (profiles/): vote_variant 0 = one red.v4 per event into per-corner
+ * accumulators (default), 1 = four scalar red.f32 into the image, 2 = shared-memory privatised int32 fixed-point
+ * window per source tile (needs CMAX_ORDER_TILE/PIXEL); grad_variant 0 = scalar red per event, 1 = warp-segmented
+ * reduction over runs of equal source pixel. */
+int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant);
+/* Measurement aid (bench.py roofline): which launches the three stages enqueue.  Bit 0 = the memsets, bit 1 = the
+ * event kernels (K1 in cmax_objective_vote, K3 in cmax_objective_grad), bit 2 = the image-sized kernels (fold, blur,
+ * statistics, gradient pictures).  Default 7 = everything; any other value produces timing-only (not meaningful)
+ * results, e.g. 2 lets a CUDA-event pair bracket exactly one K1 or K3 launch. */
+int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask);
+
+/* What one CM evaluation computes: cost = form(stat(blur(iwe_r)))   src/costs/*.py, src/solver/patch_contrast_base.py:289-352 */
+typedef struct {
+  int32_t stat;           /* cmax_stat */
+  int32_t form;           /* cmax_cost_form */
+  int32_t direction_sign; /* +1 minimize, -1 maximize                     src/costs/base.py:20-25 */
+  int32_t omit_boundary;  /* crop [1:-1,1:-1]                              src/solver/patch_contrast_base.py:290 */
+  float sigma;            /* 3x3 Gaussian blur of every IWE, 0 = none      src/event_image_converter.py:153-158 */
+  float weights[CMAX_MAX_REFS]; /* multi-focal weights per reference time  multi_focal_normalized_*.py */
+} cmax_cost_spec;
+
+/* Scratch one evaluation needs (per-corner accumulators, IWEs, gradient pictures, statistics). */
+size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_spec* spec);
+/* Stage 1 (K1 + fold): warp by `motion` and bilinear-vote into n_ref images; returns in *iwe_out a pointer INTO the
+ * workspace to [n_ref,Hp,Wp] fp32 (multi-GPU callers all-reduce it in place before stage 2).
+ * (src/warp.py:301-313|339-365|506-520 -> src/event_image_converter.py:316-374, composed as in
+ * src/solver/patch_contrast_base.py:308-347).  fuse_spec != NULL lets the fold also accumulate the variance sums
+ * when the spec allows it (VARIANCE, sigma == 0; single-GPU only); *stats_fused (may be NULL) reports whether it did. */
+int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace,
+                        float** iwe_out, const cmax_cost_spec* fuse_spec, int32_t* stats_fused, cmax_stream_t stream);
+/* Stage 2 (K2): blur, statistics, scalar cost into d_cost[0] (float64, device) and -- when want_grad -- the
+ * per-corner dL/dIWE pictures stage 3 gathers from.  d_orig_stat: device float64 statistic of the un-warped IWE
+ * (normalised / multi-focal forms), else NULL.  stats_fused must repeat what stage 1 reported. */
+int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
+                        int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream);
+/* Stage 3 (K3): re-warp, gather dL/dIWE at the 4 corners, chain to dL/dmotion (same shape as motion, ZEROED BY THE
+ * CALLEE; multi-GPU callers all-reduce it afterwards).  (autograd of stage 1) */
+int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace,
+                        float* grad_motion, cmax_stream_t stream);
+/* Single-GPU convenience: stages 1-3 back to back (one CM iteration = warp + IWE + cost + gradient). */
+int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
+                   const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion /* NULL = value only */,
+                   cmax_stream_t stream);
+/* Scalar combination of per-image statistics (exposed for the modular cost plugins).
+ * d_stats: n_ref x 4 doubles from cmax_image_stats; h_weights: n_ref multi-focal weights (NULL = 1).
+ * explicit_grad != 0: the affine pair is (d cost/d stat_r, 0); otherwise (VARIANCE) it is
+ * (d cost/d stat_r * 2/(M-1), mean_r).  Writes d_cost[0] (float64) and d_affine[2*n_ref] (fp32). */
+int cmax_combine_cost(const double* d_stats, int n_ref, int stat, int cost_form, const double* d_orig_stat,
+                      const float* h_weights, int direction_sign, int explicit_grad, double* d_cost, float* d_affine,
+                      cmax_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMAX_B200_H */

@@ -1,0 +1,176 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol include/*.h declares; host-side
+logic of the drop-in classes (registries, error conventions, shard arithmetic); and the multi-GPU composition
+(contiguous shards + GLOBAL time range + sum all-reduce) on a world_size-2 gloo group, with the oracle standing in
+for the kernels (it is the checker here, never the product path)."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from event_based_optical_flow_b200 import _build, _lib
+    path = _build.build_library()
+    assert os.path.exists(path)
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "cmax_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(cmax_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(path)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/cmax_b200.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.cmax_abi_version() == 1
+    assert lib.cmax_build_arch() == b"sm_100a"
+
+
+def test_library_is_sm100a_only():
+    import shutil
+    import subprocess
+    from event_based_optical_flow_b200 import _build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _build.build_library()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_argument_errors_need_no_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    from event_based_optical_flow_b200 import _lib
+    lib = _lib.load()
+    assert lib.cmax_time_range(None, 10, 2, None, None) == _lib.ERR_ARG
+    assert b"d_minmax" in lib.cmax_last_error()
+    assert lib.cmax_vote(None, 5, 4, None, 8, 8, 0, 0, 7, None, None) == _lib.ERR_ARG
+    assert lib.cmax_blur3(None, None, 1, 8, 8, 1.0, 0, None) == _lib.ERR_ARG
+    assert lib.cmax_objective_workspace_bytes(None, None) == 0
+    with pytest.raises(ValueError):
+        _lib.check("cmax_vote", _lib.ERR_ARG)
+    with pytest.raises(IndexError):
+        _lib.check("cmax_plan_create", _lib.ERR_SOURCE_OOB)
+    with pytest.raises(ValueError):
+        _lib.refs_array(("sideways",))
+    with pytest.raises(ValueError):
+        _lib.refs_array(())
+
+
+def test_no_cpu_fallback():
+    import event_based_optical_flow_b200 as B
+    ev = torch.zeros(4, 4)
+    with pytest.raises(RuntimeError):
+        B.ContrastObjective(ev, (8, 8))
+    with pytest.raises(RuntimeError):
+        B.Warp((8, 8)).warp_event(ev, torch.zeros(2, 8, 8), "dense-flow")
+    with pytest.raises(RuntimeError):
+        B.EventImageConverter((8, 8)).create_iwe(ev)
+    with pytest.raises(RuntimeError):
+        B.cost_functions["image_variance"]().calculate({"iwe": torch.zeros(8, 8), "omit_boundary": True})
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "event_based_optical_flow_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "cm_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_cost_registry_and_host_logic():
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.costs import HybridCost
+    assert set(B.cost_functions) == {"image_variance", "gradient_magnitude", "normalized_image_variance",
+                                     "normalized_gradient_magnitude", "multi_focal_normalized_image_variance",
+                                     "multi_focal_normalized_gradient_magnitude", "total_variation"}
+    assert set(B.COST_TABLE) == set(B.cost_functions) - {"total_variation"}
+    with pytest.raises(ValueError):
+        B.cost_functions["gradient_magnitude"](direction="up")
+    h = HybridCost("minimize", {"multi_focal_normalized_gradient_magnitude": 1.0, "total_variation": 0.01}, store_history=True)
+    assert set(h.required_keys) == {"forward_iwe", "backward_iwe", "middle_iwe", "omit_boundary", "orig_iwe", "flow"}
+    assert set(h.get_history()) == {"loss", "multi_focal_normalized_gradient_magnitude", "total_variation"}
+    w = B.Warp((4, 6), normalize_t=True)
+    assert w.get_key_names("2d-translation") == ["trans_x", "trans_y"]
+    assert w.get_motion_vector_size("rigid-optical-flow") == 2
+    with pytest.raises(B.MotionModelKeyError):
+        w.get_key_names("affine")
+    flow = w.get_flow_from_motion(np.array([1.5, -2.0]), "2d-translation")
+    assert flow.shape == (2, 4, 6) and np.all(flow[0] == -1.5) and np.all(flow[1] == 2.0)
+    im = B.EventImageConverter((4, 6), outer_padding=2)
+    assert im.image_size == (8, 10) and im.outer_padding == (2, 2)
+    # total variation stays in torch (tiny patch grid): check against the oracle-free closed form on a ramp
+    tv = B.cost_functions["total_variation"]()
+    ramp = torch.arange(5.0)[None, :, None].expand(2, 5, 5).contiguous()
+    assert abs(float(tv.calculate({"flow": ramp, "omit_boundary": True})) - 0.5) < 1e-6  # d/dx = 1 on 2 of 4 channels
+
+
+def test_shard_bounds_partition():
+    from event_based_optical_flow_b200.distributed import shard_bounds
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, world, r) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [e - b for b, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from event_based_optical_flow_b200.distributed import global_time_range, shard_events
+        from oracle import cm_oracle as O
+        rng = np.random.default_rng(5)
+        H, W, n = 24, 32, 4001
+        ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
+        ev = torch.from_numpy(ev.astype(np.float32))
+        flow = torch.from_numpy(rng.uniform(-4, 4, (2, H, W)).astype(np.float32))
+        mine = shard_events(ev, world, rank)
+        tmin, tmax = global_time_range(mine)
+        assert tmin == float(ev[:, 2].min()) and tmax == float(ev[:, 2].max())
+        # partial IWE of this shard with the GLOBAL reference time / period, then the sum all-reduce
+        t = mine[:, 2]
+        dt = (t - tmin) / torch.tensor(tmax - tmin, dtype=torch.float32)
+        src = mine[:, 0].long() * W + mine[:, 1].long()
+        warped = mine.clone()
+        warped[:, 0] = mine[:, 0] - dt * flow[0].reshape(-1)[src]
+        warped[:, 1] = mine[:, 1] - dt * flow[1].reshape(-1)[src]
+        part = O.bilinear_vote(warped, (H, W))
+        dist.all_reduce(part)
+        full = O.bilinear_vote(O.warp_dense(ev, flow, "first"), (H, W))
+        torch.testing.assert_close(part, full, rtol=1e-5, atol=1e-5)
+        # every rank computes the identical cost from the identical reduced image
+        cost = -O.image_variance(part)
+        gathered = [torch.zeros_like(cost) for _ in range(world)]
+        dist.all_gather(gathered, cost)
+        assert all(torch.equal(gathered[0], c) for c in gathered)
+        out[rank] = float(cost)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_composition_gloo_world2():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_gloo_worker, args=(world, port, out), nprocs=world, join=True)
+        assert len(out) == world and out[0] == out[1]
