@@ -144,13 +144,13 @@ def test_fused_objective_vs_reference_golden(B, dev, golden_random, case, sigma,
             assert _rel(grad.cpu().numpy(), ref_g) <= 5e-5, (model, cn, _rel(grad.cpu().numpy(), ref_g))
             assert grad.shape == motions[model].shape
             # value-only evaluation and the autograd wrapper agree with value_and_grad
-            assert float(obj.value(motions[model].to(dev))) == float(val)
+            assert abs(float(obj.value(motions[model].to(dev))) - float(val)) <= 1e-6 * abs(float(val))  # atomics: order varies
             m = motions[model].to(dev).double().requires_grad_(True)
             loss = obj(m)
             assert loss.dtype == torch.float64
             (g2,) = torch.autograd.grad(loss * 2.0, m)
-            np.testing.assert_allclose(g2.cpu().numpy(), 2.0 * grad.double().cpu().numpy(), rtol=1e-6, atol=1e-30)
-            del ref_v64
+            assert _rel(g2.cpu().numpy(), 2.0 * grad.double().cpu().numpy()) <= 1e-5
+            assert abs(float(val) - ref_v64) <= 2e-5 * abs(ref_v64)
 
 
 @pytest.mark.parametrize("pad", (0, 3))
@@ -248,7 +248,7 @@ def test_full_size_properties(B, dev):
     # (5) linearity of the gradient in dL/dIWE: variance cost 'maximize' is exactly the negated 'minimize'
     obj_max = B.ContrastObjective(evd, (H, W), cost="image_variance", motion_model="dense-flow", direction="maximize")
     v_max, g_max = obj_max.value_and_grad(flowd)
-    assert float(v_max) == -float(v_pix)
+    assert abs(float(v_max) + float(v_pix)) <= 1e-6 * abs(float(v_pix))
     assert _rel(g_max.cpu().numpy(), -g_pix.cpu().numpy()) <= 1e-6
 
 
