@@ -337,7 +337,9 @@ def run_b200(args) -> None:
                    "sample": f"5 timed + 1 warm-up CM iterations over the full {n}-event config-2 batch, fp32 torch CPU ops"}
 
         clocks = sampler.finish() if sampler else None
-        per_step_kernels = 5  # K1 vote, fold(+variance), combine, gq_build, K3 grad  (+ 2 memset nodes, not counted)
+        # default variants under the graph: K1 vote, fold(+variance+cost), K3 grad (+ 3 memset nodes, not counted);
+        # eager 3-stage path adds the combine kernel; variants 0/1 add gq_build
+        per_step_kernels = 3 + (0 if graph is not None else 1) + (1 if args.grad_variant != 2 else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -366,8 +368,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--order", choices=("asis", "tile", "pixel"), default="pixel")
-    ap.add_argument("--vote-variant", type=int, default=0)
-    ap.add_argument("--grad-variant", type=int, default=1)
+    ap.add_argument("--vote-variant", type=int, default=2)
+    ap.add_argument("--grad-variant", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
     args = ap.parse_args()

@@ -48,16 +48,34 @@ struct Vote {
   float fx, fy;    // fractions measured from the floor: fx along rows, fy along columns; may be in [-1e-6, 1)
 };
 
+// Exact floor of v as float AND int without the quarter-rate conversion pipe (FRND / F2I): adding 1.5*2^23 rounds v to
+// the nearest integer in the mantissa; one compare-and-decrement turns round-to-nearest into floor.  Valid for
+// |v| < 2^22; anything beyond (or NaN) is reported as not representable -- such coordinates are far outside any image.
+__device__ __forceinline__ bool floor_exact(float v, float& fl, int& i) {
+  const float C = 12582912.0f;  // 1.5 * 2^23
+  const float t = __fadd_rn(v, C);
+  i = __float_as_int(t) - 0x4B400000;
+  fl = __fsub_rn(t, C);
+  if (fl > v) {
+    fl = __fsub_rn(fl, 1.0f);
+    i -= 1;
+  }
+  return fabsf(v) < 4194304.0f;
+}
+
+constexpr int kFarOutside = -0x40000000;  // row/col of an event that can touch no pixel
+
 // i = floor(x' + 1e-6), f = x' - i          src/event_image_converter.py:340-345
 __device__ __forceinline__ Vote vote_geometry(float xw, float yw, int pad_h, int pad_w) {
-  const float flx = floorf(__fadd_rn(xw, 1e-6f));
-  const float fly = floorf(__fadd_rn(yw, 1e-6f));
+  float flx, fly;
+  int ix, iy;
+  const bool okx = floor_exact(__fadd_rn(xw, 1e-6f), flx, ix);
+  const bool oky = floor_exact(__fadd_rn(yw, 1e-6f), fly, iy);
   Vote v;
   v.fx = __fsub_rn(xw, flx);
   v.fy = __fsub_rn(yw, fly);
-  // float -> int conversion saturates, so wildly warped events land outside every mask instead of wrapping
-  v.row = __float2int_rz(flx) + pad_h;
-  v.col = __float2int_rz(fly) + pad_w;
+  v.row = (okx && oky) ? ix + pad_h : kFarOutside;
+  v.col = (okx && oky) ? iy + pad_w : kFarOutside;
   return v;
 }
 

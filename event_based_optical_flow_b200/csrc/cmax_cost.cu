@@ -110,45 +110,12 @@ __global__ void __launch_bounds__(256) gradmag_grad_kernel(const float* __restri
 }
 
 // ---- scalar combination                              src/costs/*.py (see cmax_b200.h cmax_cost_form)
-struct CombineArgs {
-  int n_ref, stat, form, sign, explicit_grad, has_orig;
-  float w[CMAX_MAX_REFS];
-};
-
-__global__ void combine_cost_kernel(const double* __restrict__ stats, const double* __restrict__ orig, CombineArgs a,
-                                    double* __restrict__ cost, float* __restrict__ affine) {
+__global__ void combine_cost_kernel(const double* __restrict__ stats, CombineDev cd) {
   if (threadIdx.x != 0) return;
-  double total = 0.0;
-  for (int r = 0; r < a.n_ref; ++r) {
-    const double c = stats[4 * r + 0], mean = stats[4 * r + 1], M = stats[4 * r + 2];
-    double alpha;  // d total / d c_r
-    if (a.form == CMAX_COST_PLAIN) {
-      total += -(double)a.sign * c;
-      alpha = -(double)a.sign;
-    } else {
-      const double co = orig[0];
-      const double w = (a.form == CMAX_COST_MULTIFOCAL) ? (double)a.w[r] : 1.0;
-      if (a.sign > 0) {  // minimize / natural: orig / warped
-        total += w * co / c;
-        alpha = -w * co / (c * c);
-      } else if (a.form == CMAX_COST_NORMALIZED) {  // maximize: warped / orig
-        total += c / co;
-        alpha = 1.0 / co;
-      } else {  // multi-focal "maximize" negates the sum of (warped / orig)
-        total += -w * c / co;
-        alpha = -w / co;
-      }
-    }
-    if (a.stat == CMAX_STAT_VARIANCE && !a.explicit_grad) {
-      affine[2 * r + 0] = (float)(alpha * 2.0 / (M - 1.0));
-      affine[2 * r + 1] = (float)mean;
-    } else {
-      affine[2 * r + 0] = (float)alpha;
-      affine[2 * r + 1] = 0.f;
-    }
-  }
-  cost[0] = total;
+  combine_eval(stats, cd);
 }
+
+void launch_combine(const double* stats, const CombineDev& cd, cudaStream_t s) { combine_cost_kernel<<<1, 32, 0, s>>>(stats, cd); }
 
 static inline int stat_grid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + kStatBlock - 1) / kStatBlock, kNumSMs * 2));
@@ -198,11 +165,8 @@ int cmax_combine_cost(const double* d_stats, int n_ref, int stat, int cost_form,
   CMAX_REQUIRE(cost_form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_combine_cost: normalised costs need the un-warped statistic");
   CMAX_REQUIRE(cost_form != CMAX_COST_PLAIN || n_ref == 1, "cmax_combine_cost: a plain cost takes exactly one image");
   CMAX_REQUIRE(direction_sign == 1 || direction_sign == -1, "cmax_combine_cost: direction_sign must be +1 (minimize) or -1 (maximize)");
-  CombineArgs a;
-  a.n_ref = n_ref; a.stat = stat; a.form = cost_form; a.sign = direction_sign; a.explicit_grad = explicit_grad ? 1 : 0;
-  a.has_orig = d_orig_stat != nullptr;
-  for (int r = 0; r < CMAX_MAX_REFS; ++r) a.w[r] = (h_weights && r < n_ref) ? h_weights[r] : 1.0f;
-  combine_cost_kernel<<<1, 32, 0, as_stream(stream)>>>(d_stats, d_orig_stat, a, d_cost, d_affine);
+  CombineDev cd = make_combine(n_ref, stat, cost_form, direction_sign, explicit_grad, h_weights, d_orig_stat, d_cost, d_affine);
+  launch_combine(d_stats, cd, as_stream(stream));
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
 }

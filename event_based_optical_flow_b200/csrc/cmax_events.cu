@@ -144,6 +144,20 @@ __global__ void __launch_bounds__(256) gather_events_kernel(const float* __restr
   }
 }
 
+// (x, y, t, p) -> (x, y, tz, bits(src)); see cmax_plan.  dt exactly as the kernels compute it (src/warp.py:254-258).
+__global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ ev, int64_t n, int H, int W,
+                                                     const cmax_time_params_t* __restrict__ tp, int with_dt, float4* __restrict__ out) {
+  const float ref = tp->ref[0], period = tp->period[0];
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const float4 e = ev[i];
+    int r, c;
+    source_pixel(e.x, e.y, H, W, &r, &c);
+    const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
+    out[i] = make_float4(e.x, e.y, tz, __int_as_float(r * W + c));
+  }
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int bits_for(uint64_t v) {
@@ -153,6 +167,7 @@ static int bits_for(uint64_t v) {
 }
 
 struct PlanLayout {
+  size_t off_packed;
   size_t off_params, off_minmax, off_status, off_events, off_keys[2], off_idx[2], off_counts, off_chunks, off_temp, temp_bytes, total;
   int tiles_x, tiles_y, n_tiles, max_chunks, key_bits;
 };
@@ -168,6 +183,7 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
   L.off_params = off; off = align_up(off + sizeof(cmax_time_params_t), 256);
   L.off_minmax = off; off = align_up(off + 2 * sizeof(float), 256);
   L.off_status = off; off = align_up(off + sizeof(int32_t), 256);
+  L.off_packed = off; off = align_up(off + (size_t)std::max<int64_t>(n, 1) * sizeof(float4), 256);
   if (order != CMAX_ORDER_ASIS) {
     L.key_bits = bits_for((uint64_t)L.n_tiles * (order == CMAX_ORDER_PIXEL ? kTile * kTile : 1));
     L.max_chunks = (int)(n / kChunk) + L.n_tiles + 1;
@@ -275,8 +291,11 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   p->d_minmax = reinterpret_cast<float*>(ws + L.off_minmax);
   p->d_status = reinterpret_cast<int32_t*>(ws + L.off_status);
   p->events = events;
+  p->packed = reinterpret_cast<float4*>(ws + L.off_packed);
   p->order = CMAX_ORDER_ASIS;
   p->stage_mask = 7;
+  p->vote_variant = 2;
+  p->grad_variant = 2;
 
   int rc = CMAX_OK;
   std::vector<uint32_t> h_counts;
@@ -381,8 +400,7 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
   CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 2, "cmax_plan_set_variant: vote_variant must be 0, 1 or 2");
-  CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 1, "cmax_plan_set_variant: grad_variant must be 0 or 1");
-  CMAX_REQUIRE(vote_variant != 2 || plan->order != CMAX_ORDER_ASIS, "cmax_plan_set_variant: the privatised vote needs tile- or pixel-ordered events");
+  CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 2, "cmax_plan_set_variant: grad_variant must be 0, 1 or 2");
   plan->vote_variant = vote_variant;
   plan->grad_variant = grad_variant;
   return CMAX_OK;
@@ -398,11 +416,17 @@ int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask) {
 int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_refs: plan is NULL");
   const int rc = cmax_time_params(plan->d_minmax, h_refs, n_ref, n_bins, 1, plan->d_params, stream);
-  if (rc == CMAX_OK) {
-    plan->n_ref = n_ref;
-    plan->n_bins = n_bins;
+  if (rc != CMAX_OK) return rc;
+  plan->n_ref = n_ref;
+  plan->n_bins = n_bins;
+  plan->packed_has_dt = (n_ref == 1) ? 1 : 0;
+  if (plan->n > 0) {
+    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (plan->n + 255) / 256);
+    repack_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, plan->H, plan->W,
+                                                        plan->d_params, plan->packed_has_dt, plan->packed);
+    CMAX_CUDA_CHECK(cudaGetLastError());
   }
-  return rc;
+  return CMAX_OK;
 }
 
 }  // extern "C"

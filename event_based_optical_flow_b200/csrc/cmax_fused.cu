@@ -19,7 +19,7 @@ namespace cmax {
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct ObjLayout {
-  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_gxy, off_g, off_g2, off_gq, total;
+  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_gdesc, off_gxy, off_g, off_g2, off_gq, total;
   int64_t cells, HW;
 };
 
@@ -36,6 +36,7 @@ static ObjLayout obj_layout(int Hp, int Wp) {
   L.off_blur = off;    off = align256(off + (size_t)R * L.HW * sizeof(float));
   L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
   L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
+  L.off_gdesc = off;   off = align256(off + 64 + 2 * sizeof(double));  // GradDesc, then the 2-dof fp64 staging at +64
   // [StatAcc block][Sobel pair] is exactly the workspace layout cmax_image_stats expects (cmax_cost.cu)
   L.off_statacc = off; off = align256(off + (size_t)R * sizeof(StatAcc));
   L.off_gxy = off;     off = align256(off + (size_t)R * 2 * L.HW * sizeof(float));
@@ -49,6 +50,7 @@ static ObjLayout obj_layout(int Hp, int Wp) {
 // ------------------------------------------------------------------------------------------------ per-event math
 struct FusedArgs {
   const float4* ev;
+  const float4* packed;  // the plan's (x, y, dt|t, src) copy, read by the run kernels
   int64_t n;
   int H, W, Hp, Wp, pad_h, pad_w;
   const float* motion;
@@ -160,11 +162,14 @@ __global__ void __launch_bounds__(256) vote_fused_kernel(FusedArgs a, float4* __
 }
 
 // ------------------------------------------------------------------------------------------------ fold
-// acc -> IWE; optionally the variance sums of the crop in the same pass (fp64 accumulators).
+// acc -> IWE; optionally the variance sums of the crop in the same pass (fp64 accumulators); optionally (single-GPU
+// fused path) the last CTA to finish also evaluates the scalar cost, so fold + statistics + combine are ONE launch.
 __global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restrict__ acc, float* __restrict__ iwe, int Hp, int Wp,
                                                           int64_t cells, int want_var, int omit, StatAcc* __restrict__ sacc,
-                                                          double* __restrict__ stats) {
+                                                          double* __restrict__ stats, int want_combine, CombineDev cd,
+                                                          unsigned int* __restrict__ ctas_done) {
   __shared__ double red[kStatBlock / 32];
+  __shared__ bool all_done;
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
   const float4* A = acc + img * cells;
@@ -183,6 +188,17 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restri
   if (want_var) {
     const int64_t M = omit ? (int64_t)(Hp - 2) * (Wp - 2) : HW;
     variance_commit(s, q, M, gridDim.x, &sacc[img], stats + 4 * img, red);
+    if (want_combine) {
+      if (threadIdx.x == 0) {
+        __threadfence();
+        all_done = (atomicAdd(ctas_done, 1u) == gridDim.x * gridDim.y - 1);
+      }
+      __syncthreads();
+      if (all_done && threadIdx.x == 0) {
+        __threadfence();
+        combine_eval(stats, cd);
+      }
+    }
   }
 }
 
@@ -306,15 +322,304 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(FusedArgs a, const floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------ run kernels
+// Events of a plan ordered by source pixel arrive as runs: ~N/HW consecutive events share the source pixel (hence
+// the flow vector) and, being time ordered inside the run, walk monotonically along one line of the image.  Each
+// THREAD therefore takes kRunE consecutive events and keeps the current accumulator cell in registers:
+//   K1: weights of consecutive events that fall into the same cell are summed in registers, one red.v4 per cell change
+//   K3: the four corner gradients are re-gathered only on a cell change, and the flow-gradient of a source pixel is
+//       summed in registers, one pair of reds per source-pixel change
+// which divides the number of atomics and gathers by the run length without any shuffles.  The events come from the
+// plan's packed copy (x, y, dt|t, src): everything that is constant over the CM iterations -- the source pixel index,
+// and for a single reference time the normalised dt including its IEEE division -- is precomputed once per plan.
+// They are staged through shared memory (coalesced 16-byte loads, kRunE independent loads in flight per thread; padded
+// so that both the staging stores and the per-thread reads are bank-conflict free).  Correct for ANY event order --
+// an unordered stream just degenerates to one flush per event.
+constexpr int kRunE = 8;         // consecutive events per thread
+constexpr int kRunThreads = 128;
+constexpr int kRunTile = kRunE * kRunThreads;             // events per CTA iteration
+constexpr int kRunSmem = kRunTile + kRunTile / 8;         // float4 slots incl. one pad slot per 8 events
+
+__device__ __forceinline__ void stage_events(const float4* __restrict__ ev, int64_t base, int64_t n, float4* sm) {
+#pragma unroll
+  for (int k = 0; k < kRunE; ++k) {
+    const int j = k * kRunThreads + threadIdx.x;
+    const int64_t idx = base + j;
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < n) e = __ldcs(ev + idx);
+    sm[j + (j >> 3)] = e;
+  }
+}
+
+// Per-reference-time scalars kept in registers (dense / 2-dof); the voxel model also needs the bin edges (shared).
+template <int NREF>
+struct RefRegs {
+  float ref[NREF], period[NREF];
+};
+
+template <int NREF>
+__device__ __forceinline__ RefRegs<NREF> load_refs(const cmax_time_params_t* __restrict__ tp) {
+  RefRegs<NREF> rr;
+#pragma unroll
+  for (int r = 0; r < NREF; ++r) {
+    rr.ref[r] = __ldg(&tp->ref[r]);
+    rr.period[r] = __ldg(&tp->period[r]);
+  }
+  return rr;
+}
+
+// One packed event, one reference time -> (x', y', dt, bin).  PRE_DT: e.z already is the normalised dt of reference 0.
+template <int MODEL, int NREF, bool PRE_DT>
+__device__ __forceinline__ void warp_packed(const float4 e, int src, int HW, const float* __restrict__ motion, const RefRegs<NREF>& rr,
+                                            const TimeSmem& s, int r, float f0, float f1, float& xw, float& yw, float& dt, int& bin) {
+  dt = PRE_DT ? e.z : __fdiv_rn(__fsub_rn(e.z, rr.ref[r]), rr.period[r]);
+  bin = 0;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    xw = warp_plus(e.x, dt, f0);
+    yw = warp_plus(e.y, dt, f1);
+  } else if (MODEL == CMAX_MOTION_DENSE) {
+    xw = warp_minus(e.x, dt, f0);
+    yw = warp_minus(e.y, dt, f1);
+  } else {
+    bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
+    xw = e.x;
+    yw = e.y;
+    if (bin >= 0) {
+      const float* f = motion + (int64_t)bin * 2 * HW;
+      xw = warp_minus(e.x, dt, __ldg(f + src));
+      yw = warp_minus(e.y, dt, __ldg(f + HW + src));
+    }
+  }
+}
+
+// accumulator cell of a vote, or -1 when the event touches no pixel
+__device__ __forceinline__ int vote_cell(const Vote& v, int Hp, int Wp) {
+  const bool inside = (unsigned)(v.row + 1) <= (unsigned)Hp && (unsigned)(v.col + 1) <= (unsigned)Wp;
+  return inside ? (v.row + 1) * (Wp + 1) + (v.col + 1) : -1;
+}
+
+template <int MODEL, int NREF, bool PRE_DT>
+__global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, float4* __restrict__ acc) {
+  __shared__ TimeSmem s;
+  __shared__ float4 sm[kRunSmem];
+  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
+  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
+  const int HW = a.H * a.W;
+  float th0 = 0.f, th1 = 0.f;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    th0 = __ldg(a.motion);
+    th1 = __ldg(a.motion + 1);
+  }
+  const int64_t n_tiles = (a.n + kRunTile - 1) / kRunTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kRunTile;
+    __syncthreads();  // the previous tile has been consumed
+    stage_events(a.ev, base, a.n, sm);
+    __syncthreads();
+    const int64_t left = a.n - (base + (int64_t)threadIdx.x * kRunE);
+    const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
+    int cell[NREF];
+    float w0[NREF], w1[NREF], w2[NREF], w3[NREF];
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      cell[r] = -1;
+      w0[r] = w1[r] = w2[r] = w3[r] = 0.f;
+    }
+    int src_prev = -1;
+    float f0 = th0, f1 = th1;
+    const float4* mine = sm + threadIdx.x * (kRunE + 1);
+#pragma unroll 4
+    for (int k = 0; k < count; ++k) {
+      const float4 e = mine[k];
+      const int src = __float_as_int(e.w);
+      if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
+        f0 = __ldg(a.motion + src);
+        f1 = __ldg(a.motion + HW + src);
+        src_prev = src;
+      }
+#pragma unroll
+      for (int r = 0; r < NREF; ++r) {
+        float xw, yw, dt;
+        int bin;
+        warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, f0, f1, xw, yw, dt, bin);
+        const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+        float w[4];
+        vote_weights(v, w);
+        const int c = vote_cell(v, a.Hp, a.Wp);
+        if (c != cell[r]) {
+          if (cell[r] >= 0) red_add_v4(acc + r * a.cells + cell[r], w0[r], w1[r], w2[r], w3[r]);
+          cell[r] = c;
+          w0[r] = w[0]; w1[r] = w[1]; w2[r] = w[2]; w3[r] = w[3];
+        } else {
+          w0[r] += w[0]; w1[r] += w[1]; w2[r] += w[2]; w3[r] += w[3];
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NREF; ++r)
+      if (cell[r] >= 0) red_add_v4(acc + r * a.cells + cell[r], w0[r], w1[r], w2[r], w3[r]);
+  }
+}
+
+// What K3 needs to evaluate dL/dIWE at a pixel: value = a * (img[p] - m) inside [lo, hi_r] x [lo, hi_c], else 0.
+struct GradSrcs {
+  const float* img[4];  // indexed by GradDesc::kind
+  const float* affine;
+  const GradDesc* gdesc;
+};
+
+template <int MODEL, int NREF, bool PRE_DT>
+__global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, GradSrcs gs, float* __restrict__ gmotion) {
+  __shared__ TimeSmem s;
+  __shared__ float4 sm[kRunSmem];
+  __shared__ double red2[2][kRunThreads / 32];
+  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
+  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
+  const int HW = a.H * a.W;
+  const int64_t HWp = (int64_t)a.Hp * a.Wp;
+  const GradDesc gd = *gs.gdesc;
+  const float* __restrict__ G = gd.kind == 0 ? gs.img[0] : (gd.kind == 1 ? gs.img[1] : (gd.kind == 2 ? gs.img[2] : gs.img[3]));
+  // corner (rr, cc) contributes iff lo <= rr <= hi_r and lo <= cc <= hi_c  <=>  (unsigned)(rr - lo) <= span_r ...
+  const int lo = gd.crop ? 1 : 0;
+  const unsigned span_r = (unsigned)((gd.crop ? a.Hp - 2 : a.Hp - 1) - lo), span_c = (unsigned)((gd.crop ? a.Wp - 2 : a.Wp - 1) - lo);
+  float ga[NREF], gm[NREF];
+#pragma unroll
+  for (int r = 0; r < NREF; ++r) {
+    ga[r] = __ldg(gs.affine + 2 * r);
+    gm[r] = __ldg(gs.affine + 2 * r + 1);
+  }
+  float th0 = 0.f, th1 = 0.f;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    th0 = __ldg(a.motion);
+    th1 = __ldg(a.motion + 1);
+  }
+  double t0 = 0.0, t1 = 0.0;  // 2-dof
+  constexpr int NACC = (MODEL == CMAX_MOTION_VOXEL) ? NREF : 1;
+  const int64_t n_tiles = (a.n + kRunTile - 1) / kRunTile;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * kRunTile;
+    __syncthreads();
+    stage_events(a.ev, base, a.n, sm);
+    __syncthreads();
+    const int64_t left = a.n - (base + (int64_t)threadIdx.x * kRunE);
+    const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
+    int cell[NREF];
+    float d_r[NREF], d_c0[NREF], d_c1[NREF], d_x0[NREF], d_x1[NREF];  // corner differences, see below
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      cell[r] = -2;
+      d_r[r] = d_c0[r] = d_c1[r] = d_x0[r] = d_x1[r] = 0.f;
+    }
+    int key[NACC];   // flat index into gmotion of the row-component slot being accumulated
+    float g0[NACC], g1[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+      key[q] = -1;
+      g0[q] = g1[q] = 0.f;
+    }
+    int src_prev = -1;
+    float f0 = th0, f1 = th1;
+    const float4* mine = sm + threadIdx.x * (kRunE + 1);
+#pragma unroll 4
+    for (int k = 0; k < count; ++k) {
+      const float4 e = mine[k];
+      const int src = __float_as_int(e.w);
+      if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
+        f0 = __ldg(a.motion + src);
+        f1 = __ldg(a.motion + HW + src);
+        src_prev = src;
+      }
+#pragma unroll
+      for (int r = 0; r < NREF; ++r) {
+        float xw, yw, dt;
+        int bin;
+        warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, f0, f1, xw, yw, dt, bin);
+        const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+        const int c = vote_cell(v, a.Hp, a.Wp);
+        if (c != cell[r]) {
+          cell[r] = c;
+          float c00 = 0.f, c10 = 0.f, c01 = 0.f, c11 = 0.f;
+          if (c >= 0) {
+            const float* __restrict__ I = G + r * HWp;
+            const bool r0 = (unsigned)(v.row - lo) <= span_r, r1 = (unsigned)(v.row + 1 - lo) <= span_r;
+            const bool q0 = (unsigned)(v.col - lo) <= span_c, q1 = (unsigned)(v.col + 1 - lo) <= span_c;
+            const int64_t p = (int64_t)v.row * a.Wp + v.col;
+            if (r0 && q0) c00 = ga[r] * (__ldg(I + p) - gm[r]);
+            if (r1 && q0) c10 = ga[r] * (__ldg(I + p + a.Wp) - gm[r]);
+            if (r0 && q1) c01 = ga[r] * (__ldg(I + p + 1) - gm[r]);
+            if (r1 && q1) c11 = ga[r] * (__ldg(I + p + a.Wp + 1) - gm[r]);
+          }
+          // dL/dx' = (1-fy)(c10-c00) + fy(c11-c01) = d_x0 + fy * d_r ;  dL/dy' = (1-fx)(c01-c00) + fx(c11-c10) = d_c0 + fx * d_r
+          d_x0[r] = c10 - c00;
+          d_c0[r] = c01 - c00;
+          d_r[r] = (c11 - c01) - d_x0[r];
+        }
+        const float dx = d_x0[r] + v.fy * d_r[r];
+        const float dy = d_c0[r] + v.fx * d_r[r];
+        if (MODEL == CMAX_MOTION_2DOF) {
+          t0 += (double)(dt * dx);
+          t1 += (double)(dt * dy);
+        } else {
+          const int q = (MODEL == CMAX_MOTION_VOXEL) ? r : 0;
+          const int kk = (MODEL == CMAX_MOTION_VOXEL) ? (bin >= 0 ? bin * 2 * HW + src : -1) : src;
+          if (kk != key[q]) {
+            if (key[q] >= 0) {
+              atomicAdd(gmotion + key[q], g0[q]);
+              atomicAdd(gmotion + key[q] + HW, g1[q]);
+            }
+            key[q] = kk;
+            g0[q] = g1[q] = 0.f;
+          }
+          g0[q] -= dt * dx;
+          g1[q] -= dt * dy;
+        }
+      }
+    }
+    if (MODEL != CMAX_MOTION_2DOF) {
+#pragma unroll
+      for (int q = 0; q < NACC; ++q)
+        if (key[q] >= 0) {
+          atomicAdd(gmotion + key[q], g0[q]);
+          atomicAdd(gmotion + key[q] + HW, g1[q]);
+        }
+    }
+  }
+  if (MODEL == CMAX_MOTION_2DOF) {
+    t0 = warp_sum(t0);
+    t1 = warp_sum(t1);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) {
+      red2[0][wid] = t0;
+      red2[1][wid] = t1;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double tot = 0.0;
+      for (int w = 0; w < kRunThreads / 32; ++w) tot += red2[threadIdx.x][w];
+      atomicAdd(reinterpret_cast<double*>(gmotion) + threadIdx.x, tot);  // fp64 staging, narrowed by finish_2dof_kernel
+    }
+  }
+}
+
 // 2-dof gradient: the CTAs accumulate in two doubles (staged in the G2 scratch), narrowed here.
 __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __restrict__ out) {
   if (threadIdx.x < 2) out[threadIdx.x] = (float)acc2[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+static inline int run_grid(int64_t n) {
+  const int64_t tiles = (n + kRunTile - 1) / kRunTile;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)kNumSMs * 8));
+}
+
 template <int MODEL, int NREF>
 static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
-  if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
+  if (variant == 2) {
+    FusedArgs b = a;
+    b.ev = a.packed;
+    vote_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(b, acc);
+  }
+  else if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
   else vote_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, acc, iwe);
 }
 template <int MODEL>
@@ -327,17 +632,22 @@ static void launch_vote_m(int n_ref, int variant, int grid, cudaStream_t s, cons
   }
 }
 template <int MODEL, int NREF>
-static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
-  if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
+static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, const GradSrcs& gs, float* gm) {
+  if (gvar == 2) {
+    FusedArgs b = a;
+    b.ev = a.packed;
+    grad_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(b, gs, gm);
+  }
+  else if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
   else grad_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, gq, gm);
 }
 template <int MODEL>
-static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
+static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, const GradSrcs& gs, float* gm) {
   switch (n_ref) {
-    case 1: launch_grad<MODEL, 1>(gvar, grid, s, a, gq, gm); break;
-    case 2: launch_grad<MODEL, 2>(gvar, grid, s, a, gq, gm); break;
-    case 3: launch_grad<MODEL, 3>(gvar, grid, s, a, gq, gm); break;
-    default: launch_grad<MODEL, 4>(gvar, grid, s, a, gq, gm); break;
+    case 1: launch_grad<MODEL, 1>(gvar, grid, s, a, gq, gs, gm); break;
+    case 2: launch_grad<MODEL, 2>(gvar, grid, s, a, gq, gs, gm); break;
+    case 3: launch_grad<MODEL, 3>(gvar, grid, s, a, gq, gs, gm); break;
+    default: launch_grad<MODEL, 4>(gvar, grid, s, a, gq, gs, gm); break;
   }
 }
 
@@ -352,6 +662,7 @@ static inline int image_grid(int64_t n) {
 static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   FusedArgs a;
   a.ev = reinterpret_cast<const float4*>(p->events);
+  a.packed = p->packed;
   a.n = p->n;
   a.H = p->H; a.W = p->W; a.Hp = p->Hp; a.Wp = p->Wp; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.motion = motion;
@@ -383,6 +694,86 @@ static int check_spec(const char* fn, const cmax_cost_spec* spec, int n_ref) {
   return CMAX_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ stages
+struct Ws {
+  float4* acc; float* iwe; float* blur; StatAcc* sacc; double* stats; float* affine; GradDesc* gdesc; unsigned int* ctas_done;
+  float* G; float* G2; float4* gq; char* stats_ws; double* acc2;
+};
+
+static Ws carve(void* workspace, const ObjLayout& L) {
+  char* ws = static_cast<char*>(workspace);
+  Ws w;
+  w.acc = reinterpret_cast<float4*>(ws + L.off_acc);
+  w.iwe = reinterpret_cast<float*>(ws + L.off_iwe);
+  w.blur = reinterpret_cast<float*>(ws + L.off_blur);
+  w.sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
+  w.stats = reinterpret_cast<double*>(ws + L.off_stats);
+  w.affine = reinterpret_cast<float*>(ws + L.off_affine);
+  w.gdesc = reinterpret_cast<GradDesc*>(ws + L.off_gdesc);
+  w.ctas_done = reinterpret_cast<unsigned int*>(ws + L.off_statacc + 192);  // inside the 256-byte StatAcc block: one memset clears both
+  w.G = reinterpret_cast<float*>(ws + L.off_g);
+  w.G2 = reinterpret_cast<float*>(ws + L.off_g2);
+  w.gq = reinterpret_cast<float4*>(ws + L.off_gq);
+  w.stats_ws = ws + L.off_statacc;  // [StatAcc block][Sobel pair], the layout cmax_image_stats expects
+  w.acc2 = reinterpret_cast<double*>(ws + L.off_gdesc + 64);  // 2-dof fp64 staging
+  return w;
+}
+
+// Where dL/dIWE comes from for this spec (see GradDesc).
+static GradDesc grad_desc(const cmax_cost_spec* spec) {
+  const bool blurred = spec->sigma > 0.f;
+  const bool explicit_grad = blurred || spec->stat == CMAX_STAT_GRADMAG;
+  GradDesc g;
+  g.kind = explicit_grad ? (blurred ? 3 : 2) : 0;
+  g.crop = explicit_grad ? 0 : (spec->omit_boundary ? 1 : 0);
+  return g;
+}
+
+// Stage 1.  `fused_combine` (may be NULL): when the statistics can be fused into the fold, also evaluate the scalar
+// cost in the fold's last CTA (single-GPU convenience path).
+static int vote_stage(const cmax_plan* p, int motion_model, const float* motion, void* workspace, const cmax_cost_spec* fuse_spec,
+                      const CombineDev* fused_combine, int32_t* stats_fused, cudaStream_t s) {
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
+  const int n_ref = p->n_ref;
+  const FusedArgs a = fused_args(p, motion);
+  const int variant = p->vote_variant;
+  const bool fuse = can_fuse_stats(fuse_spec) && variant != 1;
+  const int mask = p->stage_mask;
+  if (mask & 1) {
+    if (variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(w.iwe, 0, (size_t)n_ref * L.HW * sizeof(float), s));
+    else CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, (size_t)n_ref * L.cells * sizeof(float4), s));
+  }
+  if (p->n > 0 && (mask & 2)) {
+    const int grid = event_grid(p->n, 8);
+    if (motion_model == CMAX_MOTION_DENSE) launch_vote_m<CMAX_MOTION_DENSE>(n_ref, variant, grid, s, a, w.acc, w.iwe);
+    else if (motion_model == CMAX_MOTION_VOXEL) launch_vote_m<CMAX_MOTION_VOXEL>(n_ref, variant, grid, s, a, w.acc, w.iwe);
+    else launch_vote_m<CMAX_MOTION_2DOF>(n_ref, variant, grid, s, a, w.acc, w.iwe);
+  }
+  if (variant != 1 && (mask & 4)) {
+    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 192, "StatAcc block and the CTA counter share 256 bytes");
+    if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
+    dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), n_ref);
+    CombineDev cd;
+    memset(&cd, 0, sizeof(cd));
+    if (fuse && fused_combine) cd = *fused_combine;
+    fold_kernel<<<grid, kStatBlock, 0, s>>>(w.acc, w.iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0, fuse ? fuse_spec->omit_boundary : 0,
+                                            w.sacc, w.stats, (fuse && fused_combine) ? 1 : 0, cd, w.ctas_done);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  if (stats_fused) *stats_fused = fuse ? 1 : 0;
+  return CMAX_OK;
+}
+
+static CombineDev combine_for(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, double* d_cost, const Ws& w) {
+  const GradDesc g = grad_desc(spec);
+  CombineDev cd = make_combine(p->n_ref, spec->stat, spec->form, spec->direction_sign, g.kind >= 2 ? 1 : 0, spec->weights, d_orig_stat,
+                               d_cost, w.affine);
+  cd.gdesc = w.gdesc;
+  cd.g = g;
+  return cd;
+}
+
 }  // namespace cmax
 
 using namespace cmax;
@@ -404,97 +795,69 @@ int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* 
   if (rc) return rc;
   CMAX_REQUIRE(motion != nullptr && workspace != nullptr, "cmax_objective_vote: NULL motion/workspace");
   CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective_vote: workspace must be 256-byte aligned");
-  const cmax_plan* p = plan;
+  rc = vote_stage(plan, motion_model, motion, workspace, fuse_spec, nullptr, stats_fused, as_stream(stream));
+  if (rc) return rc;
+  if (iwe_out) *iwe_out = carve(workspace, obj_layout(plan->Hp, plan->Wp)).iwe;
+  return CMAX_OK;
+}
+
+// combined != 0: the scalar combination already ran inside the fold (cmax_objective's fast path)
+static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int stats_fused,
+                      int combined, int want_grad, double* d_cost, cmax_stream_t stream) {
   const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
   cudaStream_t s = as_stream(stream);
-  char* ws = static_cast<char*>(workspace);
-  float4* acc = reinterpret_cast<float4*>(ws + L.off_acc);
-  float* iwe = reinterpret_cast<float*>(ws + L.off_iwe);
-  StatAcc* sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
-  double* stats = reinterpret_cast<double*>(ws + L.off_stats);
   const int n_ref = p->n_ref;
-  const FusedArgs a = fused_args(p, motion);
-  const int variant = p->vote_variant;
-  const bool fuse = can_fuse_stats(fuse_spec) && variant != 1;
-  const int mask = p->stage_mask;
-  if (mask & 1) {
-    if (variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(iwe, 0, (size_t)n_ref * L.HW * sizeof(float), s));
-    else CMAX_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_ref * L.cells * sizeof(float4), s));
+  const bool blurred = spec->sigma > 0.f;
+  const float* img = w.iwe;
+  int rc;
+  if (p->stage_mask & 4) {
+    if (blurred) {
+      rc = cmax_blur3(w.iwe, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
+      if (rc) return rc;
+      img = w.blur;
+    }
+    // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
+    const GradDesc g = grad_desc(spec);
+    const bool explicit_grad = want_grad && g.kind >= 2;
+    if (!stats_fused) {
+      static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
+      rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, w.stats, explicit_grad ? w.G : nullptr,
+                            w.stats_ws, stream);
+      if (rc) return rc;
+    }
+    if (!combined) launch_combine(w.stats, combine_for(p, spec, d_orig_stat, d_cost, w), s);
+    if (want_grad) {
+      const float* gsrc = img;
+      int crop = spec->omit_boundary ? 1 : 0;
+      if (g.kind >= 2) {
+        gsrc = w.G;
+        crop = 0;
+        if (blurred) {
+          rc = cmax_blur3(w.G, w.G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
+          if (rc) return rc;
+          gsrc = w.G2;
+        }
+      }
+      if (p->grad_variant != 2) {  // the run kernel gathers from the image itself (GradDesc); the others need the pictures
+        dim3 grid((unsigned)image_grid(L.cells), n_ref);
+        gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, w.affine, p->Hp, p->Wp, L.cells, crop, w.gq);
+      }
+    }
+    CMAX_CUDA_CHECK(cudaGetLastError());
   }
-  if (p->n > 0 && (mask & 2)) {
-    const int grid = event_grid(p->n, 8);
-    if (motion_model == CMAX_MOTION_DENSE) launch_vote_m<CMAX_MOTION_DENSE>(n_ref, variant, grid, s, a, acc, iwe);
-    else if (motion_model == CMAX_MOTION_VOXEL) launch_vote_m<CMAX_MOTION_VOXEL>(n_ref, variant, grid, s, a, acc, iwe);
-    else launch_vote_m<CMAX_MOTION_2DOF>(n_ref, variant, grid, s, a, acc, iwe);
-  }
-  if (variant != 1 && (mask & 4)) {
-    if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(sacc, 0, (size_t)n_ref * sizeof(StatAcc), s));
-    dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), n_ref);
-    fold_kernel<<<grid, kStatBlock, 0, s>>>(acc, iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0, fuse ? fuse_spec->omit_boundary : 0, sacc, stats);
-  }
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  if (iwe_out) *iwe_out = iwe;
-  if (stats_fused) *stats_fused = fuse ? 1 : 0;
   return CMAX_OK;
 }
 
 int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
                         int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream) {
   CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost: NULL argument");
-  const cmax_plan* p = plan;
-  int rc = check_spec("cmax_objective_cost", spec, p->n_ref);
+  int rc = check_spec("cmax_objective_cost", spec, plan->n_ref);
   if (rc) return rc;
   CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_cost: normalised costs need d_orig_stat");
-  CMAX_REQUIRE(p->Hp >= 3 && p->Wp >= 3, "cmax_objective_cost: images must be at least 3x3");
+  CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective_cost: images must be at least 3x3");
   CMAX_REQUIRE(!stats_fused || can_fuse_stats(spec), "cmax_objective_cost: stats_fused set for a spec that cannot fuse");
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  cudaStream_t s = as_stream(stream);
-  char* ws = static_cast<char*>(workspace);
-  float* iwe = reinterpret_cast<float*>(ws + L.off_iwe);
-  float* blur = reinterpret_cast<float*>(ws + L.off_blur);
-  double* stats = reinterpret_cast<double*>(ws + L.off_stats);
-  float* affine = reinterpret_cast<float*>(ws + L.off_affine);
-  float* G = reinterpret_cast<float*>(ws + L.off_g);
-  float* G2 = reinterpret_cast<float*>(ws + L.off_g2);
-  float4* gq = reinterpret_cast<float4*>(ws + L.off_gq);
-  const int n_ref = p->n_ref;
-  const bool blurred = spec->sigma > 0.f;
-  const float* img = iwe;
-  if (blurred) {
-    rc = cmax_blur3(iwe, blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
-    if (rc) return rc;
-    img = blur;
-  }
-  // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
-  const bool explicit_grad = want_grad && (blurred || spec->stat == CMAX_STAT_GRADMAG);
-  if (!stats_fused) {
-    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
-    rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, stats, explicit_grad ? G : nullptr,
-                          ws + L.off_statacc, stream);
-    if (rc) return rc;
-  } else if (explicit_grad) {
-    CMAX_REQUIRE(false, "cmax_objective_cost: internal error (fused statistics with explicit gradient)");
-  }
-  rc = cmax_combine_cost(stats, n_ref, spec->stat, spec->form, d_orig_stat, spec->weights, spec->direction_sign, explicit_grad ? 1 : 0,
-                         d_cost, affine, stream);
-  if (rc) return rc;
-  if (want_grad) {
-    const float* gsrc = img;
-    int crop = spec->omit_boundary ? 1 : 0;
-    if (explicit_grad) {
-      gsrc = G;
-      crop = 0;
-      if (blurred) {
-        rc = cmax_blur3(G, G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
-        if (rc) return rc;
-        gsrc = G2;
-      }
-    }
-    dim3 grid((unsigned)image_grid(L.cells), n_ref);
-    gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, affine, p->Hp, p->Wp, L.cells, crop, gq);
-    CMAX_CUDA_CHECK(cudaGetLastError());
-  }
-  return CMAX_OK;
+  return cost_stage(plan, spec, d_orig_stat, workspace, stats_fused, 0, want_grad, d_cost, stream);
 }
 
 int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float* grad_motion,
@@ -504,10 +867,8 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
   CMAX_REQUIRE(motion != nullptr && workspace != nullptr && grad_motion != nullptr, "cmax_objective_grad: NULL argument");
   const cmax_plan* p = plan;
   const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
   cudaStream_t s = as_stream(stream);
-  char* ws = static_cast<char*>(workspace);
-  const float4* gq = reinterpret_cast<const float4*>(ws + L.off_gq);
-  double* acc2 = reinterpret_cast<double*>(ws + L.off_g2);  // 2-dof fp64 staging
   const FusedArgs a = fused_args(p, motion);
   const int HW = p->H * p->W;
   size_t bytes = 2 * sizeof(float);
@@ -515,15 +876,21 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
   if (motion_model == CMAX_MOTION_VOXEL) bytes = 2 * (size_t)p->n_bins * HW * sizeof(float);
   if (p->stage_mask & 1) {
     CMAX_CUDA_CHECK(cudaMemsetAsync(grad_motion, 0, bytes, s));
-    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s));
+    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc2, 0, 2 * sizeof(double), s));
   }
   if (p->n > 0 && (p->stage_mask & 2)) {
     const int grid = event_grid(p->n, 8);
-    const int gvar = (p->order == CMAX_ORDER_PIXEL) ? p->grad_variant : 0;
-    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, gq, grad_motion);
-    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, gq, grad_motion);
-    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, gq, reinterpret_cast<float*>(acc2));
-    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(acc2, grad_motion);
+    int gvar = p->grad_variant;
+    if (gvar == 1 && p->order != CMAX_ORDER_PIXEL) gvar = 0;  // the segmented reduction needs source-pixel order
+    GradSrcs gs;
+    gs.img[0] = w.iwe; gs.img[1] = w.blur; gs.img[2] = w.G; gs.img[3] = w.G2;
+    gs.affine = w.affine;
+    gs.gdesc = w.gdesc;
+    float* target = (motion_model == CMAX_MOTION_2DOF) ? reinterpret_cast<float*>(w.acc2) : grad_motion;
+    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
+    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
+    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
+    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(w.acc2, grad_motion);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
@@ -531,10 +898,20 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
 
 int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
                    const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion, cmax_stream_t stream) {
-  int32_t fused = 0;
-  int rc = cmax_objective_vote(plan, motion_model, motion, workspace, nullptr, spec, &fused, stream);
+  int rc = check_model("cmax_objective", plan, motion_model);
   if (rc) return rc;
-  rc = cmax_objective_cost(plan, spec, d_orig_stat, workspace, fused, grad_motion != nullptr, d_cost, stream);
+  CMAX_REQUIRE(motion != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective: NULL argument");
+  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective: workspace must be 256-byte aligned");
+  rc = check_spec("cmax_objective", spec, plan->n_ref);
+  if (rc) return rc;
+  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective: normalised costs need d_orig_stat");
+  CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective: images must be at least 3x3");
+  const Ws w = carve(workspace, obj_layout(plan->Hp, plan->Wp));
+  const CombineDev cd = combine_for(plan, spec, d_orig_stat, d_cost, w);
+  int32_t fused = 0;
+  rc = vote_stage(plan, motion_model, motion, workspace, spec, &cd, &fused, as_stream(stream));
+  if (rc) return rc;
+  rc = cost_stage(plan, spec, d_orig_stat, workspace, fused, fused, grad_motion != nullptr, d_cost, stream);
   if (rc) return rc;
   if (grad_motion != nullptr) rc = cmax_objective_grad(plan, motion_model, motion, workspace, grad_motion, stream);
   return rc;

@@ -22,6 +22,10 @@ struct Chunk {
 
 struct cmax_plan {
   const float* events;  // float4 per event; tile-sorted copy (in the workspace) or the caller's array
+  // Private re-packed copy for the run kernels: (x, y, tz, bits(src)) with src = un-warped flat pixel (src/warp.py:305)
+  // and tz = normalised dt of reference time 0 when n_ref == 1 (packed_has_dt), else the raw timestamp t.
+  float4* packed;
+  int packed_has_dt;
   int64_t n;
   int H, W, pad_h, pad_w, Hp, Wp;
   float t_min, t_max;

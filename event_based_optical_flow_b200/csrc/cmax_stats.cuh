@@ -52,4 +52,74 @@ __device__ __forceinline__ void variance_commit(double s, double q, int64_t M, u
   }
 }
 
+// ---- scalar cost combination, shared by combine_cost_kernel (cmax_cost.cu) and the fold kernel's last CTA
+struct CombineArgs {
+  int n_ref, stat, form, sign, explicit_grad, has_orig;
+  float w[CMAX_MAX_REFS];
+};
+
+// Where K3 finds dL/dIWE: value(p) = affine_a * (image[p] - affine_m) inside the crop (crop = 1) or everywhere.
+struct GradDesc {
+  int kind;  // 0 = IWE, 1 = blurred IWE, 2 = explicit gradient image G, 3 = G after the blur adjoint (G2)
+  int crop;
+};
+
+struct CombineDev {
+  CombineArgs a;
+  const double* orig;
+  double* cost;
+  float* affine;    // [2*n_ref]
+  GradDesc* gdesc;  // may be NULL
+  GradDesc g;
+};
+
+static inline CombineDev make_combine(int n_ref, int stat, int form, int sign, int explicit_grad, const float* h_weights,
+                                      const double* orig, double* cost, float* affine) {
+  CombineDev cd;
+  cd.a.n_ref = n_ref; cd.a.stat = stat; cd.a.form = form; cd.a.sign = sign; cd.a.explicit_grad = explicit_grad ? 1 : 0;
+  cd.a.has_orig = orig != nullptr;
+  for (int r = 0; r < CMAX_MAX_REFS; ++r) cd.a.w[r] = (h_weights && r < n_ref) ? h_weights[r] : 1.0f;
+  cd.orig = orig; cd.cost = cost; cd.affine = affine; cd.gdesc = nullptr; cd.g.kind = 0; cd.g.crop = 0;
+  return cd;
+}
+
+void launch_combine(const double* stats, const CombineDev& cd, cudaStream_t s);
+
+// One thread.  d cost / d stat_r = alpha_r; VARIANCE without an explicit gradient image folds the statistic's own
+// image derivative in: dL/dIWE = alpha * 2/(M-1) * (I - mean) =: a * (I - m).
+__device__ __forceinline__ void combine_eval(const double* __restrict__ stats, const CombineDev& cd) {
+  const CombineArgs& a = cd.a;
+  double total = 0.0;
+  for (int r = 0; r < a.n_ref; ++r) {
+    const double c = stats[4 * r + 0], mean = stats[4 * r + 1], M = stats[4 * r + 2];
+    double alpha;
+    if (a.form == CMAX_COST_PLAIN) {
+      total += -(double)a.sign * c;
+      alpha = -(double)a.sign;
+    } else {
+      const double co = cd.orig[0];
+      const double w = (a.form == CMAX_COST_MULTIFOCAL) ? (double)a.w[r] : 1.0;
+      if (a.sign > 0) {  // minimize: orig / warped
+        total += w * co / c;
+        alpha = -w * co / (c * c);
+      } else if (a.form == CMAX_COST_NORMALIZED) {  // maximize: warped / orig
+        total += c / co;
+        alpha = 1.0 / co;
+      } else {  // multi-focal "maximize" negates the sum of (warped / orig)
+        total += -w * c / co;
+        alpha = -w / co;
+      }
+    }
+    if (a.stat == CMAX_STAT_VARIANCE && !a.explicit_grad) {
+      cd.affine[2 * r + 0] = (float)(alpha * 2.0 / (M - 1.0));
+      cd.affine[2 * r + 1] = (float)mean;
+    } else {
+      cd.affine[2 * r + 0] = (float)alpha;
+      cd.affine[2 * r + 1] = 0.f;
+    }
+  }
+  cd.cost[0] = total;
+  if (cd.gdesc != nullptr) *cd.gdesc = cd.g;
+}
+
 }  // namespace cmax

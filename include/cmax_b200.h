@@ -152,10 +152,15 @@ void cmax_plan_destroy(cmax_plan_t* plan);
 int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_t* h_n, int32_t* h_order);
 /* Select reference times / voxel bins for subsequent calls (enqueues one tiny kernel). */
 int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream);
-/* Kernel variant knobs for experiments (profiles/): vote_variant 0 = one red.v4 per event into per-corner
- * accumulators (default), 1 = four scalar red.f32 into the image, 2 = shared-memory privatised int32 fixed-point
- * window per source tile (needs CMAX_ORDER_TILE/PIXEL); grad_variant 0 = scalar red per event, 1 = warp-segmented
- * reduction over runs of equal source pixel. */
+/* Kernel variants (all give the same results up to fp32 summation order; kept selectable so that profiles/ can show
+ * each design choice measured against the others):
+ *   vote_variant 2 (default) = each thread walks a run of consecutive events and sums the weights of events that
+ *                  fall into the same accumulator cell in registers: one red.v4 per cell change;
+ *                0 = one red.v4 per event into the per-corner accumulators; 1 = four scalar red.f32 per event
+ *                  straight into the image (the textbook scatter).
+ *   grad_variant 2 (default) = run walk: corner gradients re-gathered only on a cell change, flow gradient summed in
+ *                  registers per source-pixel run; 1 = per-event gather + warp-segmented shuffle reduction over runs
+ *                  of equal source pixel (needs CMAX_ORDER_PIXEL, else falls back to 0); 0 = scalar red per event. */
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant);
 /* Measurement aid (bench.py roofline): which launches the three stages enqueue.  Bit 0 = the memsets, bit 1 = the
  * event kernels (K1 in cmax_objective_vote, K3 in cmax_objective_grad), bit 2 = the image-sized kernels (fold, blur,
