@@ -144,19 +144,31 @@ __global__ void __launch_bounds__(256) gather_events_kernel(const float* __restr
   }
 }
 
-// (x, y, t, p) -> (x, y, tz, bits(src)); see cmax_plan.  dt exactly as the kernels compute it (src/warp.py:254-258).
-__global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ ev, int64_t n, int H, int W,
+// (x, y, t, p) -> (x, y, tz, bits(src)), written in WARP-TILE order: logical event j = tile*256 + lane*8 + k is
+// stored at slot tile*256 + k*32 + lane, so that a coalesced 16-byte load by lane `lane` at step k returns that lane's
+// k-th consecutive event (see cmax_plan.cuh).  dt exactly as the kernels compute it (src/warp.py:254-258).
+// Slots past n (the last tile's padding) are zero-filled.
+__global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ ev, int64_t n, int64_t slots, int H, int W,
                                                      const cmax_time_params_t* __restrict__ tp, int with_dt, float4* __restrict__ out) {
   const float ref = tp->ref[0], period = tp->period[0];
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-    const float4 e = ev[i];
-    int r, c;
-    source_pixel(e.x, e.y, H, W, &r, &c);
-    const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
-    out[i] = make_float4(e.x, e.y, tz, __int_as_float(r * W + c));
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < slots; j += step) {
+    float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    if (j < n) {
+      const float4 e = ev[j];
+      int r, c;
+      source_pixel(e.x, e.y, H, W, &r, &c);
+      const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
+      o = make_float4(e.x, e.y, tz, __int_as_float(r * W + c));
+    }
+    const int64_t tile = j / kWarpTile;
+    const int within = (int)(j % kWarpTile), lane = within / kRunE, k = within % kRunE;
+    out[tile * kWarpTile + k * 32 + lane] = o;
   }
 }
+
+// slots of the packed copy: whole warp-tiles of kWarpTile events
+static inline int64_t packed_slots(int64_t n) { return std::max<int64_t>(1, (n + kWarpTile - 1) / kWarpTile) * kWarpTile; }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -183,7 +195,7 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
   L.off_params = off; off = align_up(off + sizeof(cmax_time_params_t), 256);
   L.off_minmax = off; off = align_up(off + 2 * sizeof(float), 256);
   L.off_status = off; off = align_up(off + sizeof(int32_t), 256);
-  L.off_packed = off; off = align_up(off + (size_t)std::max<int64_t>(n, 1) * sizeof(float4), 256);
+  L.off_packed = off; off = align_up(off + (size_t)packed_slots(n) * sizeof(float4), 256);
   if (order != CMAX_ORDER_ASIS) {
     L.key_bits = bits_for((uint64_t)L.n_tiles * (order == CMAX_ORDER_PIXEL ? kTile * kTile : 1));
     L.max_chunks = (int)(n / kChunk) + L.n_tiles + 1;
@@ -421,8 +433,9 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
   plan->n_bins = n_bins;
   plan->packed_has_dt = (n_ref == 1) ? 1 : 0;
   if (plan->n > 0) {
-    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (plan->n + 255) / 256);
-    repack_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, plan->H, plan->W,
+    const int64_t slots = packed_slots(plan->n);
+    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (slots + 255) / 256);
+    repack_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H, plan->W,
                                                         plan->d_params, plan->packed_has_dt, plan->packed);
     CMAX_CUDA_CHECK(cudaGetLastError());
   }

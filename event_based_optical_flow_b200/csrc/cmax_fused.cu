@@ -332,23 +332,17 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(FusedArgs a, const floa
 // which divides the number of atomics and gathers by the run length without any shuffles.  The events come from the
 // plan's packed copy (x, y, dt|t, src): everything that is constant over the CM iterations -- the source pixel index,
 // and for a single reference time the normalised dt including its IEEE division -- is precomputed once per plan.
-// They are staged through shared memory (coalesced 16-byte loads, kRunE independent loads in flight per thread; padded
-// so that both the staging stores and the per-thread reads are bank-conflict free).  Correct for ANY event order --
-// an unordered stream just degenerates to one flush per event.
-constexpr int kRunE = 8;         // consecutive events per thread
+// The packed copy is stored pre-transposed in warp-tile order (cmax_plan.cuh), so kRunE coalesced, independent 16-byte
+// loads give every lane its kRunE consecutive events directly in registers: no shared-memory staging, no barriers.
+// Correct for ANY event order -- an unordered stream just degenerates to one flush per event.
 constexpr int kRunThreads = 128;
-constexpr int kRunTile = kRunE * kRunThreads;             // events per CTA iteration
-constexpr int kRunSmem = kRunTile + kRunTile / 8;         // float4 slots incl. one pad slot per 8 events
+constexpr int kRunWarps = kRunThreads / 32;
 
-__device__ __forceinline__ void stage_events(const float4* __restrict__ ev, int64_t base, int64_t n, float4* sm) {
+// The kRunE consecutive events of this lane, straight from the pre-transposed packed copy (coalesced, independent).
+__device__ __forceinline__ void load_tile(const float4* __restrict__ packed, int64_t tile, int lane, float4 (&e)[kRunE]) {
+  const float4* p = packed + tile * kWarpTile + lane;
 #pragma unroll
-  for (int k = 0; k < kRunE; ++k) {
-    const int j = k * kRunThreads + threadIdx.x;
-    const int64_t idx = base + j;
-    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx < n) e = __ldcs(ev + idx);
-    sm[j + (j >> 3)] = e;
-  }
+  for (int k = 0; k < kRunE; ++k) e[k] = __ldcs(p + k * 32);
 }
 
 // Per-reference-time scalars kept in registers (dense / 2-dof); the voxel model also needs the bin edges (shared).
@@ -401,7 +395,6 @@ __device__ __forceinline__ int vote_cell(const Vote& v, int Hp, int Wp) {
 template <int MODEL, int NREF, bool PRE_DT>
 __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, float4* __restrict__ acc) {
   __shared__ TimeSmem s;
-  __shared__ float4 sm[kRunSmem];
   if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
@@ -410,13 +403,13 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
     th0 = __ldg(a.motion);
     th1 = __ldg(a.motion + 1);
   }
-  const int64_t n_tiles = (a.n + kRunTile - 1) / kRunTile;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = tile * kRunTile;
-    __syncthreads();  // the previous tile has been consumed
-    stage_events(a.ev, base, a.n, sm);
-    __syncthreads();
-    const int64_t left = a.n - (base + (int64_t)threadIdx.x * kRunE);
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    float4 ev[kRunE];
+    load_tile(a.ev, tile, lane, ev);
+    const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
     const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
     int cell[NREF];
     float w0[NREF], w1[NREF], w2[NREF], w3[NREF];
@@ -427,10 +420,10 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
     }
     int src_prev = -1;
     float f0 = th0, f1 = th1;
-    const float4* mine = sm + threadIdx.x * (kRunE + 1);
-#pragma unroll 4
-    for (int k = 0; k < count; ++k) {
-      const float4 e = mine[k];
+#pragma unroll
+    for (int k = 0; k < kRunE; ++k) {
+      if (k >= count) break;
+      const float4 e = ev[k];
       const int src = __float_as_int(e.w);
       if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
         f0 = __ldg(a.motion + src);
@@ -471,7 +464,6 @@ struct GradSrcs {
 template <int MODEL, int NREF, bool PRE_DT>
 __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, GradSrcs gs, float* __restrict__ gmotion) {
   __shared__ TimeSmem s;
-  __shared__ float4 sm[kRunSmem];
   __shared__ double red2[2][kRunThreads / 32];
   if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
@@ -495,20 +487,20 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, Gra
   }
   double t0 = 0.0, t1 = 0.0;  // 2-dof
   constexpr int NACC = (MODEL == CMAX_MOTION_VOXEL) ? NREF : 1;
-  const int64_t n_tiles = (a.n + kRunTile - 1) / kRunTile;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t base = tile * kRunTile;
-    __syncthreads();
-    stage_events(a.ev, base, a.n, sm);
-    __syncthreads();
-    const int64_t left = a.n - (base + (int64_t)threadIdx.x * kRunE);
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
+    float4 ev[kRunE];
+    load_tile(a.ev, tile, lane, ev);
+    const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
     const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
     int cell[NREF];
-    float d_r[NREF], d_c0[NREF], d_c1[NREF], d_x0[NREF], d_x1[NREF];  // corner differences, see below
+    float d_r[NREF], d_c0[NREF], d_x0[NREF];  // corner differences, see below
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
       cell[r] = -2;
-      d_r[r] = d_c0[r] = d_c1[r] = d_x0[r] = d_x1[r] = 0.f;
+      d_r[r] = d_c0[r] = d_x0[r] = 0.f;
     }
     int key[NACC];   // flat index into gmotion of the row-component slot being accumulated
     float g0[NACC], g1[NACC];
@@ -519,10 +511,10 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, Gra
     }
     int src_prev = -1;
     float f0 = th0, f1 = th1;
-    const float4* mine = sm + threadIdx.x * (kRunE + 1);
-#pragma unroll 4
-    for (int k = 0; k < count; ++k) {
-      const float4 e = mine[k];
+#pragma unroll
+    for (int k = 0; k < kRunE; ++k) {
+      if (k >= count) break;
+      const float4 e = ev[k];
       const int src = __float_as_int(e.w);
       if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
         f0 = __ldg(a.motion + src);
@@ -608,8 +600,8 @@ __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __res
 
 // ------------------------------------------------------------------------------------------------ dispatch
 static inline int run_grid(int64_t n) {
-  const int64_t tiles = (n + kRunTile - 1) / kRunTile;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)kNumSMs * 8));
+  const int64_t ctas = ((n + kWarpTile - 1) / kWarpTile + kRunWarps - 1) / kRunWarps;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * 16));
 }
 
 template <int MODEL, int NREF>

@@ -9,6 +9,8 @@ namespace cmax {
 constexpr int kTile = 32;
 constexpr int kHalo = 16;
 constexpr int kWin = kTile + 2 * kHalo;  // 64
+constexpr int kRunE = 8;                  // consecutive events one thread of a run kernel walks
+constexpr int kWarpTile = 32 * kRunE;    // events per warp-tile of the packed copy
 constexpr int kChunk = 8192;             // events per CTA work item (bounds the fixed-point range, see cmax_fused.cu)
 
 struct Chunk {
@@ -24,6 +26,8 @@ struct cmax_plan {
   const float* events;  // float4 per event; tile-sorted copy (in the workspace) or the caller's array
   // Private re-packed copy for the run kernels: (x, y, tz, bits(src)) with src = un-warped flat pixel (src/warp.py:305)
   // and tz = normalised dt of reference time 0 when n_ref == 1 (packed_has_dt), else the raw timestamp t.
+  // Stored in warp-tile order: event tile*kWarpTile + lane*kRunE + k lives at slot tile*kWarpTile + k*32 + lane, i.e.
+  // pre-transposed so that coalesced loads hand every lane kRunE CONSECUTIVE events without a shared-memory pass.
   float4* packed;
   int packed_has_dt;
   int64_t n;
