@@ -19,7 +19,7 @@ namespace cmax {
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct ObjLayout {
-  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_gdesc, off_gxy, off_g, off_g2, off_gq, total;
+  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_misc, off_gxy, off_g, off_g2, off_gq, total;
   int64_t cells, HW;
 };
 
@@ -36,7 +36,7 @@ static ObjLayout obj_layout(int Hp, int Wp) {
   L.off_blur = off;    off = align256(off + (size_t)R * L.HW * sizeof(float));
   L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
   L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
-  L.off_gdesc = off;   off = align256(off + 64 + 2 * sizeof(double));  // GradDesc, then the 2-dof fp64 staging at +64
+  L.off_misc = off;    off = align256(off + 2 * sizeof(double));  // 2-dof fp64 staging
   // [StatAcc block][Sobel pair] is exactly the workspace layout cmax_image_stats expects (cmax_cost.cu)
   L.off_statacc = off; off = align256(off + (size_t)R * sizeof(StatAcc));
   L.off_gxy = off;     off = align256(off + (size_t)R * 2 * L.HW * sizeof(float));
@@ -56,6 +56,7 @@ struct FusedArgs {
   const float* motion;
   const cmax_time_params_t* tp;
   int64_t cells;  // (Hp+1)*(Wp+1)
+  unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block), or NULL
 };
 
 // Time parameters one CTA needs, staged in shared memory once per CTA.
@@ -162,9 +163,13 @@ __global__ void __launch_bounds__(256) vote_fused_kernel(FusedArgs a, float4* __
 }
 
 // ------------------------------------------------------------------------------------------------ fold
-// acc -> IWE; optionally the variance sums of the crop in the same pass (fp64 accumulators); optionally (single-GPU
-// fused path) the last CTA to finish also evaluates the scalar cost, so fold + statistics + combine are ONE launch.
-__global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restrict__ acc, float* __restrict__ iwe, int Hp, int Wp,
+// acc -> IWE.  Every scalar component of every accumulator cell has exactly ONE reader (pixel (r,c) reads .x of cell
+// (r,c), .y of (r-1,c), .z of (r,c-1), .w of (r-1,c-1)), so the reader also zeroes it: the accumulators are clean again
+// for the next CM iteration and no memset is ever enqueued (components no pixel reads only ever collect votes of
+// out-of-image corners and are never looked at).  Optionally the variance sums of the crop in the same pass (fp64
+// accumulators), and optionally (single-GPU fused path) the last CTA to finish also evaluates the scalar cost, so that
+// fold + statistics + combine are ONE launch.
+__global__ void __launch_bounds__(kStatBlock) fold_kernel(float4* __restrict__ acc, float* __restrict__ iwe, int Hp, int Wp,
                                                           int64_t cells, int want_var, int omit, StatAcc* __restrict__ sacc,
                                                           double* __restrict__ stats, int want_combine, CombineDev cd,
                                                           unsigned int* __restrict__ ctas_done) {
@@ -172,13 +177,21 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restri
   __shared__ bool all_done;
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
-  const float4* A = acc + img * cells;
+  float* A = reinterpret_cast<float*>(acc + img * cells);
   const int Wc = Wp + 1;
   double s = 0.0, q = 0.0;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(p / Wp), c = (int)(p % Wp);
     const int64_t k = (int64_t)(r + 1) * Wc + (c + 1);
-    const float v = ((A[k].x + A[k - Wc].y) + A[k - 1].z) + A[k - Wc - 1].w;
+    float* a00 = A + 4 * k;                  // .x of cell (r, c)
+    float* a10 = A + 4 * (k - Wc) + 1;       // .y of cell (r-1, c)
+    float* a01 = A + 4 * (k - 1) + 2;        // .z of cell (r, c-1)
+    float* a11 = A + 4 * (k - Wc - 1) + 3;   // .w of cell (r-1, c-1)
+    const float v = ((*a00 + *a10) + *a01) + *a11;
+    *a00 = 0.f;
+    *a10 = 0.f;
+    *a01 = 0.f;
+    *a11 = 0.f;
     iwe[img * HW + p] = v;
     if (want_var && (!omit || (r >= 1 && r <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
       s += (double)v;
@@ -204,9 +217,11 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(const float4* __restri
 
 // ------------------------------------------------------------------------------------------------ gq
 // Per-corner gradient pictures.  G[p] = a * (src[p] - m) (inside the crop when `crop`, else everywhere), gathered at
-// the four corners of every accumulator cell with the per-corner in-bounds masks.
+// the four corners of every accumulator cell with the per-corner in-bounds masks.  Also zeroes `zero` (the motion
+// gradient K3 is about to accumulate into) so that no memset is enqueued for it.
 __global__ void __launch_bounds__(256) gq_build_kernel(const float* __restrict__ src, const float* __restrict__ affine, int Hp, int Wp,
-                                                       int64_t cells, int crop, float4* __restrict__ gq) {
+                                                       int64_t cells, int crop, float4* __restrict__ gq, float* __restrict__ zero,
+                                                       int64_t n_zero) {
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
   const float* I = src + img * HW;
@@ -220,6 +235,8 @@ __global__ void __launch_bounds__(256) gq_build_kernel(const float* __restrict__
     };
     gq[img * cells + k] = make_float4(g(r, c), g(r + 1, c), g(r, c + 1), g(r + 1, c + 1));
   }
+  if (zero != nullptr && img == 0)
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_zero; k += (int64_t)gridDim.x * blockDim.x) zero[k] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -327,22 +344,63 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(FusedArgs a, const floa
 // the flow vector) and, being time ordered inside the run, walk monotonically along one line of the image.  Each
 // THREAD therefore takes kRunE consecutive events and keeps the current accumulator cell in registers:
 //   K1: weights of consecutive events that fall into the same cell are summed in registers, one red.v4 per cell change
-//   K3: the four corner gradients are re-gathered only on a cell change, and the flow-gradient of a source pixel is
-//       summed in registers, one pair of reds per source-pixel change
+//   K3: the per-corner gradient quad is re-gathered (one 16-byte load) only on a cell change, and the flow gradient of
+//       a source pixel is summed in registers, one pair of reds per source-pixel change
 // which divides the number of atomics and gathers by the run length without any shuffles.  The events come from the
 // plan's packed copy (x, y, dt|t, src): everything that is constant over the CM iterations -- the source pixel index,
-// and for a single reference time the normalised dt including its IEEE division -- is precomputed once per plan.
-// The packed copy is stored pre-transposed in warp-tile order (cmax_plan.cuh), so kRunE coalesced, independent 16-byte
-// loads give every lane its kRunE consecutive events directly in registers: no shared-memory staging, no barriers.
+// and for a single reference time the normalised dt including its IEEE division -- is precomputed once per plan, and
+// the copy is stored pre-transposed in warp-tile order (cmax_plan.cuh): slot k*32 + lane of a 4 KB tile is lane's k-th
+// consecutive event.  Every warp streams its tiles with TMA bulk copies (cp.async.bulk + mbarrier, double buffered in
+// shared memory): the copy of tile i+1 is in flight while tile i is walked, the walk reads its events with
+// conflict-free LDS.128, and no thread ever issues a global load for an event.
 // Correct for ANY event order -- an unordered stream just degenerates to one flush per event.
 constexpr int kRunThreads = 128;
 constexpr int kRunWarps = kRunThreads / 32;
+constexpr uint32_t kTileBytes = kWarpTile * sizeof(float4);  // 4096
 
-// The kRunE consecutive events of this lane, straight from the pre-transposed packed copy (coalesced, independent).
-__device__ __forceinline__ void load_tile(const float4* __restrict__ packed, int64_t tile, int lane, float4 (&e)[kRunE]) {
-  const float4* p = packed + tile * kWarpTile + lane;
-#pragma unroll
-  for (int k = 0; k < kRunE; ++k) e[k] = __ldcs(p + k * 32);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct alignas(128) TilePipe {  // one per warp
+  float4 buf[2][kWarpTile];
+  uint64_t bar[2];
+};
+
+__device__ __forceinline__ void pipe_init(TilePipe& p, int lane) {
+  if (lane == 0) {
+    mbar_init(&p.bar[0], 1);
+    mbar_init(&p.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void pipe_issue(TilePipe& p, int stage, const float4* __restrict__ packed, int64_t tile, int lane) {
+  if (lane == 0) {
+    mbar_expect_tx(&p.bar[stage], kTileBytes);
+    bulk_g2s(p.buf[stage], packed + tile * kWarpTile, kTileBytes, &p.bar[stage]);
+  }
 }
 
 // Per-reference-time scalars kept in registers (dense / 2-dof); the voxel model also needs the bin edges (shared).
@@ -392,194 +450,214 @@ __device__ __forceinline__ int vote_cell(const Vote& v, int Hp, int Wp) {
   return inside ? (v.row + 1) * (Wp + 1) + (v.col + 1) : -1;
 }
 
-template <int MODEL, int NREF, bool PRE_DT>
-__global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, float4* __restrict__ acc) {
-  __shared__ TimeSmem s;
-  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
-  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
-  const int HW = a.H * a.W;
-  float th0 = 0.f, th1 = 0.f;
-  if (MODEL == CMAX_MOTION_2DOF) {
-    th0 = __ldg(a.motion);
-    th1 = __ldg(a.motion + 1);
-  }
-  const int lane = threadIdx.x & 31;
-  const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
-  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
-  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
-    float4 ev[kRunE];
-    load_tile(a.ev, tile, lane, ev);
-    const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
-    const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
-    int cell[NREF];
-    float w0[NREF], w1[NREF], w2[NREF], w3[NREF];
-#pragma unroll
-    for (int r = 0; r < NREF; ++r) {
-      cell[r] = -1;
-      w0[r] = w1[r] = w2[r] = w3[r] = 0.f;
-    }
-    int src_prev = -1;
-    float f0 = th0, f1 = th1;
-#pragma unroll
-    for (int k = 0; k < kRunE; ++k) {
-      if (k >= count) break;
-      const float4 e = ev[k];
-      const int src = __float_as_int(e.w);
-      if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
-        f0 = __ldg(a.motion + src);
-        f1 = __ldg(a.motion + HW + src);
-        src_prev = src;
-      }
-#pragma unroll
-      for (int r = 0; r < NREF; ++r) {
-        float xw, yw, dt;
-        int bin;
-        warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, f0, f1, xw, yw, dt, bin);
-        const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
-        float w[4];
-        vote_weights(v, w);
-        const int c = vote_cell(v, a.Hp, a.Wp);
-        if (c != cell[r]) {
-          if (cell[r] >= 0) red_add_v4(acc + r * a.cells + cell[r], w0[r], w1[r], w2[r], w3[r]);
-          cell[r] = c;
-          w0[r] = w[0]; w1[r] = w[1]; w2[r] = w[2]; w3[r] = w[3];
-        } else {
-          w0[r] += w[0]; w1[r] += w[1]; w2[r] += w[2]; w3[r] += w[3];
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < NREF; ++r)
-      if (cell[r] >= 0) red_add_v4(acc + r * a.cells + cell[r], w0[r], w1[r], w2[r], w3[r]);
-  }
-}
-
-// What K3 needs to evaluate dL/dIWE at a pixel: value = a * (img[p] - m) inside [lo, hi_r] x [lo, hi_c], else 0.
-struct GradSrcs {
-  const float* img[4];  // indexed by GradDesc::kind
-  const float* affine;
-  const GradDesc* gdesc;
+// ---- K1 walk
+template <int NREF>
+struct VoteState {
+  int cell[NREF];
+  float w0[NREF], w1[NREF], w2[NREF], w3[NREF];
+  int src_prev;
+  float f0, f1;
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
-__global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, GradSrcs gs, float* __restrict__ gmotion) {
-  __shared__ TimeSmem s;
-  __shared__ double red2[2][kRunThreads / 32];
-  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
-  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
-  const int HW = a.H * a.W;
-  const int64_t HWp = (int64_t)a.Hp * a.Wp;
-  const GradDesc gd = *gs.gdesc;
-  const float* __restrict__ G = gd.kind == 0 ? gs.img[0] : (gd.kind == 1 ? gs.img[1] : (gd.kind == 2 ? gs.img[2] : gs.img[3]));
-  // corner (rr, cc) contributes iff lo <= rr <= hi_r and lo <= cc <= hi_c  <=>  (unsigned)(rr - lo) <= span_r ...
-  const int lo = gd.crop ? 1 : 0;
-  const unsigned span_r = (unsigned)((gd.crop ? a.Hp - 2 : a.Hp - 1) - lo), span_c = (unsigned)((gd.crop ? a.Wp - 2 : a.Wp - 1) - lo);
-  float ga[NREF], gm[NREF];
+__device__ __forceinline__ void vote_step(const float4 e, VoteState<NREF>& st, const FusedArgs& a, int HW, const RefRegs<NREF>& rr,
+                                          const TimeSmem& s, float4* __restrict__ acc) {
+  const int src = __float_as_int(e.w);
+  if (MODEL == CMAX_MOTION_DENSE && src != st.src_prev) {
+    st.f0 = __ldg(a.motion + src);
+    st.f1 = __ldg(a.motion + HW + src);
+    st.src_prev = src;
+  }
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
-    ga[r] = __ldg(gs.affine + 2 * r);
-    gm[r] = __ldg(gs.affine + 2 * r + 1);
+    float xw, yw, dt;
+    int bin;
+    warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
+    const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+    float w[4];
+    vote_weights(v, w);
+    const int c = vote_cell(v, a.Hp, a.Wp);
+    if (c != st.cell[r]) {
+      if (st.cell[r] >= 0) red_add_v4(acc + r * a.cells + st.cell[r], st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+      st.cell[r] = c;
+      st.w0[r] = w[0]; st.w1[r] = w[1]; st.w2[r] = w[2]; st.w3[r] = w[3];
+    } else {
+      st.w0[r] += w[0]; st.w1[r] += w[1]; st.w2[r] += w[2]; st.w3[r] += w[3];
+    }
   }
+}
+
+template <int MODEL, int NREF, bool PRE_DT>
+__global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, float4* __restrict__ acc) {
+  __shared__ TimeSmem s;
+  __shared__ TilePipe pipes[kRunWarps];
+  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
+  if (a.zero256 != nullptr && blockIdx.x == 0 && threadIdx.x < 64) a.zero256[threadIdx.x] = 0u;  // StatAcc block + CTA counter
+  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
+  const int HW = a.H * a.W;
+  const int lane = threadIdx.x & 31;
+  TilePipe& pipe = pipes[threadIdx.x >> 5];
+  pipe_init(pipe, lane);
   float th0 = 0.f, th1 = 0.f;
   if (MODEL == CMAX_MOTION_2DOF) {
     th0 = __ldg(a.motion);
     th1 = __ldg(a.motion + 1);
   }
-  double t0 = 0.0, t1 = 0.0;  // 2-dof
-  constexpr int NACC = (MODEL == CMAX_MOTION_VOXEL) ? NREF : 1;
-  const int lane = threadIdx.x & 31;
   const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
-  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps) {
-    float4 ev[kRunE];
-    load_tile(a.ev, tile, lane, ev);
-    const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
-    const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
-    int cell[NREF];
-    float d_r[NREF], d_c0[NREF], d_x0[NREF];  // corner differences, see below
+  if (warp0 < n_tiles) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  int it = 0;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps, ++it) {
+    const int stage = it & 1;
+    __syncwarp();  // every lane is done with the other buffer (walked in the previous iteration)
+    if (tile + n_warps < n_tiles) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
+    mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
+    const float4* mine = pipe.buf[stage] + lane;
+    VoteState<NREF> st;
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
-      cell[r] = -2;
-      d_r[r] = d_c0[r] = d_x0[r] = 0.f;
+      st.cell[r] = -1;
+      st.w0[r] = st.w1[r] = st.w2[r] = st.w3[r] = 0.f;
     }
-    int key[NACC];   // flat index into gmotion of the row-component slot being accumulated
-    float g0[NACC], g1[NACC];
+    st.src_prev = -1;
+    st.f0 = th0;
+    st.f1 = th1;
+    if ((tile + 1) * kWarpTile <= a.n) {  // full tile (warp-uniform)
 #pragma unroll
-    for (int q = 0; q < NACC; ++q) {
-      key[q] = -1;
-      g0[q] = g1[q] = 0.f;
+      for (int k = 0; k < kRunE; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
+    } else {
+      const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
+      const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
+      for (int k = 0; k < count; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
     }
-    int src_prev = -1;
-    float f0 = th0, f1 = th1;
 #pragma unroll
-    for (int k = 0; k < kRunE; ++k) {
-      if (k >= count) break;
-      const float4 e = ev[k];
-      const int src = __float_as_int(e.w);
-      if (MODEL == CMAX_MOTION_DENSE && src != src_prev) {
-        f0 = __ldg(a.motion + src);
-        f1 = __ldg(a.motion + HW + src);
-        src_prev = src;
-      }
+    for (int r = 0; r < NREF; ++r)
+      if (st.cell[r] >= 0) red_add_v4(acc + r * a.cells + st.cell[r], st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+  }
+}
+
+// ---- K3 walk
+template <int MODEL, int NREF>
+struct GradState {
+  static constexpr int NACC = (MODEL == CMAX_MOTION_VOXEL) ? NREF : 1;
+  int cell[NREF];
+  float d_x0[NREF], d_c0[NREF], d_r[NREF];  // corner differences of the current cell's gradient quad
+  int key[NACC];                            // flat index into gmotion of the row-component slot being accumulated
+  float g0[NACC], g1[NACC];
+  float f0, f1;
+  double t0, t1;  // 2-dof
+};
+
+template <int MODEL, int NREF>
+__device__ __forceinline__ void grad_flush(GradState<MODEL, NREF>& st, int q, int HW, float* __restrict__ gmotion) {
+  if (st.key[q] >= 0) {
+    atomicAdd(gmotion + st.key[q], st.g0[q]);
+    atomicAdd(gmotion + st.key[q] + HW, st.g1[q]);
+  }
+}
+
+template <int MODEL, int NREF, bool PRE_DT>
+__device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>& st, const FusedArgs& a, int HW, const RefRegs<NREF>& rr,
+                                          const TimeSmem& s, const float4* __restrict__ gq, float* __restrict__ gmotion) {
+  const int src = __float_as_int(e.w);
+  if (MODEL == CMAX_MOTION_DENSE && src != st.key[0]) {  // new source pixel: flush its predecessor, fetch the new flow vector
+    grad_flush<MODEL, NREF>(st, 0, HW, gmotion);
+    st.key[0] = src;
+    st.g0[0] = st.g1[0] = 0.f;
+    st.f0 = __ldg(a.motion + src);
+    st.f1 = __ldg(a.motion + HW + src);
+  }
 #pragma unroll
-      for (int r = 0; r < NREF; ++r) {
-        float xw, yw, dt;
-        int bin;
-        warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, f0, f1, xw, yw, dt, bin);
-        const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
-        const int c = vote_cell(v, a.Hp, a.Wp);
-        if (c != cell[r]) {
-          cell[r] = c;
-          float c00 = 0.f, c10 = 0.f, c01 = 0.f, c11 = 0.f;
-          if (c >= 0) {
-            const float* __restrict__ I = G + r * HWp;
-            const bool r0 = (unsigned)(v.row - lo) <= span_r, r1 = (unsigned)(v.row + 1 - lo) <= span_r;
-            const bool q0 = (unsigned)(v.col - lo) <= span_c, q1 = (unsigned)(v.col + 1 - lo) <= span_c;
-            const int64_t p = (int64_t)v.row * a.Wp + v.col;
-            if (r0 && q0) c00 = ga[r] * (__ldg(I + p) - gm[r]);
-            if (r1 && q0) c10 = ga[r] * (__ldg(I + p + a.Wp) - gm[r]);
-            if (r0 && q1) c01 = ga[r] * (__ldg(I + p + 1) - gm[r]);
-            if (r1 && q1) c11 = ga[r] * (__ldg(I + p + a.Wp + 1) - gm[r]);
-          }
-          // dL/dx' = (1-fy)(c10-c00) + fy(c11-c01) = d_x0 + fy * d_r ;  dL/dy' = (1-fx)(c01-c00) + fx(c11-c10) = d_c0 + fx * d_r
-          d_x0[r] = c10 - c00;
-          d_c0[r] = c01 - c00;
-          d_r[r] = (c11 - c01) - d_x0[r];
-        }
-        const float dx = d_x0[r] + v.fy * d_r[r];
-        const float dy = d_c0[r] + v.fx * d_r[r];
-        if (MODEL == CMAX_MOTION_2DOF) {
-          t0 += (double)(dt * dx);
-          t1 += (double)(dt * dy);
-        } else {
-          const int q = (MODEL == CMAX_MOTION_VOXEL) ? r : 0;
-          const int kk = (MODEL == CMAX_MOTION_VOXEL) ? (bin >= 0 ? bin * 2 * HW + src : -1) : src;
-          if (kk != key[q]) {
-            if (key[q] >= 0) {
-              atomicAdd(gmotion + key[q], g0[q]);
-              atomicAdd(gmotion + key[q] + HW, g1[q]);
-            }
-            key[q] = kk;
-            g0[q] = g1[q] = 0.f;
-          }
-          g0[q] -= dt * dx;
-          g1[q] -= dt * dy;
-        }
+  for (int r = 0; r < NREF; ++r) {
+    float xw, yw, dt;
+    int bin;
+    warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
+    const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+    const int c = vote_cell(v, a.Hp, a.Wp);
+    if (c != st.cell[r]) {
+      st.cell[r] = c;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c >= 0) g = __ldg(gq + r * a.cells + c);
+      // dL/dx' = (1-fy)(g10-g00) + fy(g11-g01) = d_x0 + fy*d_r ;  dL/dy' = (1-fx)(g01-g00) + fx(g11-g10) = d_c0 + fx*d_r
+      st.d_x0[r] = g.y - g.x;
+      st.d_c0[r] = g.z - g.x;
+      st.d_r[r] = (g.w - g.z) - st.d_x0[r];
+    }
+    const float dx = fmaf(v.fy, st.d_r[r], st.d_x0[r]);
+    const float dy = fmaf(v.fx, st.d_r[r], st.d_c0[r]);
+    if (MODEL == CMAX_MOTION_2DOF) {
+      st.t0 += (double)(dt * dx);
+      st.t1 += (double)(dt * dy);
+    } else if (MODEL == CMAX_MOTION_DENSE) {
+      st.g0[0] = fmaf(-dt, dx, st.g0[0]);
+      st.g1[0] = fmaf(-dt, dy, st.g1[0]);
+    } else {
+      const int kk = bin >= 0 ? bin * 2 * HW + src : -1;
+      if (kk != st.key[r]) {
+        grad_flush<MODEL, NREF>(st, r, HW, gmotion);
+        st.key[r] = kk;
+        st.g0[r] = st.g1[r] = 0.f;
       }
+      st.g0[r] = fmaf(-dt, dx, st.g0[r]);
+      st.g1[r] = fmaf(-dt, dy, st.g1[r]);
+    }
+  }
+}
+
+template <int MODEL, int NREF, bool PRE_DT>
+__global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, const float4* __restrict__ gq, float* __restrict__ gmotion) {
+  __shared__ TimeSmem s;
+  __shared__ TilePipe pipes[kRunWarps];
+  __shared__ double red2[2][kRunWarps];
+  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
+  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
+  const int HW = a.H * a.W;
+  const int lane = threadIdx.x & 31;
+  TilePipe& pipe = pipes[threadIdx.x >> 5];
+  pipe_init(pipe, lane);
+  GradState<MODEL, NREF> st;
+  st.f0 = st.f1 = 0.f;
+  st.t0 = st.t1 = 0.0;
+  if (MODEL == CMAX_MOTION_2DOF) {
+    st.f0 = __ldg(a.motion);
+    st.f1 = __ldg(a.motion + 1);
+  }
+  const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  if (warp0 < n_tiles) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  int it = 0;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps, ++it) {
+    const int stage = it & 1;
+    __syncwarp();
+    if (tile + n_warps < n_tiles) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
+    mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
+    const float4* mine = pipe.buf[stage] + lane;
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      st.cell[r] = -2;
+      st.d_x0[r] = st.d_c0[r] = st.d_r[r] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < GradState<MODEL, NREF>::NACC; ++q) {
+      st.key[q] = -1;
+      st.g0[q] = st.g1[q] = 0.f;
+    }
+    if ((tile + 1) * kWarpTile <= a.n) {
+#pragma unroll
+      for (int k = 0; k < kRunE; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
+    } else {
+      const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
+      const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
+      for (int k = 0; k < count; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
     }
     if (MODEL != CMAX_MOTION_2DOF) {
 #pragma unroll
-      for (int q = 0; q < NACC; ++q)
-        if (key[q] >= 0) {
-          atomicAdd(gmotion + key[q], g0[q]);
-          atomicAdd(gmotion + key[q] + HW, g1[q]);
-        }
+      for (int q = 0; q < GradState<MODEL, NREF>::NACC; ++q) grad_flush<MODEL, NREF>(st, q, HW, gmotion);
     }
   }
   if (MODEL == CMAX_MOTION_2DOF) {
-    t0 = warp_sum(t0);
-    t1 = warp_sum(t1);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double t0 = warp_sum(st.t0), t1 = warp_sum(st.t1);
+    const int wid = threadIdx.x >> 5;
     if (lane == 0) {
       red2[0][wid] = t0;
       red2[1][wid] = t1;
@@ -587,13 +665,13 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, Gra
     __syncthreads();
     if (threadIdx.x < 2) {
       double tot = 0.0;
-      for (int w = 0; w < kRunThreads / 32; ++w) tot += red2[threadIdx.x][w];
+      for (int w = 0; w < kRunWarps; ++w) tot += red2[threadIdx.x][w];
       atomicAdd(reinterpret_cast<double*>(gmotion) + threadIdx.x, tot);  // fp64 staging, narrowed by finish_2dof_kernel
     }
   }
 }
 
-// 2-dof gradient: the CTAs accumulate in two doubles (staged in the G2 scratch), narrowed here.
+// 2-dof gradient: the CTAs accumulate in two doubles (off_misc), narrowed here.
 __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __restrict__ out) {
   if (threadIdx.x < 2) out[threadIdx.x] = (float)acc2[threadIdx.x];
 }
@@ -601,15 +679,25 @@ __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __res
 // ------------------------------------------------------------------------------------------------ dispatch
 static inline int run_grid(int64_t n) {
   const int64_t ctas = ((n + kWarpTile - 1) / kWarpTile + kRunWarps - 1) / kRunWarps;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * 16));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * 6));  // 6 CTAs of 33 KB shared memory per SM
+}
+
+// The run kernels want 6 CTAs x 33 KB of shared memory per SM: ask for the largest shared-memory carveout (once per
+// instantiation; one process drives one GPU).
+template <typename K>
+static void prefer_shared(K kernel) {
+  static bool done = false;
+  if (!done) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    done = true;
+  }
 }
 
 template <int MODEL, int NREF>
 static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
   if (variant == 2) {
-    FusedArgs b = a;
-    b.ev = a.packed;
-    vote_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(b, acc);
+    prefer_shared(vote_runs_kernel<MODEL, NREF, NREF == 1>);
+    vote_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(a, acc);
   }
   else if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
   else vote_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, acc, iwe);
@@ -624,22 +712,21 @@ static void launch_vote_m(int n_ref, int variant, int grid, cudaStream_t s, cons
   }
 }
 template <int MODEL, int NREF>
-static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, const GradSrcs& gs, float* gm) {
+static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
   if (gvar == 2) {
-    FusedArgs b = a;
-    b.ev = a.packed;
-    grad_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(b, gs, gm);
+    prefer_shared(grad_runs_kernel<MODEL, NREF, NREF == 1>);
+    grad_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(a, gq, gm);
   }
   else if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
   else grad_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, gq, gm);
 }
 template <int MODEL>
-static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, const GradSrcs& gs, float* gm) {
+static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
   switch (n_ref) {
-    case 1: launch_grad<MODEL, 1>(gvar, grid, s, a, gq, gs, gm); break;
-    case 2: launch_grad<MODEL, 2>(gvar, grid, s, a, gq, gs, gm); break;
-    case 3: launch_grad<MODEL, 3>(gvar, grid, s, a, gq, gs, gm); break;
-    default: launch_grad<MODEL, 4>(gvar, grid, s, a, gq, gs, gm); break;
+    case 1: launch_grad<MODEL, 1>(gvar, grid, s, a, gq, gm); break;
+    case 2: launch_grad<MODEL, 2>(gvar, grid, s, a, gq, gm); break;
+    case 3: launch_grad<MODEL, 3>(gvar, grid, s, a, gq, gm); break;
+    default: launch_grad<MODEL, 4>(gvar, grid, s, a, gq, gm); break;
   }
 }
 
@@ -660,6 +747,7 @@ static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.motion = motion;
   a.tp = p->d_params;
   a.cells = (int64_t)(p->Hp + 1) * (p->Wp + 1);
+  a.zero256 = nullptr;
   return a;
 }
 
@@ -688,7 +776,7 @@ static int check_spec(const char* fn, const cmax_cost_spec* spec, int n_ref) {
 
 // ------------------------------------------------------------------------------------------------ stages
 struct Ws {
-  float4* acc; float* iwe; float* blur; StatAcc* sacc; double* stats; float* affine; GradDesc* gdesc; unsigned int* ctas_done;
+  float4* acc; float* iwe; float* blur; StatAcc* sacc; double* stats; float* affine; unsigned int* ctas_done;
   float* G; float* G2; float4* gq; char* stats_ws; double* acc2;
 };
 
@@ -701,24 +789,20 @@ static Ws carve(void* workspace, const ObjLayout& L) {
   w.sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
   w.stats = reinterpret_cast<double*>(ws + L.off_stats);
   w.affine = reinterpret_cast<float*>(ws + L.off_affine);
-  w.gdesc = reinterpret_cast<GradDesc*>(ws + L.off_gdesc);
-  w.ctas_done = reinterpret_cast<unsigned int*>(ws + L.off_statacc + 192);  // inside the 256-byte StatAcc block: one memset clears both
+  w.ctas_done = reinterpret_cast<unsigned int*>(ws + L.off_statacc + 192);  // inside the 256-byte StatAcc block
   w.G = reinterpret_cast<float*>(ws + L.off_g);
   w.G2 = reinterpret_cast<float*>(ws + L.off_g2);
   w.gq = reinterpret_cast<float4*>(ws + L.off_gq);
   w.stats_ws = ws + L.off_statacc;  // [StatAcc block][Sobel pair], the layout cmax_image_stats expects
-  w.acc2 = reinterpret_cast<double*>(ws + L.off_gdesc + 64);  // 2-dof fp64 staging
+  w.acc2 = reinterpret_cast<double*>(ws + L.off_misc);  // 2-dof fp64 staging
   return w;
 }
 
-// Where dL/dIWE comes from for this spec (see GradDesc).
-static GradDesc grad_desc(const cmax_cost_spec* spec) {
-  const bool blurred = spec->sigma > 0.f;
-  const bool explicit_grad = blurred || spec->stat == CMAX_STAT_GRADMAG;
-  GradDesc g;
-  g.kind = explicit_grad ? (blurred ? 3 : 2) : 0;
-  g.crop = explicit_grad ? 0 : (spec->omit_boundary ? 1 : 0);
-  return g;
+static inline size_t motion_floats(const cmax_plan* p, int motion_model) {
+  const size_t HW = (size_t)p->H * p->W;
+  if (motion_model == CMAX_MOTION_DENSE) return 2 * HW;
+  if (motion_model == CMAX_MOTION_VOXEL) return 2 * (size_t)p->n_bins * HW;
+  return 2;
 }
 
 // Stage 1.  `fused_combine` (may be NULL): when the statistics can be fused into the fold, also evaluate the scalar
@@ -728,13 +812,18 @@ static int vote_stage(const cmax_plan* p, int motion_model, const float* motion,
   const ObjLayout L = obj_layout(p->Hp, p->Wp);
   const Ws w = carve(workspace, L);
   const int n_ref = p->n_ref;
-  const FusedArgs a = fused_args(p, motion);
+  FusedArgs a = fused_args(p, motion);
   const int variant = p->vote_variant;
   const bool fuse = can_fuse_stats(fuse_spec) && variant != 1;
   const int mask = p->stage_mask;
+  static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 192, "StatAcc block and the CTA counter share 256 bytes");
+  // the 256-byte statistics block is cleared by K1's first CTA when there is one (variant 2), else by a memset
+  const bool k1_clears = fuse && variant == 2 && p->n > 0 && (mask & 2);
+  if (k1_clears) a.zero256 = reinterpret_cast<unsigned int*>(w.sacc);
   if (mask & 1) {
+    // the per-corner accumulators are left clean by the fold (see fold_kernel) and by cmax_objective_workspace_init
     if (variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(w.iwe, 0, (size_t)n_ref * L.HW * sizeof(float), s));
-    else CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc, 0, (size_t)n_ref * L.cells * sizeof(float4), s));
+    if (fuse && !k1_clears) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
   }
   if (p->n > 0 && (mask & 2)) {
     const int grid = event_grid(p->n, 8);
@@ -743,8 +832,6 @@ static int vote_stage(const cmax_plan* p, int motion_model, const float* motion,
     else launch_vote_m<CMAX_MOTION_2DOF>(n_ref, variant, grid, s, a, w.acc, w.iwe);
   }
   if (variant != 1 && (mask & 4)) {
-    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 192, "StatAcc block and the CTA counter share 256 bytes");
-    if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
     dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), n_ref);
     CombineDev cd;
     memset(&cd, 0, sizeof(cd));
@@ -758,12 +845,78 @@ static int vote_stage(const cmax_plan* p, int motion_model, const float* motion,
 }
 
 static CombineDev combine_for(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, double* d_cost, const Ws& w) {
-  const GradDesc g = grad_desc(spec);
-  CombineDev cd = make_combine(p->n_ref, spec->stat, spec->form, spec->direction_sign, g.kind >= 2 ? 1 : 0, spec->weights, d_orig_stat,
-                               d_cost, w.affine);
-  cd.gdesc = w.gdesc;
-  cd.g = g;
-  return cd;
+  const bool explicit_grad = spec->sigma > 0.f || spec->stat == CMAX_STAT_GRADMAG;
+  return make_combine(p->n_ref, spec->stat, spec->form, spec->direction_sign, explicit_grad ? 1 : 0, spec->weights, d_orig_stat, d_cost,
+                      w.affine);
+}
+
+// Stage 2.  combined != 0: the scalar combination already ran inside the fold (cmax_objective's fast path).
+// zero_grad (may be NULL): motion-gradient buffer to clear inside the gradient-picture kernel.
+static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int stats_fused,
+                      int combined, int want_grad, double* d_cost, float* zero_grad, size_t n_zero, cmax_stream_t stream) {
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
+  cudaStream_t s = as_stream(stream);
+  const int n_ref = p->n_ref;
+  const bool blurred = spec->sigma > 0.f;
+  const float* img = w.iwe;
+  int rc;
+  if (!(p->stage_mask & 4)) return CMAX_OK;
+  if (blurred) {
+    rc = cmax_blur3(w.iwe, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
+    if (rc) return rc;
+    img = w.blur;
+  }
+  // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
+  const bool explicit_grad = blurred || spec->stat == CMAX_STAT_GRADMAG;
+  if (!stats_fused) {
+    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
+    rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, w.stats, (want_grad && explicit_grad) ? w.G : nullptr,
+                          w.stats_ws, stream);
+    if (rc) return rc;
+  }
+  if (!combined) launch_combine(w.stats, combine_for(p, spec, d_orig_stat, d_cost, w), s);
+  if (want_grad) {
+    const float* gsrc = img;
+    int crop = spec->omit_boundary ? 1 : 0;
+    if (explicit_grad) {
+      gsrc = w.G;
+      crop = 0;
+      if (blurred) {
+        rc = cmax_blur3(w.G, w.G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
+        if (rc) return rc;
+        gsrc = w.G2;
+      }
+    }
+    dim3 grid((unsigned)image_grid(L.cells), n_ref);
+    gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, w.affine, p->Hp, p->Wp, L.cells, crop, w.gq, zero_grad, (int64_t)n_zero);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
+}
+
+// Stage 3.  pre_zeroed: grad_motion was cleared by stage 2.
+static int grad_stage(const cmax_plan* p, int motion_model, const float* motion, void* workspace, float* grad_motion, int pre_zeroed,
+                      cudaStream_t s) {
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
+  const FusedArgs a = fused_args(p, motion);
+  if (p->stage_mask & 1) {
+    if (!pre_zeroed) CMAX_CUDA_CHECK(cudaMemsetAsync(grad_motion, 0, motion_floats(p, motion_model) * sizeof(float), s));
+    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc2, 0, 2 * sizeof(double), s));
+  }
+  if (p->n > 0 && (p->stage_mask & 2)) {
+    const int grid = event_grid(p->n, 8);
+    int gvar = p->grad_variant;
+    if (gvar == 1 && p->order != CMAX_ORDER_PIXEL) gvar = 0;  // the segmented reduction needs source-pixel order
+    float* target = (motion_model == CMAX_MOTION_2DOF) ? reinterpret_cast<float*>(w.acc2) : grad_motion;
+    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, w.gq, target);
+    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, w.gq, target);
+    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, w.gq, target);
+    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(w.acc2, grad_motion);
+  }
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
 }
 
 }  // namespace cmax
@@ -781,6 +934,13 @@ size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_s
   return obj_layout(plan->Hp, plan->Wp).total;
 }
 
+int cmax_objective_workspace_init(const cmax_plan_t* plan, void* workspace, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr && workspace != nullptr, "cmax_objective_workspace_init: NULL argument");
+  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective_workspace_init: workspace must be 256-byte aligned");
+  CMAX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, obj_layout(plan->Hp, plan->Wp).total, as_stream(stream)));
+  return CMAX_OK;
+}
+
 int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float** iwe_out,
                         const cmax_cost_spec* fuse_spec, int32_t* stats_fused, cmax_stream_t stream) {
   int rc = check_model("cmax_objective_vote", plan, motion_model);
@@ -793,54 +953,6 @@ int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* 
   return CMAX_OK;
 }
 
-// combined != 0: the scalar combination already ran inside the fold (cmax_objective's fast path)
-static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int stats_fused,
-                      int combined, int want_grad, double* d_cost, cmax_stream_t stream) {
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  cudaStream_t s = as_stream(stream);
-  const int n_ref = p->n_ref;
-  const bool blurred = spec->sigma > 0.f;
-  const float* img = w.iwe;
-  int rc;
-  if (p->stage_mask & 4) {
-    if (blurred) {
-      rc = cmax_blur3(w.iwe, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
-      if (rc) return rc;
-      img = w.blur;
-    }
-    // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
-    const GradDesc g = grad_desc(spec);
-    const bool explicit_grad = want_grad && g.kind >= 2;
-    if (!stats_fused) {
-      static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
-      rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, w.stats, explicit_grad ? w.G : nullptr,
-                            w.stats_ws, stream);
-      if (rc) return rc;
-    }
-    if (!combined) launch_combine(w.stats, combine_for(p, spec, d_orig_stat, d_cost, w), s);
-    if (want_grad) {
-      const float* gsrc = img;
-      int crop = spec->omit_boundary ? 1 : 0;
-      if (g.kind >= 2) {
-        gsrc = w.G;
-        crop = 0;
-        if (blurred) {
-          rc = cmax_blur3(w.G, w.G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
-          if (rc) return rc;
-          gsrc = w.G2;
-        }
-      }
-      if (p->grad_variant != 2) {  // the run kernel gathers from the image itself (GradDesc); the others need the pictures
-        dim3 grid((unsigned)image_grid(L.cells), n_ref);
-        gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, w.affine, p->Hp, p->Wp, L.cells, crop, w.gq);
-      }
-    }
-    CMAX_CUDA_CHECK(cudaGetLastError());
-  }
-  return CMAX_OK;
-}
-
 int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
                         int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream) {
   CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost: NULL argument");
@@ -849,7 +961,7 @@ int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, con
   CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_cost: normalised costs need d_orig_stat");
   CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective_cost: images must be at least 3x3");
   CMAX_REQUIRE(!stats_fused || can_fuse_stats(spec), "cmax_objective_cost: stats_fused set for a spec that cannot fuse");
-  return cost_stage(plan, spec, d_orig_stat, workspace, stats_fused, 0, want_grad, d_cost, stream);
+  return cost_stage(plan, spec, d_orig_stat, workspace, stats_fused, 0, want_grad, d_cost, nullptr, 0, stream);
 }
 
 int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float* grad_motion,
@@ -857,35 +969,7 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
   int rc = check_model("cmax_objective_grad", plan, motion_model);
   if (rc) return rc;
   CMAX_REQUIRE(motion != nullptr && workspace != nullptr && grad_motion != nullptr, "cmax_objective_grad: NULL argument");
-  const cmax_plan* p = plan;
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  cudaStream_t s = as_stream(stream);
-  const FusedArgs a = fused_args(p, motion);
-  const int HW = p->H * p->W;
-  size_t bytes = 2 * sizeof(float);
-  if (motion_model == CMAX_MOTION_DENSE) bytes = 2 * (size_t)HW * sizeof(float);
-  if (motion_model == CMAX_MOTION_VOXEL) bytes = 2 * (size_t)p->n_bins * HW * sizeof(float);
-  if (p->stage_mask & 1) {
-    CMAX_CUDA_CHECK(cudaMemsetAsync(grad_motion, 0, bytes, s));
-    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc2, 0, 2 * sizeof(double), s));
-  }
-  if (p->n > 0 && (p->stage_mask & 2)) {
-    const int grid = event_grid(p->n, 8);
-    int gvar = p->grad_variant;
-    if (gvar == 1 && p->order != CMAX_ORDER_PIXEL) gvar = 0;  // the segmented reduction needs source-pixel order
-    GradSrcs gs;
-    gs.img[0] = w.iwe; gs.img[1] = w.blur; gs.img[2] = w.G; gs.img[3] = w.G2;
-    gs.affine = w.affine;
-    gs.gdesc = w.gdesc;
-    float* target = (motion_model == CMAX_MOTION_2DOF) ? reinterpret_cast<float*>(w.acc2) : grad_motion;
-    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
-    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
-    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, w.gq, gs, target);
-    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(w.acc2, grad_motion);
-  }
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  return CMAX_OK;
+  return grad_stage(plan, motion_model, motion, workspace, grad_motion, 0, as_stream(stream));
 }
 
 int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
@@ -903,9 +987,12 @@ int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motio
   int32_t fused = 0;
   rc = vote_stage(plan, motion_model, motion, workspace, spec, &cd, &fused, as_stream(stream));
   if (rc) return rc;
-  rc = cost_stage(plan, spec, d_orig_stat, workspace, fused, fused, grad_motion != nullptr, d_cost, stream);
+  // with everything enabled the gradient buffer is cleared inside the gradient-picture kernel instead of by a memset
+  const bool zero_in_gq = grad_motion != nullptr && plan->stage_mask == 7;
+  rc = cost_stage(plan, spec, d_orig_stat, workspace, fused, fused, grad_motion != nullptr, d_cost, zero_in_gq ? grad_motion : nullptr,
+                  zero_in_gq ? motion_floats(plan, motion_model) : 0, stream);
   if (rc) return rc;
-  if (grad_motion != nullptr) rc = cmax_objective_grad(plan, motion_model, motion, workspace, grad_motion, stream);
+  if (grad_motion != nullptr) rc = grad_stage(plan, motion_model, motion, workspace, grad_motion, zero_in_gq ? 1 : 0, as_stream(stream));
   return rc;
 }
 

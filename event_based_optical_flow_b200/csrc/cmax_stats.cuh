@@ -58,19 +58,11 @@ struct CombineArgs {
   float w[CMAX_MAX_REFS];
 };
 
-// Where K3 finds dL/dIWE: value(p) = affine_a * (image[p] - affine_m) inside the crop (crop = 1) or everywhere.
-struct GradDesc {
-  int kind;  // 0 = IWE, 1 = blurred IWE, 2 = explicit gradient image G, 3 = G after the blur adjoint (G2)
-  int crop;
-};
-
 struct CombineDev {
   CombineArgs a;
   const double* orig;
   double* cost;
   float* affine;    // [2*n_ref]
-  GradDesc* gdesc;  // may be NULL
-  GradDesc g;
 };
 
 static inline CombineDev make_combine(int n_ref, int stat, int form, int sign, int explicit_grad, const float* h_weights,
@@ -79,7 +71,7 @@ static inline CombineDev make_combine(int n_ref, int stat, int form, int sign, i
   cd.a.n_ref = n_ref; cd.a.stat = stat; cd.a.form = form; cd.a.sign = sign; cd.a.explicit_grad = explicit_grad ? 1 : 0;
   cd.a.has_orig = orig != nullptr;
   for (int r = 0; r < CMAX_MAX_REFS; ++r) cd.a.w[r] = (h_weights && r < n_ref) ? h_weights[r] : 1.0f;
-  cd.orig = orig; cd.cost = cost; cd.affine = affine; cd.gdesc = nullptr; cd.g.kind = 0; cd.g.crop = 0;
+  cd.orig = orig; cd.cost = cost; cd.affine = affine;
   return cd;
 }
 
@@ -119,7 +111,6 @@ __device__ __forceinline__ void combine_eval(const double* __restrict__ stats, c
     }
   }
   cd.cost[0] = total;
-  if (cd.gdesc != nullptr) *cd.gdesc = cd.g;
 }
 
 }  // namespace cmax

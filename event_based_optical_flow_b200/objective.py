@@ -193,6 +193,8 @@ class ContrastObjective:
             nbytes = self.lib.cmax_objective_workspace_bytes(self.plan.handle, C.byref(self.spec))
             self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
         self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            _lib.call("cmax_objective_workspace_init", self.plan.handle, self._ws_ptr, _stream_ptr())
         self._cost = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._orig_stat = None
         if form != "plain":

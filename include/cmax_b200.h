@@ -180,6 +180,10 @@ typedef struct {
 
 /* Scratch one evaluation needs (per-corner accumulators, IWEs, gradient pictures, statistics). */
 size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_spec* spec);
+/* Must be called once on a freshly allocated workspace (and again after any failed call): the per-corner accumulators
+ * are kept clean BETWEEN evaluations by the kernels themselves (the fold zeroes what it reads), so no evaluation ever
+ * enqueues a memset for them. */
+int cmax_objective_workspace_init(const cmax_plan_t* plan, void* workspace, cmax_stream_t stream);
 /* Stage 1 (K1 + fold): warp by `motion` and bilinear-vote into n_ref images; returns in *iwe_out a pointer INTO the
  * workspace to [n_ref,Hp,Wp] fp32 (multi-GPU callers all-reduce it in place before stage 2).
  * (src/warp.py:301-313|339-365|506-520 -> src/event_image_converter.py:316-374, composed as in
