@@ -505,12 +505,13 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
   }
   const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
-  if (warp0 < n_tiles) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  const int64_t t_end = n_tiles;  // warps stride over all tiles (a contiguous range per CTA measured no better: profiles/)
+  if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);
   int it = 0;
-  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps, ++it) {
+  for (int64_t tile = warp0; tile < t_end; tile += n_warps, ++it) {
     const int stage = it & 1;
     __syncwarp();  // every lane is done with the other buffer (walked in the previous iteration)
-    if (tile + n_warps < n_tiles) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
+    if (tile + n_warps < t_end) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
     mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
     const float4* mine = pipe.buf[stage] + lane;
     VoteState<NREF> st;
@@ -523,8 +524,38 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
     st.f0 = th0;
     st.f1 = th1;
     if ((tile + 1) * kWarpTile <= a.n) {  // full tile (warp-uniform)
+      if constexpr (MODEL == CMAX_MOTION_DENSE) {
+        // batched: all flow loads of the tile's kRunE events are in flight together (one L2 latency per tile, not one
+        // per source-pixel change), then the walk runs out of registers
+        float f0[kRunE], f1[kRunE];
+        bool nw[kRunE];
+        int prev = -1;
 #pragma unroll
-      for (int k = 0; k < kRunE; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
+        for (int k = 0; k < kRunE; ++k) {
+          const int src = __float_as_int(mine[k * 32].w);
+          nw[k] = src != prev;
+          prev = src;
+          if (nw[k]) {
+            f0[k] = __ldg(a.motion + src);
+            f1[k] = __ldg(a.motion + HW + src);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kRunE; ++k) {
+          if (k > 0 && !nw[k]) {
+            f0[k] = f0[k - 1];
+            f1[k] = f1[k - 1];
+          }
+          const float4 e = mine[k * 32];
+          st.f0 = f0[k];
+          st.f1 = f1[k];
+          st.src_prev = __float_as_int(e.w);
+          vote_step<MODEL, NREF, PRE_DT>(e, st, a, HW, rr, s, acc);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kRunE; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
+      }
     } else {
       const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
       const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
@@ -604,7 +635,81 @@ __device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>
   }
 }
 
-template <int MODEL, int NREF, bool PRE_DT>
+// Full tile of the dense-flow model, batched so that the dependent L2 round trips of the walk overlap.  Per batch of
+// KB consecutive events: (A) all flow loads, (B) per reference time all warps / cells, then all gradient-quad gathers,
+// (C) the accumulation with one flush per source-pixel change.  Two exposed L2 latencies per batch instead of up to
+// 2*KB; KB trades registers (occupancy) against memory-level parallelism.
+template <int NREF, bool PRE_DT, int KB>
+__device__ __forceinline__ void grad_tile_dense(const float4* __restrict__ mine, GradState<CMAX_MOTION_DENSE, NREF>& st, const FusedArgs& a,
+                                                int HW, const RefRegs<NREF>& rr, const float4* __restrict__ gq,
+                                                float* __restrict__ gmotion) {
+#pragma unroll
+  for (int b = 0; b < kRunE; b += KB) {
+    float f0[KB], f1[KB];
+    int srcs[KB];
+    bool nw[KB];
+    int prev = -1;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {  // (A)
+      srcs[k] = __float_as_int(mine[(b + k) * 32].w);
+      nw[k] = srcs[k] != prev;
+      prev = srcs[k];
+      if (nw[k]) {
+        f0[k] = __ldg(a.motion + srcs[k]);
+        f1[k] = __ldg(a.motion + HW + srcs[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 1; k < KB; ++k)
+      if (!nw[k]) {
+        f0[k] = f0[k - 1];
+        f1[k] = f1[k - 1];
+      }
+    float gx[KB], gy[KB];  // sum over reference times of -dt * dL/dx', -dt * dL/dy' per event
+#pragma unroll
+    for (int k = 0; k < KB; ++k) gx[k] = gy[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      float fx[KB], fy[KB], dts[KB];
+      int cs[KB];
+      float4 g[KB];
+      int cprev = -2;
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {  // (B)
+        const float4 e = mine[(b + k) * 32];
+        const float dt = PRE_DT ? e.z : __fdiv_rn(__fsub_rn(e.z, rr.ref[r]), rr.period[r]);
+        const Vote v = vote_geometry(warp_minus(e.x, dt, f0[k]), warp_minus(e.y, dt, f1[k]), a.pad_h, a.pad_w);
+        fx[k] = v.fx;
+        fy[k] = v.fy;
+        dts[k] = dt;
+        cs[k] = vote_cell(v, a.Hp, a.Wp);
+        if (cs[k] != cprev && cs[k] >= 0) g[k] = __ldg(gq + r * a.cells + cs[k]);
+        cprev = cs[k];
+      }
+#pragma unroll
+      for (int k = 0; k < KB; ++k) {  // (C)
+        if (cs[k] < 0) g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (k > 0 && cs[k] == cs[k - 1]) g[k] = g[k - 1];
+        const float d_x0 = g[k].y - g[k].x, d_c0 = g[k].z - g[k].x;
+        const float d_r = (g[k].w - g[k].z) - d_x0;
+        gx[k] = fmaf(-dts[k], fmaf(fy[k], d_r, d_x0), gx[k]);
+        gy[k] = fmaf(-dts[k], fmaf(fx[k], d_r, d_c0), gy[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      if (srcs[k] != st.key[0]) {
+        grad_flush<CMAX_MOTION_DENSE, NREF>(st, 0, HW, gmotion);
+        st.key[0] = srcs[k];
+        st.g0[0] = st.g1[0] = 0.f;
+      }
+      st.g0[0] += gx[k];
+      st.g1[0] += gy[k];
+    }
+  }
+}
+
+template <int MODEL, int NREF, bool PRE_DT, int KB>
 __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, const float4* __restrict__ gq, float* __restrict__ gmotion) {
   __shared__ TimeSmem s;
   __shared__ TilePipe pipes[kRunWarps];
@@ -624,12 +729,13 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
   }
   const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
-  if (warp0 < n_tiles) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  const int64_t t_end = n_tiles;  // warps stride over all tiles (a contiguous range per CTA measured no better: profiles/)
+  if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);
   int it = 0;
-  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps, ++it) {
+  for (int64_t tile = warp0; tile < t_end; tile += n_warps, ++it) {
     const int stage = it & 1;
     __syncwarp();
-    if (tile + n_warps < n_tiles) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
+    if (tile + n_warps < t_end) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
     mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
     const float4* mine = pipe.buf[stage] + lane;
 #pragma unroll
@@ -643,8 +749,12 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
       st.g0[q] = st.g1[q] = 0.f;
     }
     if ((tile + 1) * kWarpTile <= a.n) {
+      if constexpr (MODEL == CMAX_MOTION_DENSE && KB > 0) {
+        grad_tile_dense<NREF, PRE_DT, KB>(mine, st, a, HW, rr, gq, gmotion);
+      } else {
 #pragma unroll
-      for (int k = 0; k < kRunE; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
+        for (int k = 0; k < kRunE; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
+      }
     } else {
       const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
       const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
@@ -677,27 +787,27 @@ __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __res
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
-static inline int run_grid(int64_t n) {
-  const int64_t ctas = ((n + kWarpTile - 1) / kWarpTile + kRunWarps - 1) / kRunWarps;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * 6));  // 6 CTAs of 33 KB shared memory per SM
-}
-
-// The run kernels want 6 CTAs x 33 KB of shared memory per SM: ask for the largest shared-memory carveout (once per
-// instantiation; one process drives one GPU).
+// Persistent-style grid for the run kernels: exactly the number of CTAs that are resident at once (occupancy x SMs),
+// each warp striding over the warp-tiles; the shared-memory carveout is raised to the maximum first (the kernels want
+// up to 6 CTAs x 33 KB per SM).  Cached per kernel instantiation (one process drives one GPU).
 template <typename K>
-static void prefer_shared(K kernel) {
-  static bool done = false;
-  if (!done) {
+static int run_grid(K kernel, int64_t n) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    done = true;
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kRunThreads, 0) != cudaSuccess || v < 1) v = 4;
+    per_sm = v;
   }
+  const int64_t ctas = ((n + kWarpTile - 1) / kWarpTile + kRunWarps - 1) / kRunWarps;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm));
 }
 
 template <int MODEL, int NREF>
 static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
   if (variant == 2) {
-    prefer_shared(vote_runs_kernel<MODEL, NREF, NREF == 1>);
-    vote_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(a, acc);
+    auto k = vote_runs_kernel<MODEL, NREF, NREF == 1>;
+    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, acc);
   }
   else if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
   else vote_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, acc, iwe);
@@ -713,9 +823,15 @@ static void launch_vote_m(int n_ref, int variant, int grid, cudaStream_t s, cons
 }
 template <int MODEL, int NREF>
 static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
-  if (gvar == 2) {
-    prefer_shared(grad_runs_kernel<MODEL, NREF, NREF == 1>);
-    grad_runs_kernel<MODEL, NREF, NREF == 1><<<run_grid(a.n), kRunThreads, 0, s>>>(a, gq, gm);
+  if (gvar == 2) {  // batches of 4
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 4>;
+    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
+  } else if (gvar == 3) {  // batches of 8
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 8>;
+    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
+  } else if (gvar == 4) {  // sequential walk
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 0>;
+    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
   }
   else if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
   else grad_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, gq, gm);
