@@ -320,6 +320,24 @@ def run_b200(args) -> None:
             k1 = time_kernel(lambda: L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, None, None, None, stream))
             k3 = time_kernel(lambda: L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), stream))
             obj.plan.set_stage_mask(7)
+            # in-situ stage times of one eager iteration (L2 flushed before the iteration only): K1+fold | cost | K3
+            spec_p = C.byref(obj.spec)
+            stage_ms = np.zeros(3)
+            for rep in range(13):
+                flush_l2()
+                e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                fused = C.c_int32(0)
+                e[0].record()
+                L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, None, spec_p, C.byref(fused), stream)
+                e[1].record()
+                L.call("cmax_objective_cost", obj.plan.handle, spec_p, None, obj._ws_ptr, fused.value, 1, cost_buf.data_ptr(), stream)
+                e[2].record()
+                L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), stream)
+                e[3].record()
+                torch.cuda.synchronize()
+                if rep >= 3:
+                    stage_ms += [e[i].elapsed_time(e[i + 1]) for i in range(3)]
+            stage_ms /= 10
             # algorithmic bytes per launch (DESIGN.md "Kernels"): K1 = 16 B/event + flow read 8 HW + IWE write 4 HW;
             # K3 = 16 B/event + flow read 8 HW + dL/dIWE read 4 HW + gradient write 8 HW
             kernels = {"vote_fused_kernel(K1)": {"ms": k1, "bytes": 16 * n + 12 * HWp},
@@ -332,7 +350,8 @@ def run_b200(args) -> None:
             dom = max(kernels, key=lambda k: kernels[k]["ms"])
             roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
-                    "kernels": kernels, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
+                    "kernels": kernels, "stages_in_situ_ms": {"vote(K1+fold)": stage_ms[0], "cost(combine+gq)": stage_ms[1],
+                                                              "grad(memset+K3)": stage_ms[2]}, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
         else:
             roof = {"bound": "hbm", "kernel": "whole CM iteration (per GPU)", "achieved": step_gbps, "peak": peak, "unit": "GB/s",
                     "frac": step_gbps / peak, "traffic": None, "peak_source": peak_src}

@@ -113,6 +113,13 @@ __device__ __forceinline__ void warp_ref(const float4 e, int src, int HW, const 
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// predicated form: no branch, so the walk of consecutive events stays one basic block the scheduler can interleave
+__device__ __forceinline__ void red_add_v4_if(bool pred, float4* addr, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n}" ::"l"(addr), "f"(a), "f"(b),
+      "f"(c), "f"(d), "r"((unsigned)pred)
+      : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------ K1
 // VARIANT 0: one red.v4 per event per reference time into the per-corner accumulators.
@@ -477,13 +484,13 @@ __device__ __forceinline__ void vote_step(const float4 e, VoteState<NREF>& st, c
     float w[4];
     vote_weights(v, w);
     const int c = vote_cell(v, a.Hp, a.Wp);
-    if (c != st.cell[r]) {
-      if (st.cell[r] >= 0) red_add_v4(acc + r * a.cells + st.cell[r], st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
-      st.cell[r] = c;
-      st.w0[r] = w[0]; st.w1[r] = w[1]; st.w2[r] = w[2]; st.w3[r] = w[3];
-    } else {
-      st.w0[r] += w[0]; st.w1[r] += w[1]; st.w2[r] += w[2]; st.w3[r] += w[3];
-    }
+    const bool same = c == st.cell[r];
+    red_add_v4_if(!same && st.cell[r] >= 0, acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+    st.cell[r] = c;
+    st.w0[r] = w[0] + (same ? st.w0[r] : 0.f);
+    st.w1[r] = w[1] + (same ? st.w1[r] : 0.f);
+    st.w2[r] = w[2] + (same ? st.w2[r] : 0.f);
+    st.w3[r] = w[3] + (same ? st.w3[r] : 0.f);
   }
 }
 

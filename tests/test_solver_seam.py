@@ -1,0 +1,148 @@
+"""The solver seam: `B200CostMixin.calculate_cost` against (a) the reference's own composition of warp -> IWE -> cost
+(restated below from src/solver/patch_contrast_base.py:273-352, running on the drop-in CUDA operator classes) and
+(b) the CPU oracle; plus an end-to-end scipy L-BFGS-B loop driven by the fused objective."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+class _ReferenceSeam:
+    """What the reference solver does per objective call (src/solver/patch_contrast_base.py:273-352), verbatim in
+    structure; it is the base class the mixin is mixed into in these tests."""
+
+    def __init__(self, B, image_shape, cost_name, sigma, cost_with_weight=None, pad=0):
+        self.iwe_config = {"method": "bilinear_vote", "blur_sigma": sigma}
+        self.imager = B.EventImageConverter(image_shape, outer_padding=pad)
+        self.warper = B.Warp(image_shape, normalize_t=True)
+        if cost_name == "hybrid":
+            from event_based_optical_flow_b200.costs import HybridCost
+            self.cost_func = HybridCost("minimize", cost_with_weight, store_history=True, precision="64")
+        else:
+            self.cost_func = B.cost_functions[cost_name](direction="minimize", store_history=True, precision="64")
+
+    def calculate_cost(self, events, warp, motion_model, coarse_flow=None, save_intermediate_result=True):
+        return self.cost_func.calculate(self.get_arg_for_cost(events, warp, motion_model, coarse_flow))
+
+    def get_arg_for_cost(self, events, warp, motion_model, coarse_flow=None):
+        arg = {"omit_boundary": True, "clip": True}
+        keys = self.cost_func.required_keys
+        m, s = self.iwe_config["method"], self.iwe_config["blur_sigma"]
+        if "orig_iwe" in keys:
+            arg["orig_iwe"] = self.imager.create_iwe(events, m, s)
+        if "iwe" in keys or "backward_iwe" in keys or "backward_warp" in keys:
+            ev, _ = self.warper.warp_event(events, warp, motion_model, direction="first")
+            iwe = self.imager.create_iwe(ev, m, s)
+            arg.update({"iwe": iwe, "backward_iwe": iwe, "backward_warp": ev})
+        if "forward_iwe" in keys or "forward_warp" in keys:
+            ev, _ = self.warper.warp_event(events, warp, motion_model, direction="last")
+            arg.update({"forward_iwe": self.imager.create_iwe(ev, m, s), "forward_warp": ev})
+        if "middle_iwe" in keys:
+            ev, _ = self.warper.warp_event(events, warp, motion_model, direction="middle")
+            arg["middle_iwe"] = self.imager.create_iwe(ev, m, s)
+        if "flow" in keys:
+            arg["flow"] = coarse_flow
+        return arg
+
+
+def _problem(seed=3, H=48, W=64, n=30000, patch=(4, 4)):
+    rng = np.random.default_rng(seed)
+    ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
+    motion = rng.uniform(-5, 5, (2,) + patch)
+    return torch.from_numpy(ev).double(), torch.from_numpy(motion).double(), (H, W)
+
+
+def _dense(motion, image_shape):
+    """A differentiable tile-flow -> dense-flow map standing in for the reference's upsample (torch ops, unchanged caller code)."""
+    return torch.nn.functional.interpolate(motion[None], size=image_shape, mode="bilinear", align_corners=False)[0]
+
+
+@pytest.mark.parametrize("cost_name,sigma", [("image_variance", 0), ("gradient_magnitude", 1),
+                                             ("multi_focal_normalized_gradient_magnitude", 1), ("hybrid", 1)])
+def test_mixin_matches_reference_composition_and_oracle(cost_name, sigma):
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.solver import B200CostMixin
+    dev = torch.device("cuda:0")
+    ev, motion, shape = _problem()
+    weights = {"multi_focal_normalized_gradient_magnitude": 1.0, "total_variation": 0.01}
+
+    class Fast(B200CostMixin, _ReferenceSeam):
+        pass
+
+    ref = _ReferenceSeam(B, shape, cost_name, sigma, weights)
+    fast = Fast(B, shape, cost_name, sigma, weights)
+    evd = ev.to(dev).requires_grad_()  # the reference hands the solver float64 events with requires_grad (pyramid.py:186)
+    out = {}
+    for tag, slv in (("ref", ref), ("fast", fast)):
+        m = motion.clone().to(dev).requires_grad_(True)
+        loss = slv.calculate_cost(evd, _dense(m, shape), "dense-flow", m)
+        (g,) = torch.autograd.grad(loss, m)
+        out[tag] = (float(loss), g.cpu().numpy())
+        assert loss.dtype == torch.float64
+    assert abs(out["fast"][0] - out["ref"][0]) <= 2e-5 * abs(out["ref"][0])
+    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-4 * np.linalg.norm(out["ref"][1])
+    hist = fast.cost_func.get_history()
+    assert len(hist["loss"]) == 1
+    # the oracle (fp32, same dtype as the kernels) for the contrast part
+    if cost_name != "hybrid":
+        m = motion.clone().float().requires_grad_(True)
+        val = O.objective(ev.float(), _dense(m, shape), shape, motion_model="dense-flow", cost=cost_name, sigma=float(sigma))
+        (g,) = torch.autograd.grad(val, m)
+        assert abs(out["fast"][0] - float(val)) <= 2e-5 * abs(float(val))
+        assert np.linalg.norm(out["fast"][1] - g.numpy()) <= 2e-4 * np.linalg.norm(g.numpy())
+    # second call re-uses the resident plan
+    n_plans = len(fast._b200_plans)
+    fast.calculate_cost(evd, _dense(motion.to(dev), shape), "dense-flow", motion.to(dev))
+    assert len(fast._b200_plans) == n_plans == 1
+
+
+def test_use_b200_operators_swaps_seam_objects():
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.solver import use_b200_operators
+    slv = _ReferenceSeam(B, (20, 30), "image_variance", 0, pad=2)
+    slv.cost_func.direction = "minimize"
+    use_b200_operators(slv)
+    assert isinstance(slv.imager, B.EventImageConverter) and slv.imager.image_size == (24, 34)
+    assert isinstance(slv.warper, B.Warp) and slv.warper.normalize_t is True
+    assert slv.cost_func.name == "image_variance"
+
+
+def test_scipy_lbfgs_recovers_translation():
+    """Events generated by a known 2-dof translation; scipy L-BFGS-B on the fused objective must recover it
+    (the outer optimiser stays scipy, as in src/solver/scipy_autograd/scipy_minimize.py:100-115)."""
+    import scipy.optimize
+    import event_based_optical_flow_b200 as B
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    H, W, n_edges, per_edge = 64, 80, 12, 1500
+    # a few straight "edges" moving with constant velocity: x(t) = x0 - theta * dt  (so warping by +theta*dt realigns them)
+    theta_true = np.array([6.0, -9.0])
+    t = rng.uniform(0, 1, n_edges * per_edge)
+    x0 = np.repeat(rng.uniform(12, H - 12, n_edges), per_edge) + rng.normal(0, 0.15, n_edges * per_edge)
+    y0 = np.repeat(rng.uniform(15, W - 15, n_edges), per_edge) + rng.normal(0, 0.15, n_edges * per_edge)
+    ev = np.stack([x0 - theta_true[0] * t, y0 - theta_true[1] * t, t, np.ones_like(t)], 1).astype(np.float32)
+    ev = ev[np.argsort(ev[:, 2])]
+    obj = B.ContrastObjective(torch.from_numpy(ev).to(dev), (H, W), cost="image_variance", motion_model="2d-translation", order="asis")
+
+    def fun(x):
+        val, grad = obj.value_and_grad(torch.tensor(x, dtype=torch.float32, device=dev))
+        return float(val), grad.double().cpu().numpy()
+
+    def fun_oracle(x):
+        val, grad = O.objective_value_and_grad(torch.from_numpy(ev), torch.tensor(x, dtype=torch.float32), (H, W),
+                                               motion_model="2d-translation", cost="image_variance")
+        return float(val), grad.double().numpy()
+
+    # multi-start as the reference does with its random / grid initialisation (patch_contrast_base.py / pyramid.py)
+    starts = ([0.0, 0.0], [4.0, -6.0], [8.0, -12.0])
+    best = min((scipy.optimize.minimize(fun, x0_, jac=True, method="L-BFGS-B") for x0_ in starts), key=lambda r: r.fun)
+    best_oracle = min((scipy.optimize.minimize(fun_oracle, x0_, jac=True, method="L-BFGS-B") for x0_ in starts), key=lambda r: r.fun)
+    # the contrast maximum sits within a pixel of the generating motion (the bilinear vote favours integer alignment) ...
+    assert np.allclose(best.x, theta_true, atol=1.0), best.x
+    assert best.fun < 0.5 * fun(np.zeros(2))[0]
+    # ... and the same loop driven by the CPU oracle ends in the same place
+    assert abs(best.fun - best_oracle.fun) <= 1e-3 * abs(best_oracle.fun), (best.fun, best_oracle.fun)
+    assert np.allclose(best.x, best_oracle.x, atol=5e-2), (best.x, best_oracle.x)
