@@ -181,7 +181,7 @@ def run_b200(args) -> None:
     group = dist.group.WORLD if world > 1 else None
     t_range = global_time_range(ev, group)
     obj = ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow", sigma=0.0, order=args.order,
-                            process_group=group, t_range=t_range)
+                            process_group=group, t_range=t_range, exchange=args.exchange)
     obj.plan.set_variant(args.vote_variant, args.grad_variant)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
@@ -196,14 +196,19 @@ def run_b200(args) -> None:
     grad_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
     flow_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
 
-    # one CM iteration; single GPU: captured once in a CUDA graph (7 nodes), multi GPU: eager (NCCL in between)
+    # one CM iteration, captured once in a CUDA graph: single GPU = 4 kernel nodes; sharded = 5 kernels + 2 NCCL
+    # all-reduces (NCCL is capturable; every rank captures the same sequence)
     graph = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            obj.step_into(flow_buf, cost_buf, grad_buf)
+            for _ in range(3):
+                obj.step_into(flow_buf, cost_buf, grad_buf)
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             obj.step_into(flow_buf, cost_buf, grad_buf)
@@ -365,7 +370,7 @@ def run_b200(args) -> None:
 
         clocks = sampler.finish() if sampler else None
         # K1 vote, fold(+variance+cost), gradient pictures, K3 grad; the eager 3-stage path adds the combine kernel
-        per_step_kernels = 4 + (0 if graph is not None else 1)
+        per_step_kernels = (4 if graph is not None else 5) if world == 1 else (6 if args.exchange == 'peer' else 5)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -374,20 +379,30 @@ def run_b200(args) -> None:
                        "image": [H, W], "flow": "smooth (16x16 grid upsampled), |f|<=10px, fresh per step",
                        "event_order": args.order, "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
                        "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
-                       "parallelism": f"events sharded x{world}, allreduce(IWE)+allreduce(grad)" if world > 1 else "single GPU"},
+                       "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
+                                       ("NCCL all-reduce" if args.exchange == "nccl" else "NVLink peer-memory kernels + in-stream barriers"))
+                       if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host pinned flow -> device, value_and_grad through the Python API, cost+grad -> host, sync; events resident"},
             "gpu_launches": per_step_kernels * args.steps,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        # a live CUDA graph that holds NCCL kernels keeps the communicator busy: release it before tearing NCCL down
+        if graph is not None:
+            graph.reset()
+            del graph
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
+    if os.environ.get("BENCH_DEBUG_DUMP_AFTER"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_DEBUG_DUMP_AFTER"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -397,6 +412,7 @@ def main():
     ap.add_argument("--vote-variant", type=int, default=2)
     ap.add_argument("--grad-variant", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer", help="multi-GPU: NCCL all-reduce or NVLink peer-memory kernels")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -12,6 +12,7 @@ from . import _build
 
 MAX_REFS = 4
 MAX_BINS = 64
+MAX_PEERS = 8
 
 OK, ERR_ARG, ERR_CUDA, ERR_SOURCE_OOB, ERR_WORKSPACE = 0, 1, 2, 3, 4
 MOTION = {"dense-flow": 0, "dense-flow-voxel": 1, "2d-translation": 2, "rigid-optical-flow": 2}
@@ -60,6 +61,11 @@ _SIGNATURES = {
     "cmax_objective_cost": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _i, _p, _p]),
     "cmax_objective_grad": (_i, [_p, _i, _p, _p, _p, _p]),
     "cmax_objective": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, _p, _p, _p]),
+    "cmax_objective_iwe_offset": (_sz, [_p]),
+    "cmax_objective_full_iwe_offset": (_sz, [_p]),
+    "cmax_objective_reduce_iwe": (_i, [_p, C.POINTER(CostSpec), C.POINTER(_p), _i, _p, _p, _p, C.POINTER(C.c_int32), _p]),
+    "cmax_objective_cost_after_reduce": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _i, _p, _p]),
+    "cmax_reduce_peers": (_i, [C.POINTER(_p), _i, _i64, _p, _p]),
     "cmax_combine_cost": (_i, [_p, _i, _i, _i, _p, C.POINTER(_f), _i, _i, _p, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -19,7 +19,7 @@ namespace cmax {
 
 // ------------------------------------------------------------------------------------------------ workspace
 struct ObjLayout {
-  size_t off_acc, off_iwe, off_blur, off_statacc, off_stats, off_affine, off_misc, off_gxy, off_g, off_g2, off_gq, total;
+  size_t off_acc, off_iwe, off_iwe_full, off_blur, off_statacc, off_stats, off_affine, off_misc, off_gxy, off_g, off_g2, off_gq, total;
   int64_t cells, HW;
 };
 
@@ -33,6 +33,7 @@ static ObjLayout obj_layout(int Hp, int Wp) {
   size_t off = 0;
   L.off_acc = off;     off = align256(off + (size_t)R * L.cells * sizeof(float4));
   L.off_iwe = off;     off = align256(off + (size_t)R * L.HW * sizeof(float));
+  L.off_iwe_full = off; off = align256(off + (size_t)R * L.HW * sizeof(float));  // peer exchange: the summed IWE (off_iwe stays the partial peers read)
   L.off_blur = off;    off = align256(off + (size_t)R * L.HW * sizeof(float));
   L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
   L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
@@ -793,6 +794,60 @@ __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __res
   if (threadIdx.x < 2) out[threadIdx.x] = (float)acc2[threadIdx.x];
 }
 
+// ------------------------------------------------------------------------------------------------ peer reductions
+// Multi-GPU exchange over NVLink peer memory (the workspaces live in symmetric memory, one process per GPU): instead
+// of an NCCL all-reduce followed by the statistics kernels, ONE kernel on every rank reads all ranks' partial IWEs
+// (P2P loads, summed in rank order so every rank gets the bit-identical image), writes the full IWE and -- exactly like
+// the single-GPU fold -- accumulates the variance sums and lets its last CTA evaluate the scalar cost.
+struct PeerPtrs {
+  const float* p[CMAX_MAX_PEERS];
+  int n;
+};
+
+__global__ void __launch_bounds__(kStatBlock) peer_iwe_kernel(PeerPtrs peers, float* __restrict__ iwe, int Hp, int Wp, int want_var, int omit,
+                                                              StatAcc* __restrict__ sacc, double* __restrict__ stats, int want_combine,
+                                                              CombineDev cd, unsigned int* __restrict__ ctas_done) {
+  __shared__ double red[kStatBlock / 32];
+  __shared__ bool all_done;
+  const int img = blockIdx.y;
+  const int64_t HW = (int64_t)Hp * Wp;
+  double s = 0.0, q = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + img * HW + p);  // L2-coherent: the data was written by another GPU
+    iwe[img * HW + p] = v;
+    const int rr = (int)(p / Wp), c = (int)(p % Wp);
+    if (want_var && (!omit || (rr >= 1 && rr <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
+      s += (double)v;
+      q += (double)v * (double)v;
+    }
+  }
+  if (want_var) {
+    const int64_t M = omit ? (int64_t)(Hp - 2) * (Wp - 2) : HW;
+    variance_commit(s, q, M, gridDim.x, &sacc[img], stats + 4 * img, red);
+    if (want_combine) {
+      if (threadIdx.x == 0) {
+        __threadfence();
+        all_done = (atomicAdd(ctas_done, 1u) == gridDim.x * gridDim.y - 1);
+      }
+      __syncthreads();
+      if (all_done && threadIdx.x == 0) {
+        __threadfence();
+        combine_eval(stats, cd);
+      }
+    }
+  }
+}
+
+// out[i] = sum over ranks of peers[r][i], rank order (the motion-gradient exchange)
+__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs peers, int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + i);
+    out[i] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dispatch
 // Persistent-style grid for the run kernels: exactly the number of CTAs that are resident at once (occupancy x SMs),
 // each warp striding over the warp-tiles; the shared-memory carveout is raised to the maximum first (the kernels want
@@ -899,7 +954,7 @@ static int check_spec(const char* fn, const cmax_cost_spec* spec, int n_ref) {
 
 // ------------------------------------------------------------------------------------------------ stages
 struct Ws {
-  float4* acc; float* iwe; float* blur; StatAcc* sacc; double* stats; float* affine; unsigned int* ctas_done;
+  float4* acc; float* iwe; float* iwe_full; float* blur; StatAcc* sacc; double* stats; float* affine; unsigned int* ctas_done;
   float* G; float* G2; float4* gq; char* stats_ws; double* acc2;
 };
 
@@ -908,6 +963,7 @@ static Ws carve(void* workspace, const ObjLayout& L) {
   Ws w;
   w.acc = reinterpret_cast<float4*>(ws + L.off_acc);
   w.iwe = reinterpret_cast<float*>(ws + L.off_iwe);
+  w.iwe_full = reinterpret_cast<float*>(ws + L.off_iwe_full);
   w.blur = reinterpret_cast<float*>(ws + L.off_blur);
   w.sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
   w.stats = reinterpret_cast<double*>(ws + L.off_stats);
@@ -976,17 +1032,18 @@ static CombineDev combine_for(const cmax_plan* p, const cmax_cost_spec* spec, co
 // Stage 2.  combined != 0: the scalar combination already ran inside the fold (cmax_objective's fast path).
 // zero_grad (may be NULL): motion-gradient buffer to clear inside the gradient-picture kernel.
 static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int stats_fused,
-                      int combined, int want_grad, double* d_cost, float* zero_grad, size_t n_zero, cmax_stream_t stream) {
+                      int combined, int want_grad, double* d_cost, float* zero_grad, size_t n_zero, cmax_stream_t stream,
+                      bool use_full = false) {
   const ObjLayout L = obj_layout(p->Hp, p->Wp);
   const Ws w = carve(workspace, L);
   cudaStream_t s = as_stream(stream);
   const int n_ref = p->n_ref;
   const bool blurred = spec->sigma > 0.f;
-  const float* img = w.iwe;
+  const float* img = use_full ? w.iwe_full : w.iwe;
   int rc;
   if (!(p->stage_mask & 4)) return CMAX_OK;
   if (blurred) {
-    rc = cmax_blur3(w.iwe, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
+    rc = cmax_blur3(img, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
     if (rc) return rc;
     img = w.blur;
   }
@@ -1117,6 +1174,74 @@ int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motio
   if (rc) return rc;
   if (grad_motion != nullptr) rc = grad_stage(plan, motion_model, motion, workspace, grad_motion, zero_in_gq ? 1 : 0, as_stream(stream));
   return rc;
+}
+
+int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
+                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && h_peer_iwe != nullptr && d_cost != nullptr, "cmax_objective_reduce_iwe: NULL argument");
+  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_objective_reduce_iwe: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
+  int rc = check_spec("cmax_objective_reduce_iwe", spec, plan->n_ref);
+  if (rc) return rc;
+  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_reduce_iwe: normalised costs need d_orig_stat");
+  const cmax_plan* p = plan;
+  const ObjLayout L = obj_layout(p->Hp, p->Wp);
+  const Ws w = carve(workspace, L);
+  cudaStream_t s = as_stream(stream);
+  PeerPtrs peers;
+  peers.n = n_peers;
+  for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_iwe[r] : nullptr;
+  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_objective_reduce_iwe: peer %d IWE pointer is NULL", r);
+  const bool fuse = can_fuse_stats(spec);
+  if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
+  CombineDev cd;
+  memset(&cd, 0, sizeof(cd));
+  if (fuse) cd = combine_for(p, spec, d_orig_stat, d_cost, w);
+  dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), p->n_ref);
+  peer_iwe_kernel<<<grid, kStatBlock, 0, s>>>(peers, w.iwe_full, p->Hp, p->Wp, fuse ? 1 : 0, fuse ? spec->omit_boundary : 0, w.sacc, w.stats,
+                                              fuse ? 1 : 0, cd, w.ctas_done);
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  if (combined) *combined = fuse ? 1 : 0;
+  return CMAX_OK;
+}
+
+int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
+                                     int combined, int want_grad, double* d_cost, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost_after_reduce: NULL argument");
+  int rc = check_spec("cmax_objective_cost_after_reduce", spec, plan->n_ref);
+  if (rc) return rc;
+  CMAX_REQUIRE(!combined || can_fuse_stats(spec), "cmax_objective_cost_after_reduce: combined set for a spec that cannot fuse");
+  return cost_stage(plan, spec, d_orig_stat, workspace, combined, combined, want_grad, d_cost, nullptr, 0, stream, true);
+}
+
+int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, cmax_stream_t stream) {
+  CMAX_REQUIRE(h_peer_bufs != nullptr && out != nullptr, "cmax_reduce_peers: NULL argument");
+  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_reduce_peers: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
+  CMAX_REQUIRE(n >= 0, "cmax_reduce_peers: n must be >= 0");
+  PeerPtrs peers;
+  peers.n = n_peers;
+  for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_bufs[r] : nullptr;
+  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_reduce_peers: peer %d pointer is NULL", r);
+  if (n > 0) {
+    peer_sum_kernel<<<image_grid(n), 256, 0, as_stream(stream)>>>(peers, n, out);
+    CMAX_CUDA_CHECK(cudaGetLastError());
+  }
+  return CMAX_OK;
+}
+
+size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan) {
+  if (plan == nullptr) {
+    set_error("cmax_objective_full_iwe_offset: plan is NULL");
+    return 0;
+  }
+  return obj_layout(plan->Hp, plan->Wp).off_iwe_full;
+}
+
+size_t cmax_objective_iwe_offset(const cmax_plan_t* plan) {
+  if (plan == nullptr) {
+    set_error("cmax_objective_iwe_offset: plan is NULL");
+    return 0;
+  }
+  return obj_layout(plan->Hp, plan->Wp).off_iwe;
 }
 
 }  // extern "C"

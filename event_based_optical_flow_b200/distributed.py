@@ -43,7 +43,8 @@ def global_time_range(events_shard: torch.Tensor, group=None) -> Tuple[float, fl
 
 
 def make_sharded_objective(events_shard: torch.Tensor, image_size, group=None, **kw):
-    """ContrastObjective over this rank's shard with the global time range and the two all-reduces wired in."""
+    """ContrastObjective over this rank's shard with the global time range and the two exchanges wired in
+    (`exchange="nccl"` or `"peer"`, see ContrastObjective)."""
     from .objective import ContrastObjective
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     t_range = global_time_range(events_shard, group)

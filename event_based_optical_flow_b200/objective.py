@@ -145,14 +145,17 @@ class ContrastObjective:
     Args mirror the reference's configuration vocabulary: `motion_model` as in `Warp.warp_event`
     (src/warp.py:156-199), `cost` a key of `costs.functions` (src/costs/__init__.py:35), `sigma` = `iwe.blur_sigma`,
     `direction` = the cost direction (src/costs/base.py:20-25), `outer_padding` as in `EventImageConverter`.
-    `process_group`: events are sharded over its ranks; the partial IWE and the partial gradient are summed with one
-    NCCL all-reduce each.
+    `process_group`: events are sharded over its ranks; the partial IWE and the partial gradient are summed once each per
+    evaluation, either with an NCCL all-reduce (`exchange="nccl"`) or over NVLink peer memory
+    (`exchange="peer"`: the workspaces live in torch symmetric memory, an in-stream barrier replaces the collective
+    launch, and one kernel per exchange reads all ranks' partial buffers -- the IWE one also computes the cost).
     """
 
     def __init__(self, events: Union[torch.Tensor, EventPlan], image_size: Tuple[int, int], *, cost: str = "image_variance",
                  motion_model: str = "dense-flow", sigma: float = 0.0, omit_boundary: bool = True, direction: str = "minimize",
                  outer_padding=0, n_bins: Optional[int] = None, order: str = "pixel", process_group=None,
-                 t_range: Optional[Tuple[float, float]] = None, orig_events: Optional[torch.Tensor] = None):
+                 t_range: Optional[Tuple[float, float]] = None, orig_events: Optional[torch.Tensor] = None,
+                 exchange: str = "nccl"):
         if cost not in COST_TABLE:
             raise KeyError(f"cost {cost!r} has no fused CUDA form; available: {sorted(COST_TABLE)}")
         if motion_model not in _lib.MOTION:
@@ -166,6 +169,9 @@ class ContrastObjective:
         self.stat, self.form = stat, form
         self.ref_keys = tuple(k for k, _ in refs)
         self.group = process_group
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"exchange must be 'nccl' or 'peer', got {exchange}")
+        self.exchange = exchange if process_group is not None else "nccl"
         if orig_events is None and isinstance(events, torch.Tensor):
             orig_events = events
         self.plan = events if isinstance(events, EventPlan) else EventPlan(events, image_size, outer_padding, order, t_range)
@@ -189,9 +195,13 @@ class ContrastObjective:
         self.omit_boundary = bool(omit_boundary)
         self.motion_shape = _motion_shape(motion_model, self.image_size, self.n_bins)
         self.lib = _lib.load()
+        self._symm = None
         with torch.cuda.device(self.device):
             nbytes = self.lib.cmax_objective_workspace_bytes(self.plan.handle, C.byref(self.spec))
-            self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            if self.exchange == "peer":
+                self._setup_peer_exchange(nbytes)
+            else:
+                self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
         self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
         with torch.cuda.device(self.device):
             _lib.call("cmax_objective_workspace_init", self.plan.handle, self._ws_ptr, _stream_ptr())
@@ -200,6 +210,33 @@ class ContrastObjective:
         if form != "plain":
             self._orig_stat = self._orig_statistic(orig_events)
         self._iwe_view = None
+
+    # -- NVLink peer-memory exchange: the workspace and the partial-gradient buffer are symmetric allocations
+    def _setup_peer_exchange(self, nbytes: int) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+        world = torch.distributed.get_world_size(self.group)
+        if world > _lib.MAX_PEERS:
+            raise ValueError(f"exchange='peer' supports up to {_lib.MAX_PEERS} ranks (one NVLink domain), got {world}")
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass  # newer torch enables it implicitly
+        n_motion = int(np.prod(self.motion_shape))
+        grad_off = (nbytes + 255) // 256 * 256
+        total = grad_off + 4 * n_motion + 256
+        self._ws = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
+        if self._ws.data_ptr() % 256 != 0:
+            raise RuntimeError("symmetric allocation is not 256-byte aligned")
+        self._ws.zero_()
+        self._symm = symm_mem.rendezvous(self._ws, self.group)
+        bases = [int(p) for p in self._symm.buffer_ptrs]
+        iwe_off = int(self.lib.cmax_objective_iwe_offset(self.plan.handle))
+        self._peer_iwe = (C.c_void_p * world)(*[b + iwe_off for b in bases])
+        self._peer_grad = (C.c_void_p * world)(*[b + grad_off for b in bases])
+        self._n_peers = world
+        self._grad_part = self._ws[grad_off:grad_off + 4 * n_motion].view(torch.float32).view(self.motion_shape)
+        torch.cuda.synchronize(self.device)
+        torch.distributed.barrier(group=self.group)
 
     # -- the statistic of the un-warped IWE (normalised costs); constant per optimize(), so computed once
     #    (the reference recomputes it on every call, src/solver/patch_contrast_base.py:295-301)
@@ -236,27 +273,45 @@ class ContrastObjective:
             Hp, Wp = self.padded_size
             k = len(self.directions)
             self._iwe_view = self._ws[off:off + 4 * k * Hp * Wp].view(torch.float32).view(k, Hp, Wp)
-        if self.group is not None:
+        if self.group is not None and self.exchange == "nccl":
             torch.distributed.all_reduce(self._iwe_view, group=self.group)
         return fused.value
+
+    def _evaluate(self, m: torch.Tensor, cost: torch.Tensor, grad: Optional[torch.Tensor], stream: int) -> None:
+        """Stages 1-3 with the exchange of this objective in between; writes cost[0] and (if given) grad.  No host sync."""
+        model = _lib.MOTION[self.motion_model]
+        orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
+        want = 1 if grad is not None else 0
+        fused = self._vote(m, stream)
+        if self.exchange == "peer":
+            self._symm.barrier(channel=0)  # every rank's partial IWE is complete and visible
+            combined = C.c_int32(0)
+            _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
+                      self._ws_ptr, cost.data_ptr(), C.byref(combined), stream)
+            _lib.call("cmax_objective_cost_after_reduce", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, combined.value,
+                      want, cost.data_ptr(), stream)
+            if grad is not None:
+                _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
+                self._symm.barrier(channel=1)
+                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), stream)
+            else:
+                # value only: still close the evaluation with a barrier, so that no rank overwrites its partial IWE (next
+                # evaluation's fold) while a slower peer is reading it
+                self._symm.barrier(channel=1)
+            return
+        _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, fused, want, cost.data_ptr(), stream)
+        if grad is not None:
+            _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, grad.data_ptr(), stream)
+            if self.group is not None:
+                torch.distributed.all_reduce(grad, group=self.group)
 
     def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
         """-> (cost: 0-dim float64 CUDA tensor, grad: fp32 tensor shaped like motion or None).  No host sync."""
         m = self._check_motion(motion)
         with torch.cuda.device(self.device):
-            stream = _stream_ptr()
-            fused = self._vote(m, stream)
-            orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
             cost = torch.empty(1, dtype=torch.float64, device=self.device)
-            _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, fused, 1 if want_grad else 0,
-                      cost.data_ptr(), stream)
-            grad = None
-            if want_grad:
-                grad = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device)
-                _lib.call("cmax_objective_grad", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr,
-                          grad.data_ptr(), stream)
-                if self.group is not None:
-                    torch.distributed.all_reduce(grad, group=self.group)
+            grad = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device) if want_grad else None
+            self._evaluate(m, cost, grad, _stream_ptr())
         if self._post_sign < 0:
             cost = -cost
             grad = -grad if grad is not None else None
@@ -266,19 +321,29 @@ class ContrastObjective:
         return self.value_and_grad(motion, want_grad=False)[0]
 
     def iwe(self, motion: torch.Tensor) -> torch.Tensor:
-        """The (un-blurred) IWE stack [n_ref, Hp, Wp] for `motion` (a copy)."""
+        """The (un-blurred) IWE stack [n_ref, Hp, Wp] for `motion` (a copy; summed over all ranks when sharded)."""
         m = self._check_motion(motion)
         with torch.cuda.device(self.device):
             self._vote(m, _stream_ptr())
-        return self._iwe_view.clone()
+            out = self._iwe_view.clone()
+            if self.group is not None and self.exchange == "peer":
+                torch.distributed.all_reduce(out, group=self.group)  # off the hot path: plain NCCL
+        return out
 
     def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
-        """Allocation-free evaluation into caller buffers (CUDA-graph capturable, single GPU only)."""
-        if self.group is not None or self._post_sign < 0:
-            raise RuntimeError("step_into is the single-GPU graph path (minimize / maximize directions)")
+        """Allocation-free evaluation into caller buffers (fp32 motion, float64[1] cost, fp32 gradient), CUDA-graph
+        capturable.  Single GPU: one `cmax_objective` call.  Sharded: the three stages with the two NCCL all-reduces in
+        between (NCCL collectives are capturable, every rank captures the same sequence)."""
+        if self._post_sign < 0:
+            raise RuntimeError("step_into supports the minimize / maximize directions")
         orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
-        _lib.call("cmax_objective", self.plan.handle, _lib.MOTION[self.motion_model], motion_f32.data_ptr(), C.byref(self.spec), orig,
-                  self._ws_ptr, cost_out.data_ptr(), grad_out.data_ptr(), _stream_ptr())
+        model = _lib.MOTION[self.motion_model]
+        stream = _stream_ptr()
+        if self.group is None:
+            _lib.call("cmax_objective", self.plan.handle, model, motion_f32.data_ptr(), C.byref(self.spec), orig, self._ws_ptr,
+                      cost_out.data_ptr(), grad_out.data_ptr(), stream)
+            return
+        self._evaluate(motion_f32, cost_out, grad_out, stream)
 
     def __call__(self, motion: torch.Tensor) -> torch.Tensor:
         """Autograd-aware scalar in motion's dtype: drop-in for the reference's `calculate_cost` result."""

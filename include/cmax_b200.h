@@ -32,6 +32,7 @@ extern "C" {
 #define CMAX_ABI_VERSION 1
 #define CMAX_MAX_REFS 4   /* reference times fused into one event pass (first / middle / last / one more) */
 #define CMAX_MAX_BINS 64  /* time bins of a flow voxel */
+#define CMAX_MAX_PEERS 8  /* GPUs of one NVLink domain whose partial images one kernel sums */
 
 typedef void* cmax_stream_t;
 
@@ -204,6 +205,25 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
 int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
                    const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion /* NULL = value only */,
                    cmax_stream_t stream);
+/* ---- multi-GPU exchange over NVLink peer memory (workspaces in symmetric memory) ----
+ * After cmax_objective_vote on every rank and a cross-GPU barrier, every rank calls cmax_objective_reduce_iwe with the
+ * device pointers of ALL ranks' partial IWE stacks (h_peer_iwe[r] = peer r's workspace base + cmax_objective_iwe_offset,
+ * a host array of device pointers, rank order): one kernel sums them (P2P loads, rank order -> bit-identical on all
+ * ranks) into this rank's FULL-IWE buffer (workspace + cmax_objective_full_iwe_offset; the partial stays intact because
+ * peers are reading it) and, when the spec allows (VARIANCE, sigma == 0), also accumulates the
+ * statistics and evaluates the scalar cost -- the collective and the cost are ONE kernel.  *combined reports whether
+ * it did; pass it to cmax_objective_cost_after_reduce, which runs what is left of stage 2 (blur / statistics / cost when
+ * not combined, then the gradient pictures).  The partial gradient is exchanged the same way: cmax_objective_grad into
+ * a symmetric buffer, barrier, cmax_reduce_peers. */
+size_t cmax_objective_iwe_offset(const cmax_plan_t* plan);
+size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan);
+int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
+                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, cmax_stream_t stream);
+int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
+                                     int combined, int want_grad, double* d_cost, cmax_stream_t stream);
+/* out[i] = sum_r h_peer_bufs[r][i], rank order (n floats). */
+int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, cmax_stream_t stream);
+
 /* Scalar combination of per-image statistics (exposed for the modular cost plugins).
  * d_stats: n_ref x 4 doubles from cmax_image_stats; h_weights: n_ref multi-focal weights (NULL = 1).
  * explicit_grad != 0: the affine pair is (d cost/d stat_r, 0); otherwise (VARIANCE) it is
