@@ -183,6 +183,7 @@ def run_b200(args) -> None:
     obj = ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow", sigma=0.0, order=args.order,
                             process_group=group, t_range=t_range, exchange=args.exchange)
     obj.plan.set_variant(args.vote_variant, args.grad_variant)
+    compact = obj.plan.set_compact(not args.no_compact)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
 
@@ -377,7 +378,7 @@ def run_b200(args) -> None:
             "data": "synthetic",
             "config": {"workload": "config2: 5M events per GPU, 260x346 dense flow, variance cost+grad", "events_per_gpu": n,
                        "image": [H, W], "flow": "smooth (16x16 grid upsampled), |f|<=10px, fresh per step",
-                       "event_order": args.order, "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
+                       "event_order": args.order, "packed_event_bytes": 8 if compact else 16, "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
                        "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
                                        ("NCCL all-reduce" if args.exchange == "nccl" else "NVLink peer-memory kernels + in-stream barriers"))
@@ -412,6 +413,7 @@ def main():
     ap.add_argument("--vote-variant", type=int, default=2)
     ap.add_argument("--grad-variant", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
     ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer", help="multi-GPU: NCCL all-reduce or NVLink peer-memory kernels")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
     args = ap.parse_args()

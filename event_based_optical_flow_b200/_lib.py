@@ -55,6 +55,7 @@ _SIGNATURES = {
     "cmax_plan_set_refs": (_i, [_p, C.POINTER(Ref), _i, _i, _p]),
     "cmax_plan_set_variant": (_i, [_p, _i, _i]),
     "cmax_plan_set_stage_mask": (_i, [_p, _i]),
+    "cmax_plan_set_compact": (_i, [_p, _i, C.POINTER(C.c_int32), _p]),
     "cmax_objective_workspace_bytes": (_sz, [_p, C.POINTER(CostSpec)]),
     "cmax_objective_workspace_init": (_i, [_p, _p, _p]),
     "cmax_objective_vote": (_i, [_p, _i, _p, _p, C.POINTER(_p), C.POINTER(CostSpec), C.POINTER(C.c_int32), _p]),

@@ -49,9 +49,11 @@ struct Vote {
 };
 
 // Exact floor of v as float AND int without the quarter-rate conversion pipe (FRND / F2I): adding 1.5*2^23 rounds v to
-// the nearest integer in the mantissa; one compare-and-decrement turns round-to-nearest into floor.  Valid for
-// |v| < 2^22; anything beyond (or NaN) is reported as not representable -- such coordinates are far outside any image.
-__device__ __forceinline__ bool floor_exact(float v, float& fl, int& i) {
+// the nearest integer in the mantissa; one compare-and-decrement turns round-to-nearest into floor.  Exact for
+// |v| < 2^22.  Beyond that (or for NaN / inf) the integer is garbage, but provably far outside any image: the biased
+// float is then not within [1.5*2^23 - 2^22, 1.5*2^23 + 2^22), so `i` has magnitude >= 2^22 (NaN/inf give ~8.8e8) and
+// every bounds check against an image of fewer than 2^22 rows / columns rejects it -- no explicit range guard needed.
+__device__ __forceinline__ void floor_exact(float v, float& fl, int& i) {
   const float C = 12582912.0f;  // 1.5 * 2^23
   const float t = __fadd_rn(v, C);
   i = __float_as_int(t) - 0x4B400000;
@@ -60,22 +62,21 @@ __device__ __forceinline__ bool floor_exact(float v, float& fl, int& i) {
     fl = __fsub_rn(fl, 1.0f);
     i -= 1;
   }
-  return fabsf(v) < 4194304.0f;
 }
 
-constexpr int kFarOutside = -0x40000000;  // row/col of an event that can touch no pixel
-
 // i = floor(x' + 1e-6), f = x' - i          src/event_image_converter.py:340-345
+// For coordinates beyond +-2^22 row / col are garbage-but-out-of-range and fx / fy meaningless: callers must not use the
+// fractions of an event that fails its bounds checks.
 __device__ __forceinline__ Vote vote_geometry(float xw, float yw, int pad_h, int pad_w) {
   float flx, fly;
   int ix, iy;
-  const bool okx = floor_exact(__fadd_rn(xw, 1e-6f), flx, ix);
-  const bool oky = floor_exact(__fadd_rn(yw, 1e-6f), fly, iy);
+  floor_exact(__fadd_rn(xw, 1e-6f), flx, ix);
+  floor_exact(__fadd_rn(yw, 1e-6f), fly, iy);
   Vote v;
   v.fx = __fsub_rn(xw, flx);
   v.fy = __fsub_rn(yw, fly);
-  v.row = (okx && oky) ? ix + pad_h : kFarOutside;
-  v.col = (okx && oky) ? iy + pad_w : kFarOutside;
+  v.row = ix + pad_h;
+  v.col = iy + pad_w;
   return v;
 }
 

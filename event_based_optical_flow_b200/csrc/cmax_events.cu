@@ -111,12 +111,15 @@ __device__ __forceinline__ bool source_pixel(float x, float y, int H, int W, int
 __global__ void __launch_bounds__(256) validate_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
                                                        int32_t* __restrict__ status) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  bool bad = false;
+  bool bad = false, frac = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     int r, c;
-    bad |= !source_pixel(__ldg(ev + i * stride), __ldg(ev + i * stride + 1), H, W, &r, &c);
+    const float x = __ldg(ev + i * stride), y = __ldg(ev + i * stride + 1);
+    bad |= !source_pixel(x, y, H, W, &r, &c);
+    frac |= (x != truncf(x)) || (y != truncf(y));  // bit 1: fractional coordinates -> no compact packing
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
+  if (__any_sync(0xffffffffu, frac) && (threadIdx.x & 31) == 0) atomicOr(status, 2);
 }
 
 // Sort key: tile id (TILE order: events of a tile keep their time order) or tile id * 1024 + pixel inside the tile
@@ -148,22 +151,27 @@ __global__ void __launch_bounds__(256) gather_events_kernel(const float* __restr
 // stored at slot tile*256 + k*32 + lane, so that a coalesced 16-byte load by lane `lane` at step k returns that lane's
 // k-th consecutive event (see cmax_plan.cuh).  dt exactly as the kernels compute it (src/warp.py:254-258).
 // Slots past n (the last tile's padding) are zero-filled.
+template <bool COMPACT>
 __global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ ev, int64_t n, int64_t slots, int H, int W,
-                                                     const cmax_time_params_t* __restrict__ tp, int with_dt, float4* __restrict__ out) {
+                                                     const cmax_time_params_t* __restrict__ tp, int with_dt, void* __restrict__ out) {
   const float ref = tp->ref[0], period = tp->period[0];
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < slots; j += step) {
     float4 o = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    uint2 oc = make_uint2(0u, 0u);
     if (j < n) {
       const float4 e = ev[j];
       int r, c;
       source_pixel(e.x, e.y, H, W, &r, &c);
       const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
       o = make_float4(e.x, e.y, tz, __int_as_float(r * W + c));
+      oc = make_uint2(__float_as_uint(tz), ((unsigned)r << 16) | (unsigned)c);
     }
     const int64_t tile = j / kWarpTile;
     const int within = (int)(j % kWarpTile), lane = within / kRunE, k = within % kRunE;
-    out[tile * kWarpTile + k * 32 + lane] = o;
+    const int64_t slot = tile * kWarpTile + k * 32 + lane;
+    if (COMPACT) reinterpret_cast<uint2*>(out)[slot] = oc;
+    else reinterpret_cast<float4*>(out)[slot] = o;
   }
 }
 
@@ -277,6 +285,7 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   CMAX_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "cmax_plan_create: n must be in [0, 2^31), got %lld", (long long)n);
   CMAX_REQUIRE(H > 0 && W > 0 && pad_h >= 0 && pad_w >= 0, "cmax_plan_create: bad image size %dx%d pad %d,%d", H, W, pad_h, pad_w);
   CMAX_REQUIRE((int64_t)(H + 2 * pad_h + 1) * (W + 2 * pad_w + 1) < (int64_t)1 << 28, "cmax_plan_create: image too large");
+  CMAX_REQUIRE(H + 2 * pad_h < (1 << 22) && W + 2 * pad_w < (1 << 22), "cmax_plan_create: image sides must be < 2^22 (exact-floor range)");
   CMAX_REQUIRE(ev_stride >= 3, "cmax_plan_create: ev_stride must be >= 3");
   CMAX_REQUIRE(n == 0 || events != nullptr, "cmax_plan_create: events is NULL");
   CMAX_REQUIRE(order >= CMAX_ORDER_ASIS && order <= CMAX_ORDER_PIXEL, "cmax_plan_create: unknown event order %d", order);
@@ -303,7 +312,7 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   p->d_minmax = reinterpret_cast<float*>(ws + L.off_minmax);
   p->d_status = reinterpret_cast<int32_t*>(ws + L.off_status);
   p->events = events;
-  p->packed = reinterpret_cast<float4*>(ws + L.off_packed);
+  p->packed = ws + L.off_packed;
   p->order = CMAX_ORDER_ASIS;
   p->stage_mask = 7;
   p->vote_variant = 2;
@@ -334,12 +343,14 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   }
   PLAN_CHECK(cudaMemcpyAsync(&h_status, p->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   PLAN_CHECK(cudaStreamSynchronize(s));
-  if (h_status != 0) {
+  if (h_status & 1) {
     set_error("cmax_plan_create: an event's pixel (x=row, y=col) lies outside the %dx%d image (or is NaN); "
               "the reference's torch.gather raises here (src/warp.py:305-307)", H, W);
     rc = CMAX_ERR_SOURCE_OOB;
     goto fail;
   }
+  p->compact_ok = (!(h_status & 2) && H <= 65535 && W <= 65535) ? 1 : 0;
+  p->compact = p->compact_ok;
   p->t_min = h_mm[0];
   p->t_max = h_mm[1];
 
@@ -411,10 +422,32 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
-  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 2, "cmax_plan_set_variant: vote_variant must be 0, 1 or 2");
+  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 3, "cmax_plan_set_variant: vote_variant must be in [0,3]");
   CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 4, "cmax_plan_set_variant: grad_variant must be in [0,4]");
   plan->vote_variant = vote_variant;
   plan->grad_variant = grad_variant;
+  return CMAX_OK;
+}
+
+int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cmax_stream_t stream) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_compact: plan is NULL");
+  const int want = (enable && plan->compact_ok) ? 1 : 0;
+  if (want != plan->compact) {
+    plan->compact = want;
+    // re-pack with the reference times already on the device
+    if (plan->n > 0) {
+      const int64_t slots = packed_slots(plan->n);
+      const int grid = (int)std::min<int64_t>(kNumSMs * 8, (slots + 255) / 256);
+      if (want)
+        repack_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
+                                                                  plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
+      else
+        repack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
+                                                                   plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
+      CMAX_CUDA_CHECK(cudaGetLastError());
+    }
+  }
+  if (h_compact) *h_compact = plan->compact;
   return CMAX_OK;
 }
 
@@ -435,8 +468,12 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
   if (plan->n > 0) {
     const int64_t slots = packed_slots(plan->n);
     const int grid = (int)std::min<int64_t>(kNumSMs * 8, (slots + 255) / 256);
-    repack_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H, plan->W,
-                                                        plan->d_params, plan->packed_has_dt, plan->packed);
+    if (plan->compact)
+      repack_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
+                                                                plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
+    else
+      repack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
+                                                                 plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
     CMAX_CUDA_CHECK(cudaGetLastError());
   }
   return CMAX_OK;

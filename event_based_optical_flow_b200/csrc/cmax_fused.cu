@@ -51,7 +51,8 @@ static ObjLayout obj_layout(int Hp, int Wp) {
 // ------------------------------------------------------------------------------------------------ per-event math
 struct FusedArgs {
   const float4* ev;
-  const float4* packed;  // the plan's (x, y, dt|t, src) copy, read by the run kernels
+  const void* packed;    // the plan's packed copy (16-byte or compact 8-byte events), read by the run kernels
+  int compact;
   int64_t n;
   int H, W, Hp, Wp, pad_h, pad_w;
   const float* motion;
@@ -220,6 +221,10 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(float4* __restrict__ a
         combine_eval(stats, cd);
       }
     }
+  } else if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 64) {
+    // statistics not fused here: leave the 256-byte statistics block clean for whoever accumulates next
+    // (the peer IWE reduction of the multi-GPU path), instead of a memset node
+    reinterpret_cast<unsigned int*>(sacc)[threadIdx.x] = 0u;
   }
 }
 
@@ -362,9 +367,11 @@ __global__ void __launch_bounds__(256) grad_fused_kernel(FusedArgs a, const floa
 // shared memory): the copy of tile i+1 is in flight while tile i is walked, the walk reads its events with
 // conflict-free LDS.128, and no thread ever issues a global load for an event.
 // Correct for ANY event order -- an unordered stream just degenerates to one flush per event.
+// When every event has integer pixel coordinates (what a sensor delivers; checked by the plan) the packed copy uses
+// 8 bytes per event -- (dt|t, row<<16|col) -- halving the DRAM stream and the shared-memory landing zone, which doubles
+// the number of resident warps.
 constexpr int kRunThreads = 128;
 constexpr int kRunWarps = kRunThreads / 32;
-constexpr uint32_t kTileBytes = kWarpTile * sizeof(float4);  // 4096
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -390,12 +397,47 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-struct alignas(128) TilePipe {  // one per warp
-  float4 buf[2][kWarpTile];
+// The two packed-event formats (cmax_plan.cuh).  `key` identifies the source pixel for change detection; `src()` turns
+// it into the flat pixel index (only needed when the key changes).
+template <bool COMPACT>
+struct PackedEv;
+template <>
+struct PackedEv<false> {  // (x, y, dt|t, bits(src)) : 16 bytes, any coordinates
+  static constexpr uint32_t kTileBytes = kWarpTile * 16;
+  __device__ static __forceinline__ void get(const void* buf, int k, int lane, float& x, float& y, float& tz, int& key) {
+    const float4 e = reinterpret_cast<const float4*>(buf)[k * 32 + lane];
+    x = e.x; y = e.y; tz = e.z; key = __float_as_int(e.w);
+  }
+  __device__ static __forceinline__ int key_of(const void* buf, int k, int lane) {
+    return __float_as_int(reinterpret_cast<const float4*>(buf)[k * 32 + lane].w);
+  }
+  __device__ static __forceinline__ int src(int key, int W) { return key; }
+};
+template <>
+struct PackedEv<true> {  // (dt|t, row<<16|col) : 8 bytes, integer pixel coordinates (what an event camera delivers)
+  static constexpr uint32_t kTileBytes = kWarpTile * 8;
+  __device__ static __forceinline__ void get(const void* buf, int k, int lane, float& x, float& y, float& tz, int& key) {
+    const uint2 u = reinterpret_cast<const uint2*>(buf)[k * 32 + lane];
+    tz = __uint_as_float(u.x);
+    key = (int)u.y;
+    // exact small-int -> float without the conversion pipe: 2^23 + v has v in its mantissa
+    x = __fsub_rn(__uint_as_float(0x4B000000u | (u.y >> 16)), 8388608.0f);
+    y = __fsub_rn(__uint_as_float(0x4B000000u | (u.y & 0xFFFFu)), 8388608.0f);
+  }
+  __device__ static __forceinline__ int key_of(const void* buf, int k, int lane) {
+    return (int)reinterpret_cast<const uint2*>(buf)[k * 32 + lane].y;
+  }
+  __device__ static __forceinline__ int src(int key, int W) { return (int)((unsigned)key >> 16) * W + (key & 0xFFFF); }
+};
+
+template <uint32_t BYTES>
+struct alignas(128) TilePipe {  // one per warp: double-buffered landing zone of the TMA bulk copies
+  unsigned char buf[2][BYTES];
   uint64_t bar[2];
 };
 
-__device__ __forceinline__ void pipe_init(TilePipe& p, int lane) {
+template <uint32_t BYTES>
+__device__ __forceinline__ void pipe_init(TilePipe<BYTES>& p, int lane) {
   if (lane == 0) {
     mbar_init(&p.bar[0], 1);
     mbar_init(&p.bar[1], 1);
@@ -404,10 +446,11 @@ __device__ __forceinline__ void pipe_init(TilePipe& p, int lane) {
   }
   __syncwarp();
 }
-__device__ __forceinline__ void pipe_issue(TilePipe& p, int stage, const float4* __restrict__ packed, int64_t tile, int lane) {
+template <uint32_t BYTES>
+__device__ __forceinline__ void pipe_issue(TilePipe<BYTES>& p, int stage, const void* __restrict__ packed, int64_t tile, int lane) {
   if (lane == 0) {
-    mbar_expect_tx(&p.bar[stage], kTileBytes);
-    bulk_g2s(p.buf[stage], packed + tile * kWarpTile, kTileBytes, &p.bar[stage]);
+    mbar_expect_tx(&p.bar[stage], BYTES);
+    bulk_g2s(p.buf[stage], static_cast<const unsigned char*>(packed) + tile * BYTES, BYTES, &p.bar[stage]);
   }
 }
 
@@ -428,33 +471,34 @@ __device__ __forceinline__ RefRegs<NREF> load_refs(const cmax_time_params_t* __r
   return rr;
 }
 
-// One packed event, one reference time -> (x', y', dt, bin).  PRE_DT: e.z already is the normalised dt of reference 0.
+// One packed event, one reference time -> (x', y', dt, bin).  PRE_DT: tz already is the normalised dt of reference 0.
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void warp_packed(const float4 e, int src, int HW, const float* __restrict__ motion, const RefRegs<NREF>& rr,
-                                            const TimeSmem& s, int r, float f0, float f1, float& xw, float& yw, float& dt, int& bin) {
-  dt = PRE_DT ? e.z : __fdiv_rn(__fsub_rn(e.z, rr.ref[r]), rr.period[r]);
+__device__ __forceinline__ void warp_packed(float x, float y, float tz, int src, int HW, const float* __restrict__ motion,
+                                            const RefRegs<NREF>& rr, const TimeSmem& s, int r, float f0, float f1, float& xw, float& yw,
+                                            float& dt, int& bin) {
+  dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
   bin = 0;
   if (MODEL == CMAX_MOTION_2DOF) {
-    xw = warp_plus(e.x, dt, f0);
-    yw = warp_plus(e.y, dt, f1);
+    xw = warp_plus(x, dt, f0);
+    yw = warp_plus(y, dt, f1);
   } else if (MODEL == CMAX_MOTION_DENSE) {
-    xw = warp_minus(e.x, dt, f0);
-    yw = warp_minus(e.y, dt, f1);
+    xw = warp_minus(x, dt, f0);
+    yw = warp_minus(y, dt, f1);
   } else {
     bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
-    xw = e.x;
-    yw = e.y;
+    xw = x;
+    yw = y;
     if (bin >= 0) {
       const float* f = motion + (int64_t)bin * 2 * HW;
-      xw = warp_minus(e.x, dt, __ldg(f + src));
-      yw = warp_minus(e.y, dt, __ldg(f + HW + src));
+      xw = warp_minus(x, dt, __ldg(f + src));
+      yw = warp_minus(y, dt, __ldg(f + HW + src));
     }
   }
 }
 
 // accumulator cell of a vote, or -1 when the event touches no pixel
 __device__ __forceinline__ int vote_cell(const Vote& v, int Hp, int Wp) {
-  const bool inside = (unsigned)(v.row + 1) <= (unsigned)Hp && (unsigned)(v.col + 1) <= (unsigned)Wp;
+  const bool inside = ((unsigned)(v.row + 1) <= (unsigned)Hp) & ((unsigned)(v.col + 1) <= (unsigned)Wp);
   return inside ? (v.row + 1) * (Wp + 1) + (v.col + 1) : -1;
 }
 
@@ -463,24 +507,29 @@ template <int NREF>
 struct VoteState {
   int cell[NREF];
   float w0[NREF], w1[NREF], w2[NREF], w3[NREF];
-  int src_prev;
+  int key, src;  // source pixel of the current run: packed key and flat index
   float f0, f1;
 };
 
-template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void vote_step(const float4 e, VoteState<NREF>& st, const FusedArgs& a, int HW, const RefRegs<NREF>& rr,
-                                          const TimeSmem& s, float4* __restrict__ acc) {
-  const int src = __float_as_int(e.w);
-  if (MODEL == CMAX_MOTION_DENSE && src != st.src_prev) {
-    st.f0 = __ldg(a.motion + src);
-    st.f1 = __ldg(a.motion + HW + src);
-    st.src_prev = src;
+template <int MODEL, int NREF, bool PRE_DT, bool COMPACT>
+__device__ __forceinline__ void vote_step(float x, float y, float tz, int key, VoteState<NREF>& st, const FusedArgs& a, int HW,
+                                          const RefRegs<NREF>& rr, const TimeSmem& s, float4* __restrict__ acc) {
+  // a source pixel changes in ~1 of 50 events per lane: skip the whole block unless some lane of the warp needs it
+  if (MODEL != CMAX_MOTION_2DOF && __any_sync(0xffffffffu, key != st.key)) {
+    if (key != st.key) {
+      st.key = key;
+      st.src = PackedEv<COMPACT>::src(key, a.W);
+      if (MODEL == CMAX_MOTION_DENSE) {
+        st.f0 = __ldg(a.motion + st.src);
+        st.f1 = __ldg(a.motion + HW + st.src);
+      }
+    }
   }
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float xw, yw, dt;
     int bin;
-    warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
+    warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
     const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
     float w[4];
     vote_weights(v, w);
@@ -488,23 +537,26 @@ __device__ __forceinline__ void vote_step(const float4 e, VoteState<NREF>& st, c
     const bool same = c == st.cell[r];
     red_add_v4_if(!same && st.cell[r] >= 0, acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
     st.cell[r] = c;
-    st.w0[r] = w[0] + (same ? st.w0[r] : 0.f);
-    st.w1[r] = w[1] + (same ? st.w1[r] : 0.f);
-    st.w2[r] = w[2] + (same ? st.w2[r] : 0.f);
-    st.w3[r] = w[3] + (same ? st.w3[r] : 0.f);
+    const float keep = same ? 1.0f : 0.0f;  // acc * 1 + w and acc * 0 + w are exact: one select instead of four
+    st.w0[r] = fmaf(st.w0[r], keep, w[0]);
+    st.w1[r] = fmaf(st.w1[r], keep, w[1]);
+    st.w2[r] = fmaf(st.w2[r], keep, w[2]);
+    st.w3[r] = fmaf(st.w3[r], keep, w[3]);
   }
 }
 
-template <int MODEL, int NREF, bool PRE_DT>
+// FB: batch the flow loads of a full tile (dense model) so that they share one L2 round trip -- costs 16 registers.
+template <int MODEL, int NREF, bool PRE_DT, bool COMPACT, bool FB>
 __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, float4* __restrict__ acc) {
+  using PE = PackedEv<COMPACT>;
   __shared__ TimeSmem s;
-  __shared__ TilePipe pipes[kRunWarps];
+  __shared__ TilePipe<PE::kTileBytes> pipes[kRunWarps];
   if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
   if (a.zero256 != nullptr && blockIdx.x == 0 && threadIdx.x < 64) a.zero256[threadIdx.x] = 0u;  // StatAcc block + CTA counter
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
   const int lane = threadIdx.x & 31;
-  TilePipe& pipe = pipes[threadIdx.x >> 5];
+  TilePipe<PE::kTileBytes>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
   float th0 = 0.f, th1 = 0.f;
   if (MODEL == CMAX_MOTION_2DOF) {
@@ -521,53 +573,58 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
     __syncwarp();  // every lane is done with the other buffer (walked in the previous iteration)
     if (tile + n_warps < t_end) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
     mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
-    const float4* mine = pipe.buf[stage] + lane;
+    const void* buf = pipe.buf[stage];
     VoteState<NREF> st;
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
       st.cell[r] = -1;
       st.w0[r] = st.w1[r] = st.w2[r] = st.w3[r] = 0.f;
     }
-    st.src_prev = -1;
+    st.key = -1;
+    st.src = 0;
     st.f0 = th0;
     st.f1 = th1;
+    float x, y, tz;
+    int key;
     if ((tile + 1) * kWarpTile <= a.n) {  // full tile (warp-uniform)
-      if constexpr (MODEL == CMAX_MOTION_DENSE) {
-        // batched: all flow loads of the tile's kRunE events are in flight together (one L2 latency per tile, not one
-        // per source-pixel change), then the walk runs out of registers
+      if constexpr (MODEL == CMAX_MOTION_DENSE && FB) {
         float f0[kRunE], f1[kRunE];
-        bool nw[kRunE];
         int prev = -1;
 #pragma unroll
         for (int k = 0; k < kRunE; ++k) {
-          const int src = __float_as_int(mine[k * 32].w);
-          nw[k] = src != prev;
-          prev = src;
-          if (nw[k]) {
+          const int kk = PE::key_of(buf, k, lane);
+          if (kk != prev) {
+            const int src = PE::src(kk, a.W);
             f0[k] = __ldg(a.motion + src);
             f1[k] = __ldg(a.motion + HW + src);
+          } else {
+            f0[k] = f0[k > 0 ? k - 1 : 0];
+            f1[k] = f1[k > 0 ? k - 1 : 0];
           }
+          prev = kk;
         }
 #pragma unroll
         for (int k = 0; k < kRunE; ++k) {
-          if (k > 0 && !nw[k]) {
-            f0[k] = f0[k - 1];
-            f1[k] = f1[k - 1];
-          }
-          const float4 e = mine[k * 32];
+          PE::get(buf, k, lane, x, y, tz, key);
+          st.key = key;  // flow already fetched
           st.f0 = f0[k];
           st.f1 = f1[k];
-          st.src_prev = __float_as_int(e.w);
-          vote_step<MODEL, NREF, PRE_DT>(e, st, a, HW, rr, s, acc);
+          vote_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, acc);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < kRunE; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
+        for (int k = 0; k < kRunE; ++k) {
+          PE::get(buf, k, lane, x, y, tz, key);
+          vote_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, acc);
+        }
       }
     } else {
       const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
       const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
-      for (int k = 0; k < count; ++k) vote_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, acc);
+      for (int k = 0; k < count; ++k) {
+        PE::get(buf, k, lane, x, y, tz, key);
+        vote_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, acc);
+      }
     }
 #pragma unroll
     for (int r = 0; r < NREF; ++r)
@@ -581,36 +638,43 @@ struct GradState {
   static constexpr int NACC = (MODEL == CMAX_MOTION_VOXEL) ? NREF : 1;
   int cell[NREF];
   float d_x0[NREF], d_c0[NREF], d_r[NREF];  // corner differences of the current cell's gradient quad
-  int key[NACC];                            // flat index into gmotion of the row-component slot being accumulated
+  int slot[NACC];                           // flat index into gmotion of the row-component slot being accumulated (-1: none)
   float g0[NACC], g1[NACC];
+  int key, src;  // source pixel of the current run
   float f0, f1;
   double t0, t1;  // 2-dof
 };
 
 template <int MODEL, int NREF>
 __device__ __forceinline__ void grad_flush(GradState<MODEL, NREF>& st, int q, int HW, float* __restrict__ gmotion) {
-  if (st.key[q] >= 0) {
-    atomicAdd(gmotion + st.key[q], st.g0[q]);
-    atomicAdd(gmotion + st.key[q] + HW, st.g1[q]);
+  if (st.slot[q] >= 0) {
+    atomicAdd(gmotion + st.slot[q], st.g0[q]);
+    atomicAdd(gmotion + st.slot[q] + HW, st.g1[q]);
   }
 }
 
-template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>& st, const FusedArgs& a, int HW, const RefRegs<NREF>& rr,
-                                          const TimeSmem& s, const float4* __restrict__ gq, float* __restrict__ gmotion) {
-  const int src = __float_as_int(e.w);
-  if (MODEL == CMAX_MOTION_DENSE && src != st.key[0]) {  // new source pixel: flush its predecessor, fetch the new flow vector
-    grad_flush<MODEL, NREF>(st, 0, HW, gmotion);
-    st.key[0] = src;
-    st.g0[0] = st.g1[0] = 0.f;
-    st.f0 = __ldg(a.motion + src);
-    st.f1 = __ldg(a.motion + HW + src);
+template <int MODEL, int NREF, bool PRE_DT, bool COMPACT>
+__device__ __forceinline__ void grad_step(float x, float y, float tz, int key, GradState<MODEL, NREF>& st, const FusedArgs& a, int HW,
+                                          const RefRegs<NREF>& rr, const TimeSmem& s, const float4* __restrict__ gq,
+                                          float* __restrict__ gmotion) {
+  if (MODEL != CMAX_MOTION_2DOF && __any_sync(0xffffffffu, key != st.key)) {  // some lane starts a new source pixel
+    if (key != st.key) {
+      st.key = key;
+      st.src = PackedEv<COMPACT>::src(key, a.W);
+      if (MODEL == CMAX_MOTION_DENSE) {  // flush the predecessor's gradient, fetch the new flow vector
+        grad_flush<MODEL, NREF>(st, 0, HW, gmotion);
+        st.slot[0] = st.src;
+        st.g0[0] = st.g1[0] = 0.f;
+        st.f0 = __ldg(a.motion + st.src);
+        st.f1 = __ldg(a.motion + HW + st.src);
+      }
+    }
   }
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float xw, yw, dt;
     int bin;
-    warp_packed<MODEL, NREF, PRE_DT>(e, src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
+    warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
     const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
     const int c = vote_cell(v, a.Hp, a.Wp);
     if (c != st.cell[r]) {
@@ -622,8 +686,9 @@ __device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>
       st.d_c0[r] = g.z - g.x;
       st.d_r[r] = (g.w - g.z) - st.d_x0[r];
     }
-    const float dx = fmaf(v.fy, st.d_r[r], st.d_x0[r]);
-    const float dy = fmaf(v.fx, st.d_r[r], st.d_c0[r]);
+    // (the fractions of an event outside the image are meaningless, see vote_geometry: its quad is zero, keep it zero)
+    const float dx = c >= 0 ? fmaf(v.fy, st.d_r[r], st.d_x0[r]) : 0.f;
+    const float dy = c >= 0 ? fmaf(v.fx, st.d_r[r], st.d_c0[r]) : 0.f;
     if (MODEL == CMAX_MOTION_2DOF) {
       st.t0 += (double)(dt * dx);
       st.t1 += (double)(dt * dy);
@@ -631,10 +696,10 @@ __device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>
       st.g0[0] = fmaf(-dt, dx, st.g0[0]);
       st.g1[0] = fmaf(-dt, dy, st.g1[0]);
     } else {
-      const int kk = bin >= 0 ? bin * 2 * HW + src : -1;
-      if (kk != st.key[r]) {
+      const int kk = bin >= 0 ? bin * 2 * HW + st.src : -1;
+      if (kk != st.slot[r]) {
         grad_flush<MODEL, NREF>(st, r, HW, gmotion);
-        st.key[r] = kk;
+        st.slot[r] = kk;
         st.g0[r] = st.g1[r] = 0.f;
       }
       st.g0[r] = fmaf(-dt, dx, st.g0[r]);
@@ -647,32 +712,29 @@ __device__ __forceinline__ void grad_step(const float4 e, GradState<MODEL, NREF>
 // KB consecutive events: (A) all flow loads, (B) per reference time all warps / cells, then all gradient-quad gathers,
 // (C) the accumulation with one flush per source-pixel change.  Two exposed L2 latencies per batch instead of up to
 // 2*KB; KB trades registers (occupancy) against memory-level parallelism.
-template <int NREF, bool PRE_DT, int KB>
-__device__ __forceinline__ void grad_tile_dense(const float4* __restrict__ mine, GradState<CMAX_MOTION_DENSE, NREF>& st, const FusedArgs& a,
-                                                int HW, const RefRegs<NREF>& rr, const float4* __restrict__ gq,
+template <int NREF, bool PRE_DT, bool COMPACT, int KB>
+__device__ __forceinline__ void grad_tile_dense(const void* __restrict__ buf, int lane, GradState<CMAX_MOTION_DENSE, NREF>& st,
+                                                const FusedArgs& a, int HW, const RefRegs<NREF>& rr, const float4* __restrict__ gq,
                                                 float* __restrict__ gmotion) {
+  using PE = PackedEv<COMPACT>;
 #pragma unroll
   for (int b = 0; b < kRunE; b += KB) {
     float f0[KB], f1[KB];
-    int srcs[KB];
-    bool nw[KB];
+    int keys[KB];
     int prev = -1;
 #pragma unroll
     for (int k = 0; k < KB; ++k) {  // (A)
-      srcs[k] = __float_as_int(mine[(b + k) * 32].w);
-      nw[k] = srcs[k] != prev;
-      prev = srcs[k];
-      if (nw[k]) {
-        f0[k] = __ldg(a.motion + srcs[k]);
-        f1[k] = __ldg(a.motion + HW + srcs[k]);
+      keys[k] = PE::key_of(buf, b + k, lane);
+      if (keys[k] != prev) {
+        const int src = PE::src(keys[k], a.W);
+        f0[k] = __ldg(a.motion + src);
+        f1[k] = __ldg(a.motion + HW + src);
+      } else {
+        f0[k] = f0[k > 0 ? k - 1 : 0];
+        f1[k] = f1[k > 0 ? k - 1 : 0];
       }
+      prev = keys[k];
     }
-#pragma unroll
-    for (int k = 1; k < KB; ++k)
-      if (!nw[k]) {
-        f0[k] = f0[k - 1];
-        f1[k] = f1[k - 1];
-      }
     float gx[KB], gy[KB];  // sum over reference times of -dt * dL/dx', -dt * dL/dy' per event
 #pragma unroll
     for (int k = 0; k < KB; ++k) gx[k] = gy[k] = 0.f;
@@ -684,9 +746,11 @@ __device__ __forceinline__ void grad_tile_dense(const float4* __restrict__ mine,
       int cprev = -2;
 #pragma unroll
       for (int k = 0; k < KB; ++k) {  // (B)
-        const float4 e = mine[(b + k) * 32];
-        const float dt = PRE_DT ? e.z : __fdiv_rn(__fsub_rn(e.z, rr.ref[r]), rr.period[r]);
-        const Vote v = vote_geometry(warp_minus(e.x, dt, f0[k]), warp_minus(e.y, dt, f1[k]), a.pad_h, a.pad_w);
+        float x, y, tz;
+        int key;
+        PE::get(buf, b + k, lane, x, y, tz, key);
+        const float dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
+        const Vote v = vote_geometry(warp_minus(x, dt, f0[k]), warp_minus(y, dt, f1[k]), a.pad_h, a.pad_w);
         fx[k] = v.fx;
         fy[k] = v.fy;
         dts[k] = dt;
@@ -700,15 +764,18 @@ __device__ __forceinline__ void grad_tile_dense(const float4* __restrict__ mine,
         else if (k > 0 && cs[k] == cs[k - 1]) g[k] = g[k - 1];
         const float d_x0 = g[k].y - g[k].x, d_c0 = g[k].z - g[k].x;
         const float d_r = (g[k].w - g[k].z) - d_x0;
-        gx[k] = fmaf(-dts[k], fmaf(fy[k], d_r, d_x0), gx[k]);
-        gy[k] = fmaf(-dts[k], fmaf(fx[k], d_r, d_c0), gy[k]);
+        if (cs[k] >= 0) {  // fractions of an out-of-image event are meaningless (vote_geometry)
+          gx[k] = fmaf(-dts[k], fmaf(fy[k], d_r, d_x0), gx[k]);
+          gy[k] = fmaf(-dts[k], fmaf(fx[k], d_r, d_c0), gy[k]);
+        }
       }
     }
 #pragma unroll
     for (int k = 0; k < KB; ++k) {
-      if (srcs[k] != st.key[0]) {
+      if (keys[k] != st.key) {
         grad_flush<CMAX_MOTION_DENSE, NREF>(st, 0, HW, gmotion);
-        st.key[0] = srcs[k];
+        st.key = keys[k];
+        st.slot[0] = PE::src(keys[k], a.W);
         st.g0[0] = st.g1[0] = 0.f;
       }
       st.g0[0] += gx[k];
@@ -717,16 +784,17 @@ __device__ __forceinline__ void grad_tile_dense(const float4* __restrict__ mine,
   }
 }
 
-template <int MODEL, int NREF, bool PRE_DT, int KB>
+template <int MODEL, int NREF, bool PRE_DT, bool COMPACT, int KB>
 __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, const float4* __restrict__ gq, float* __restrict__ gmotion) {
+  using PE = PackedEv<COMPACT>;
   __shared__ TimeSmem s;
-  __shared__ TilePipe pipes[kRunWarps];
+  __shared__ TilePipe<PE::kTileBytes> pipes[kRunWarps];
   __shared__ double red2[2][kRunWarps];
   if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
   const int lane = threadIdx.x & 31;
-  TilePipe& pipe = pipes[threadIdx.x >> 5];
+  TilePipe<PE::kTileBytes>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
   GradState<MODEL, NREF> st;
   st.f0 = st.f1 = 0.f;
@@ -737,7 +805,7 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
   }
   const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
-  const int64_t t_end = n_tiles;  // warps stride over all tiles (a contiguous range per CTA measured no better: profiles/)
+  const int64_t t_end = n_tiles;
   if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);
   int it = 0;
   for (int64_t tile = warp0; tile < t_end; tile += n_warps, ++it) {
@@ -745,7 +813,7 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
     __syncwarp();
     if (tile + n_warps < t_end) pipe_issue(pipe, stage ^ 1, a.packed, tile + n_warps, lane);
     mbar_wait(&pipe.bar[stage], (it >> 1) & 1);
-    const float4* mine = pipe.buf[stage] + lane;
+    const void* buf = pipe.buf[stage];
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
       st.cell[r] = -2;
@@ -753,20 +821,30 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
     }
 #pragma unroll
     for (int q = 0; q < GradState<MODEL, NREF>::NACC; ++q) {
-      st.key[q] = -1;
+      st.slot[q] = -1;
       st.g0[q] = st.g1[q] = 0.f;
     }
+    st.key = -1;
+    st.src = 0;
+    float x, y, tz;
+    int key;
     if ((tile + 1) * kWarpTile <= a.n) {
       if constexpr (MODEL == CMAX_MOTION_DENSE && KB > 0) {
-        grad_tile_dense<NREF, PRE_DT, KB>(mine, st, a, HW, rr, gq, gmotion);
+        grad_tile_dense<NREF, PRE_DT, COMPACT, KB>(buf, lane, st, a, HW, rr, gq, gmotion);
       } else {
 #pragma unroll
-        for (int k = 0; k < kRunE; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
+        for (int k = 0; k < kRunE; ++k) {
+          PE::get(buf, k, lane, x, y, tz, key);
+          grad_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, gq, gmotion);
+        }
       }
     } else {
       const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
       const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
-      for (int k = 0; k < count; ++k) grad_step<MODEL, NREF, PRE_DT>(mine[k * 32], st, a, HW, rr, s, gq, gmotion);
+      for (int k = 0; k < count; ++k) {
+        PE::get(buf, k, lane, x, y, tz, key);
+        grad_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, gq, gmotion);
+      }
     }
     if (MODEL != CMAX_MOTION_2DOF) {
 #pragma unroll
@@ -865,13 +943,23 @@ static int run_grid(K kernel, int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm));
 }
 
-template <int MODEL, int NREF>
-static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
-  if (variant == 2) {
-    auto k = vote_runs_kernel<MODEL, NREF, NREF == 1>;
+template <int MODEL, int NREF, bool COMPACT>
+static void launch_vote_runs(int variant, cudaStream_t s, const FusedArgs& a, float4* acc) {
+  if (variant == 3) {  // batched flow loads
+    auto k = vote_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, true>;
+    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, acc);
+  } else {
+    auto k = vote_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, false>;
     k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, acc);
   }
-  else if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
+}
+
+template <int MODEL, int NREF>
+static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
+  if (variant >= 2) {
+    if (a.compact) launch_vote_runs<MODEL, NREF, true>(variant, s, a, acc);
+    else launch_vote_runs<MODEL, NREF, false>(variant, s, a, acc);
+  } else if (variant == 1) vote_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, acc, iwe);
   else vote_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, acc, iwe);
 }
 template <int MODEL>
@@ -883,19 +971,26 @@ static void launch_vote_m(int n_ref, int variant, int grid, cudaStream_t s, cons
     default: launch_vote<MODEL, 4>(variant, grid, s, a, acc, iwe); break;
   }
 }
-template <int MODEL, int NREF>
-static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
+template <int MODEL, int NREF, bool COMPACT>
+static void launch_grad_runs(int gvar, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
   if (gvar == 2) {  // batches of 4
-    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 4>;
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 4>;
     k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
   } else if (gvar == 3) {  // batches of 8
-    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 8>;
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 8>;
     k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
-  } else if (gvar == 4) {  // sequential walk
-    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, 0>;
+  } else {  // sequential walk
+    auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 0>;
     k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
   }
-  else if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
+}
+
+template <int MODEL, int NREF>
+static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
+  if (gvar >= 2) {
+    if (a.compact) launch_grad_runs<MODEL, NREF, true>(gvar, s, a, gq, gm);
+    else launch_grad_runs<MODEL, NREF, false>(gvar, s, a, gq, gm);
+  } else if (gvar == 1 && MODEL == CMAX_MOTION_DENSE) grad_fused_kernel<MODEL, NREF, 1><<<grid, 256, 0, s>>>(a, gq, gm);
   else grad_fused_kernel<MODEL, NREF, 0><<<grid, 256, 0, s>>>(a, gq, gm);
 }
 template <int MODEL>
@@ -920,6 +1015,7 @@ static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   FusedArgs a;
   a.ev = reinterpret_cast<const float4*>(p->events);
   a.packed = p->packed;
+  a.compact = p->compact;
   a.n = p->n;
   a.H = p->H; a.W = p->W; a.Hp = p->Hp; a.Wp = p->Wp; a.pad_h = p->pad_h; a.pad_w = p->pad_w;
   a.motion = motion;
@@ -997,7 +1093,7 @@ static int vote_stage(const cmax_plan* p, int motion_model, const float* motion,
   const int mask = p->stage_mask;
   static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 192, "StatAcc block and the CTA counter share 256 bytes");
   // the 256-byte statistics block is cleared by K1's first CTA when there is one (variant 2), else by a memset
-  const bool k1_clears = fuse && variant == 2 && p->n > 0 && (mask & 2);
+  const bool k1_clears = fuse && variant >= 2 && p->n > 0 && (mask & 2);
   if (k1_clears) a.zero256 = reinterpret_cast<unsigned int*>(w.sacc);
   if (mask & 1) {
     // the per-corner accumulators are left clean by the fold (see fold_kernel) and by cmax_objective_workspace_init
@@ -1192,7 +1288,8 @@ int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spe
   for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_iwe[r] : nullptr;
   for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_objective_reduce_iwe: peer %d IWE pointer is NULL", r);
   const bool fuse = can_fuse_stats(spec);
-  if (fuse) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
+  // the statistics block was left clean by this rank's fold (fold_kernel); variant 1 has no fold
+  if (fuse && p->vote_variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
   CombineDev cd;
   memset(&cd, 0, sizeof(cd));
   if (fuse) cd = combine_for(p, spec, d_orig_stat, d_cost, w);

@@ -278,7 +278,7 @@ int cmax_warp_events_backward(const float* events, int64_t n, int ev_stride, int
 int cmax_vote(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h, int pad_w, int vote,
               float* image, cmax_stream_t stream) {
   CMAX_REQUIRE(n >= 0 && xy_stride >= 2, "cmax_vote: need n >= 0 and xy_stride >= 2");
-  CMAX_REQUIRE(Hp > 0 && Wp > 0 && (int64_t)Hp * Wp < ((int64_t)1 << 30), "cmax_vote: bad image size %dx%d", Hp, Wp);
+  CMAX_REQUIRE(Hp > 0 && Wp > 0 && (int64_t)Hp * Wp < ((int64_t)1 << 30) && Hp < (1 << 22) && Wp < (1 << 22), "cmax_vote: bad image size %dx%d", Hp, Wp);
   CMAX_REQUIRE(image != nullptr && (n == 0 || xy != nullptr), "cmax_vote: NULL pointer");
   CMAX_REQUIRE(vote == CMAX_VOTE_BILINEAR || vote == CMAX_VOTE_COUNT, "cmax_vote: method %d is not implemented", vote);
   cudaStream_t s = as_stream(stream);

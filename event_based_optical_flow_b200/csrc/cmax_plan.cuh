@@ -28,8 +28,12 @@ struct cmax_plan {
   // and tz = normalised dt of reference time 0 when n_ref == 1 (packed_has_dt), else the raw timestamp t.
   // Stored in warp-tile order: event tile*kWarpTile + lane*kRunE + k lives at slot tile*kWarpTile + k*32 + lane, i.e.
   // pre-transposed so that coalesced loads hand every lane kRunE CONSECUTIVE events without a shared-memory pass.
-  float4* packed;
+  void* packed;
   int packed_has_dt;
+  // compact: every event has integer pixel coordinates < 65536, the packed copy is 8 bytes per event
+  // (tz, row<<16|col) in the same warp-tile order; else 16 bytes (x, y, tz, bits(src)).
+  int compact_ok;  // eligibility (from validation)
+  int compact;     // format currently packed
   int64_t n;
   int H, W, pad_h, pad_w, Hp, Wp;
   float t_min, t_max;

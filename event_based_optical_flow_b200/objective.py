@@ -114,6 +114,14 @@ class EventPlan:
     def set_variant(self, vote_variant: int = 0, grad_variant: int = 0) -> None:
         _lib.call("cmax_plan_set_variant", self.handle, int(vote_variant), int(grad_variant))
 
+    def set_compact(self, enable: bool = True) -> bool:
+        """Choose the packed-event format (8-byte compact when the batch allows it, else / or forced 16-byte); returns
+        whether the compact format is in use.  See cmax_plan_set_compact in include/cmax_b200.h."""
+        out = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.call("cmax_plan_set_compact", self.handle, 1 if enable else 0, C.byref(out), _stream_ptr())
+        return bool(out.value)
+
     def set_stage_mask(self, mask: int = 7) -> None:
         """Measurement aid, see cmax_plan_set_stage_mask in include/cmax_b200.h."""
         _lib.call("cmax_plan_set_stage_mask", self.handle, int(mask))

@@ -157,12 +157,20 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
  * each design choice measured against the others):
  *   vote_variant 2 (default) = each thread walks a run of consecutive events and sums the weights of events that
  *                  fall into the same accumulator cell in registers: one red.v4 per cell change;
+ *                3 = the same with the flow loads of a warp-tile batched (16 more registers);
  *                0 = one red.v4 per event into the per-corner accumulators; 1 = four scalar red.f32 per event
  *                  straight into the image (the textbook scatter).
- *   grad_variant 2 (default) = run walk: corner gradients re-gathered only on a cell change, flow gradient summed in
+ *   grad_variant 2 = run walk batched by 4 events (flow loads, then quad gathers, then accumulation), 3 = batched by 8,
+ *                  4 = sequential run walk: corner gradients re-gathered only on a cell change, flow gradient summed in
  *                  registers per source-pixel run; 1 = per-event gather + warp-segmented shuffle reduction over runs
  *                  of equal source pixel (needs CMAX_ORDER_PIXEL, else falls back to 0); 0 = scalar red per event. */
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant);
+/* Packed-event format.  When every event of the batch has integer pixel coordinates (what a sensor delivers; checked at
+ * plan creation) the plan's private copy uses 8 bytes per event -- (dt|t, row<<16|col) -- instead of 16, halving the
+ * event stream the kernels read; fractional coordinates (e.g. undistorted events) keep the 16-byte format.  Results are
+ * identical.  enable = 0 forces the 16-byte format (measurement / tests); *h_compact (may be NULL) returns the format in
+ * use afterwards. */
+int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cmax_stream_t stream);
 /* Measurement aid (bench.py roofline): which launches the three stages enqueue.  Bit 0 = the memsets, bit 1 = the
  * event kernels (K1 in cmax_objective_vote, K3 in cmax_objective_grad), bit 2 = the image-sized kernels (fold, blur,
  * statistics, gradient pictures).  Default 7 = everything; any other value produces timing-only (not meaningful)

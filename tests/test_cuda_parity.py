@@ -174,6 +174,15 @@ def test_fused_iwe_and_indices_bit_exact(B, dev, golden_random, pad):
             np.testing.assert_array_equal(fl.numpy(), torch.floor(w[:, :2] + 1e-6).long().numpy())
 
 
+def test_fractional_coordinates_keep_the_16_byte_format(B, dev, golden_random):
+    H, W, ev, motions = _inputs(golden_random, "frac")
+    obj = B.ContrastObjective(ev.to(dev), (H, W), cost="image_variance", motion_model="dense-flow")
+    assert obj.plan.set_compact(True) is False
+    H, W, ev, motions = _inputs(golden_random, "small")
+    obj = B.ContrastObjective(ev.to(dev), (H, W), cost="image_variance", motion_model="dense-flow")
+    assert obj.plan.set_compact(True) is (bool((ev[:, :2] == ev[:, :2].floor()).all()))
+
+
 def test_c1_config(B, dev, golden_c1):
     """BASELINE config 1: 30k events, 346x260, 2-dof warp + variance; and the dense-flow metric path."""
     g = golden_c1
@@ -207,7 +216,7 @@ def _synthetic(n, H, W, seed=0, max_flow=10.0):
     return torch.from_numpy(ev), torch.from_numpy(flow)
 
 
-@pytest.mark.parametrize("variants", ((2, 2), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
+@pytest.mark.parametrize("variants", ((2, 2), (3, 3), (2, 4), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
 def test_one_million_events_vs_oracle(B, dev, variants):
     H, W = 260, 346
     ev, flow = _synthetic(1_000_000, H, W, seed=1)
@@ -215,10 +224,13 @@ def test_one_million_events_vs_oracle(B, dev, variants):
     ref_v64, _ = O.objective_value_and_grad(ev.double(), flow.double(), (H, W), motion_model="dense-flow", cost="image_variance")
     obj = B.ContrastObjective(ev.to(dev), (H, W), cost="image_variance", motion_model="dense-flow", order="pixel")
     obj.plan.set_variant(*variants)
-    val, grad = obj.value_and_grad(flow.to(dev))
-    assert abs(float(val) - float(ref_v64)) <= RTOL * abs(float(ref_v64))
-    assert abs(float(val) - float(ref_v)) <= 3e-5 * abs(float(ref_v))  # the fp32 oracle itself is ~1e-5 off fp64
-    assert _rel(grad.cpu().numpy(), ref_g.numpy()) <= 2e-5
+    assert obj.plan.set_compact(True) is True  # integer pixel coordinates -> 8-byte packed events
+    for compact in (True, False):              # ... and the 16-byte format must give the same answer
+        assert obj.plan.set_compact(compact) is compact
+        val, grad = obj.value_and_grad(flow.to(dev))
+        assert abs(float(val) - float(ref_v64)) <= RTOL * abs(float(ref_v64))
+        assert abs(float(val) - float(ref_v)) <= 3e-5 * abs(float(ref_v))  # the fp32 oracle itself is ~1e-5 off fp64
+        assert _rel(grad.cpu().numpy(), ref_g.numpy()) <= 2e-5
 
 
 def test_full_size_properties(B, dev):
