@@ -48,37 +48,70 @@ struct Vote {
   float fx, fy;    // fractions measured from the floor: fx along rows, fy along columns; may be in [-1e-6, 1)
 };
 
-// Exact floor of v as float AND int without the quarter-rate conversion pipe (FRND / F2I): adding 1.5*2^23 rounds v to
-// the nearest integer in the mantissa; one compare-and-decrement turns round-to-nearest into floor.  Exact for
-// |v| < 2^22.  Beyond that (or for NaN / inf) the integer is garbage, but provably far outside any image: the biased
-// float is then not within [1.5*2^23 - 2^22, 1.5*2^23 + 2^22), so `i` has magnitude >= 2^22 (NaN/inf give ~8.8e8) and
-// every bounds check against an image of fewer than 2^22 rows / columns rejects it -- no explicit range guard needed.
+// ---- Blackwell packed fp32x2 arithmetic (PTX add/sub/mul/fma .f32x2, SASS FADD2 / FMUL2 / FFMA2): one instruction does the
+// row AND the column component of an event, each component IEEE-rounded exactly like its scalar counterpart (the
+// library is built with -fmad=false, so ptxas never contracts a mul2 + add2 pair either).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {  // round toward -inf
+  f32x2 r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Exact floor without the quarter-rate conversion pipe (FRND / F2I) and without a compare: v + 1.5*2^23 ROUNDED DOWN has
+// floor(v) in its mantissa (ulp = 1 there), so the biased float minus the bias is floor(v) as a float and its bit
+// pattern minus 0x4B400000 is floor(v) as an int.  Exact for |v| < 2^22.  Beyond that (or for NaN / inf) the integer is
+// garbage, but provably far outside any image: the biased float is then outside [2^23, 2^24), so `i` has magnitude
+// >= 2^22 (NaN/inf give ~8.8e8) and every bounds check against an image of fewer than 2^22 rows / columns rejects it.
+constexpr float kFloorBias = 12582912.0f;  // 1.5 * 2^23
 __device__ __forceinline__ void floor_exact(float v, float& fl, int& i) {
-  const float C = 12582912.0f;  // 1.5 * 2^23
-  const float t = __fadd_rn(v, C);
+  const float t = __fadd_rd(v, kFloorBias);
   i = __float_as_int(t) - 0x4B400000;
-  fl = __fsub_rn(t, C);
-  if (fl > v) {
-    fl = __fsub_rn(fl, 1.0f);
-    i -= 1;
-  }
+  fl = __fsub_rn(t, kFloorBias);
 }
 
 // i = floor(x' + 1e-6), f = x' - i          src/event_image_converter.py:340-345
-// For coordinates beyond +-2^22 row / col are garbage-but-out-of-range and fx / fy meaningless: callers must not use the
-// fractions of an event that fails its bounds checks.
-__device__ __forceinline__ Vote vote_geometry(float xw, float yw, int pad_h, int pad_w) {
-  float flx, fly;
-  int ix, iy;
-  floor_exact(__fadd_rn(xw, 1e-6f), flx, ix);
-  floor_exact(__fadd_rn(yw, 1e-6f), fly, iy);
+// Both components in packed arithmetic.  For coordinates beyond +-2^22 row / col are garbage-but-out-of-range and
+// fx / fy meaningless: callers must not use the fractions of an event that fails its bounds checks.
+__device__ __forceinline__ Vote vote_geometry2(f32x2 w, int pad_h, int pad_w) {
+  const f32x2 bias = pk2(kFloorBias, kFloorBias);
+  const f32x2 t = add2_rd(add2(w, pk2(1e-6f, 1e-6f)), bias);
+  const f32x2 f = sub2(w, sub2(t, bias));
+  float tx, ty;
+  upk2(t, tx, ty);
   Vote v;
-  v.fx = __fsub_rn(xw, flx);
-  v.fy = __fsub_rn(yw, fly);
-  v.row = ix + pad_h;
-  v.col = iy + pad_w;
+  upk2(f, v.fx, v.fy);
+  v.row = __float_as_int(tx) - 0x4B400000 + pad_h;
+  v.col = __float_as_int(ty) - 0x4B400000 + pad_w;
   return v;
 }
+__device__ __forceinline__ Vote vote_geometry(float xw, float yw, int pad_h, int pad_w) { return vote_geometry2(pk2(xw, yw), pad_h, pad_w); }
 
 // The 4 bilinear weights in the reference's corner order (r,c), (r+1,c), (r,c+1), (r+1,c+1)
 //                                            src/event_image_converter.py:365-369
@@ -100,6 +133,15 @@ __device__ __forceinline__ float normalised_dt(float t, float ref, float period,
 __device__ __forceinline__ float warp_minus(float x, float dt, float f) { return __fsub_rn(x, __fmul_rn(dt, f)); }
 // x' = x + dt * theta                        src/warp.py:507-514
 __device__ __forceinline__ float warp_plus(float x, float dt, float th) { return __fadd_rn(x, __fmul_rn(dt, th)); }
+// Both components.  The products stay SCALAR on purpose: ptxas contracts mul.rn.f32x2 + sub.rn.f32x2 into one FFMA2
+// (observed, CUDA 12.9), which would skip the rounding of dt*f that the reference performs; __fmul_rn / __fsub_rn are
+// never contracted.
+__device__ __forceinline__ f32x2 warp_minus2(float x, float y, float dt, float f0, float f1) {
+  return pk2(warp_minus(x, dt, f0), warp_minus(y, dt, f1));
+}
+__device__ __forceinline__ f32x2 warp_plus2(float x, float y, float dt, float f0, float f1) {
+  return pk2(warp_plus(x, dt, f0), warp_plus(y, dt, f1));
+}
 
 // Time bin of a normalised dt: edges[b] <= dt < edges[b+1], compared in fp32   src/warp.py:346-352.
 // Returns -1 if in no bin (NaN).  A closed-form guess is corrected against the exact edges.

@@ -422,7 +422,7 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
-  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 3, "cmax_plan_set_variant: vote_variant must be in [0,3]");
+  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 4, "cmax_plan_set_variant: vote_variant must be in [0,4]");
   CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 4, "cmax_plan_set_variant: grad_variant must be in [0,4]");
   plan->vote_variant = vote_variant;
   plan->grad_variant = grad_variant;

@@ -12,6 +12,8 @@
 //                                            by construction (src/event_image_converter.py:355-372)
 //   gq       float4[n_ref][(Hp+1)*(Wp+1)]    the adjoint of that fold: cell (i,j) = dL/dIWE at the four (masked)
 //                                            corners, so K3 gathers ONE float4 per event per reference time
+#include <stdlib.h>
+
 #include "cmax_plan.cuh"
 #include "cmax_stats.cuh"
 
@@ -59,6 +61,7 @@ struct FusedArgs {
   const cmax_time_params_t* tp;
   int64_t cells;  // (Hp+1)*(Wp+1)
   unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block), or NULL
+  int dbg;                // measurement only (CMAX_DEBUG): bit 0 = skip the reductions, bit 1 = skip the flow loads
 };
 
 // Time parameters one CTA needs, staged in shared memory once per CTA.
@@ -111,6 +114,13 @@ __device__ __forceinline__ void warp_ref(const float4 e, int src, int HW, const 
     }
   }
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still running; it must not touch anything the predecessor produces (or still reads)
+// before pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.  A predecessor
+// calls pdl_trigger() to allow the early start.  Both are no-ops for kernels launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -184,6 +194,8 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(float4* __restrict__ a
                                                           unsigned int* __restrict__ ctas_done) {
   __shared__ double red[kStatBlock / 32];
   __shared__ bool all_done;
+  pdl_trigger();
+  pdl_wait();  // K1's reductions are complete and visible
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
   float* A = reinterpret_cast<float*>(acc + img * cells);
@@ -235,6 +247,8 @@ __global__ void __launch_bounds__(kStatBlock) fold_kernel(float4* __restrict__ a
 __global__ void __launch_bounds__(256) gq_build_kernel(const float* __restrict__ src, const float* __restrict__ affine, int Hp, int Wp,
                                                        int64_t cells, int crop, float4* __restrict__ gq, float* __restrict__ zero,
                                                        int64_t n_zero) {
+  pdl_trigger();  // K3 may start prefetching its event tiles now
+  pdl_wait();     // the IWE / statistics / affine pair of the predecessor are complete
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
   const float* I = src + img * HW;
@@ -430,24 +444,24 @@ struct PackedEv<true> {  // (dt|t, row<<16|col) : 8 bytes, integer pixel coordin
   __device__ static __forceinline__ int src(int key, int W) { return (int)((unsigned)key >> 16) * W + (key & 0xFFFF); }
 };
 
-template <uint32_t BYTES>
-struct alignas(128) TilePipe {  // one per warp: double-buffered landing zone of the TMA bulk copies
-  unsigned char buf[2][BYTES];
-  uint64_t bar[2];
+template <uint32_t BYTES, int NS = 2>
+struct alignas(128) TilePipe {  // one per warp: NS-deep landing zone of the TMA bulk copies
+  unsigned char buf[NS][BYTES];
+  uint64_t bar[NS];
 };
 
-template <uint32_t BYTES>
-__device__ __forceinline__ void pipe_init(TilePipe<BYTES>& p, int lane) {
+template <uint32_t BYTES, int NS>
+__device__ __forceinline__ void pipe_init(TilePipe<BYTES, NS>& p, int lane) {
   if (lane == 0) {
-    mbar_init(&p.bar[0], 1);
-    mbar_init(&p.bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) mbar_init(&p.bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
 }
-template <uint32_t BYTES>
-__device__ __forceinline__ void pipe_issue(TilePipe<BYTES>& p, int stage, const void* __restrict__ packed, int64_t tile, int lane) {
+template <uint32_t BYTES, int NS>
+__device__ __forceinline__ void pipe_issue(TilePipe<BYTES, NS>& p, int stage, const void* __restrict__ packed, int64_t tile, int lane) {
   if (lane == 0) {
     mbar_expect_tx(&p.bar[stage], BYTES);
     bulk_g2s(p.buf[stage], static_cast<const unsigned char*>(packed) + tile * BYTES, BYTES, &p.bar[stage]);
@@ -471,29 +485,18 @@ __device__ __forceinline__ RefRegs<NREF> load_refs(const cmax_time_params_t* __r
   return rr;
 }
 
-// One packed event, one reference time -> (x', y', dt, bin).  PRE_DT: tz already is the normalised dt of reference 0.
+// One packed event, one reference time -> ((x', y') packed, dt, bin).  PRE_DT: tz already is the normalised dt of reference 0.
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void warp_packed(float x, float y, float tz, int src, int HW, const float* __restrict__ motion,
-                                            const RefRegs<NREF>& rr, const TimeSmem& s, int r, float f0, float f1, float& xw, float& yw,
-                                            float& dt, int& bin) {
+__device__ __forceinline__ f32x2 warp_packed(float x, float y, float tz, int src, int HW, const float* __restrict__ motion,
+                                             const RefRegs<NREF>& rr, const TimeSmem& s, int r, float f0, float f1, float& dt, int& bin) {
   dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
   bin = 0;
-  if (MODEL == CMAX_MOTION_2DOF) {
-    xw = warp_plus(x, dt, f0);
-    yw = warp_plus(y, dt, f1);
-  } else if (MODEL == CMAX_MOTION_DENSE) {
-    xw = warp_minus(x, dt, f0);
-    yw = warp_minus(y, dt, f1);
-  } else {
-    bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
-    xw = x;
-    yw = y;
-    if (bin >= 0) {
-      const float* f = motion + (int64_t)bin * 2 * HW;
-      xw = warp_minus(x, dt, __ldg(f + src));
-      yw = warp_minus(y, dt, __ldg(f + HW + src));
-    }
-  }
+  if (MODEL == CMAX_MOTION_2DOF) return warp_plus2(x, y, dt, f0, f1);
+  if (MODEL == CMAX_MOTION_DENSE) return warp_minus2(x, y, dt, f0, f1);
+  bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
+  if (bin < 0) return pk2(x, y);
+  const float* f = motion + (int64_t)bin * 2 * HW;
+  return warp_minus2(x, y, dt, __ldg(f + src), __ldg(f + HW + src));
 }
 
 // accumulator cell of a vote, or -1 when the event touches no pixel
@@ -520,28 +523,32 @@ __device__ __forceinline__ void vote_step(float x, float y, float tz, int key, V
       st.key = key;
       st.src = PackedEv<COMPACT>::src(key, a.W);
       if (MODEL == CMAX_MOTION_DENSE) {
-        st.f0 = __ldg(a.motion + st.src);
-        st.f1 = __ldg(a.motion + HW + st.src);
+        if (a.dbg & 2) {
+          st.f0 = 3.0f + (float)(st.src & 7);
+          st.f1 = -2.0f;
+        } else {
+          st.f0 = __ldg(a.motion + st.src);
+          st.f1 = __ldg(a.motion + HW + st.src);
+        }
       }
     }
   }
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
-    float xw, yw, dt;
+    float dt;
     int bin;
-    warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
-    const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+    const f32x2 xyw = warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, dt, bin);
+    const Vote v = vote_geometry2(xyw, a.pad_h, a.pad_w);
     float w[4];
     vote_weights(v, w);
     const int c = vote_cell(v, a.Hp, a.Wp);
     const bool same = c == st.cell[r];
-    red_add_v4_if(!same && st.cell[r] >= 0, acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+    red_add_v4_if(!same && st.cell[r] >= 0 && !(a.dbg & 1), acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
     st.cell[r] = c;
     const float keep = same ? 1.0f : 0.0f;  // acc * 1 + w and acc * 0 + w are exact: one select instead of four
-    st.w0[r] = fmaf(st.w0[r], keep, w[0]);
-    st.w1[r] = fmaf(st.w1[r], keep, w[1]);
-    st.w2[r] = fmaf(st.w2[r], keep, w[2]);
-    st.w3[r] = fmaf(st.w3[r], keep, w[3]);
+    const f32x2 keep2 = pk2(keep, keep);
+    upk2(fma2(pk2(st.w0[r], st.w1[r]), keep2, pk2(w[0], w[1])), st.w0[r], st.w1[r]);
+    upk2(fma2(pk2(st.w2[r], st.w3[r]), keep2, pk2(w[2], w[3])), st.w2[r], st.w3[r]);
   }
 }
 
@@ -567,6 +574,7 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
   const int64_t t_end = n_tiles;  // warps stride over all tiles (a contiguous range per CTA measured no better: profiles/)
   if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  pdl_trigger();  // the fold may be scheduled as soon as this grid drains
   int it = 0;
   for (int64_t tile = warp0; tile < t_end; tile += n_warps, ++it) {
     const int stage = it & 1;
@@ -632,6 +640,94 @@ __global__ void __launch_bounds__(kRunThreads) vote_runs_kernel(FusedArgs a, flo
   }
 }
 
+// K1 with the flow fetched one tile AHEAD (dense model): a 3-deep TMA pipeline means tile i+1 has already landed when
+// tile i starts, so its source pixels are known and its flow vectors are requested before tile i is walked -- a whole
+// tile walk (thousands of cycles) hides the L2 round trip that the plain walk exposes right after every tile arrival.
+template <int NREF, bool PRE_DT, bool COMPACT>
+__global__ void __launch_bounds__(kRunThreads) vote_runs_ahead_kernel(FusedArgs a, float4* __restrict__ acc) {
+  using PE = PackedEv<COMPACT>;
+  constexpr int MODEL = CMAX_MOTION_DENSE;
+  constexpr int NS = 3;
+  __shared__ TilePipe<PE::kTileBytes, NS> pipes[kRunWarps];
+  // the dense model never reads the voxel time table: hand the shared step function a reference it will not touch
+  const TimeSmem& s = *reinterpret_cast<const TimeSmem*>(pipes);
+  if (a.zero256 != nullptr && blockIdx.x == 0 && threadIdx.x < 64) a.zero256[threadIdx.x] = 0u;
+  const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
+  const int HW = a.H * a.W;
+  const int lane = threadIdx.x & 31;
+  TilePipe<PE::kTileBytes, NS>& pipe = pipes[threadIdx.x >> 5];
+  pipe_init(pipe, lane);
+  const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  if (warp0 < n_tiles) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  if (warp0 + n_warps < n_tiles) pipe_issue(pipe, 1, a.packed, warp0 + n_warps, lane);
+  pdl_trigger();
+  float fn0[kRunE], fn1[kRunE];  // flow vectors of the NEXT tile's events (in flight while the current tile is walked)
+  auto fetch_flows = [&](const void* buf) {
+    int prev = -1;
+#pragma unroll
+    for (int k = 0; k < kRunE; ++k) {
+      const int kk = PE::key_of(buf, k, lane);
+      if (kk != prev && kk != -1) {
+        const int src = PE::src(kk, a.W);
+        fn0[k] = __ldg(a.motion + src);
+        fn1[k] = __ldg(a.motion + HW + src);
+      } else {
+        fn0[k] = fn0[k > 0 ? k - 1 : 0];
+        fn1[k] = fn1[k > 0 ? k - 1 : 0];
+      }
+      prev = kk;
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < kRunE; ++k) fn0[k] = fn1[k] = 0.f;
+  if (warp0 < n_tiles) {
+    mbar_wait(&pipe.bar[0], 0);
+    fetch_flows(pipe.buf[0]);
+  }
+  int it = 0;
+  for (int64_t tile = warp0; tile < n_tiles; tile += n_warps, ++it) {
+    const int stage = it % NS;
+    float f0[kRunE], f1[kRunE];
+#pragma unroll
+    for (int k = 0; k < kRunE; ++k) {
+      f0[k] = fn0[k];
+      f1[k] = fn1[k];
+    }
+    __syncwarp();  // every lane is done with the buffer of the previous iteration: refill it with tile it+2
+    if (tile + 2 * n_warps < n_tiles) pipe_issue(pipe, (it + 2) % NS, a.packed, tile + 2 * n_warps, lane);
+    if (tile + n_warps < n_tiles) {  // tile it+1 landed during the previous walk: request its flow vectors now
+      mbar_wait(&pipe.bar[(it + 1) % NS], ((it + 1) / NS) & 1);
+      fetch_flows(pipe.buf[(it + 1) % NS]);
+    }
+    const void* buf = pipe.buf[stage];
+    VoteState<NREF> st;
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) {
+      st.cell[r] = -1;
+      st.w0[r] = st.w1[r] = st.w2[r] = st.w3[r] = 0.f;
+    }
+    st.src = 0;
+    float x, y, tz;
+    int key;
+    const int64_t left = a.n - (tile * kWarpTile + (int64_t)lane * kRunE);
+    const int count = left >= kRunE ? kRunE : (left > 0 ? (int)left : 0);
+#pragma unroll
+    for (int k = 0; k < kRunE; ++k) {
+      if (k < count) {  // (padding slots of the last tile carry key -1 and are skipped)
+        PE::get(buf, k, lane, x, y, tz, key);
+        st.key = key;  // flow already fetched
+        st.f0 = f0[k];
+        st.f1 = f1[k];
+        vote_step<MODEL, NREF, PRE_DT, COMPACT>(x, y, tz, key, st, a, HW, rr, s, acc);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NREF; ++r)
+      if (st.cell[r] >= 0) red_add_v4(acc + r * a.cells + st.cell[r], st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+  }
+}
+
 // ---- K3 walk
 template <int MODEL, int NREF>
 struct GradState {
@@ -672,10 +768,10 @@ __device__ __forceinline__ void grad_step(float x, float y, float tz, int key, G
   }
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
-    float xw, yw, dt;
+    float dt;
     int bin;
-    warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, xw, yw, dt, bin);
-    const Vote v = vote_geometry(xw, yw, a.pad_h, a.pad_w);
+    const f32x2 xyw = warp_packed<MODEL, NREF, PRE_DT>(x, y, tz, st.src, HW, a.motion, rr, s, r, st.f0, st.f1, dt, bin);
+    const Vote v = vote_geometry2(xyw, a.pad_h, a.pad_w);
     const int c = vote_cell(v, a.Hp, a.Wp);
     if (c != st.cell[r]) {
       st.cell[r] = c;
@@ -750,7 +846,7 @@ __device__ __forceinline__ void grad_tile_dense(const void* __restrict__ buf, in
         int key;
         PE::get(buf, b + k, lane, x, y, tz, key);
         const float dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
-        const Vote v = vote_geometry(warp_minus(x, dt, f0[k]), warp_minus(y, dt, f1[k]), a.pad_h, a.pad_w);
+        const Vote v = vote_geometry2(warp_minus2(x, y, dt, f0[k], f1[k]), a.pad_h, a.pad_w);
         fx[k] = v.fx;
         fy[k] = v.fy;
         dts[k] = dt;
@@ -806,7 +902,8 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
   const int64_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
   const int64_t t_end = n_tiles;
-  if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);
+  if (warp0 < t_end) pipe_issue(pipe, 0, a.packed, warp0, lane);  // the packed events do not depend on the predecessor
+  pdl_wait();  // gradient quads (and the zeroed gradient buffer) of the predecessor kernel are complete
   int it = 0;
   for (int64_t tile = warp0; tile < t_end; tile += n_warps, ++it) {
     const int stage = it & 1;
@@ -927,6 +1024,32 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs peers, int64_t n
 }
 
 // ------------------------------------------------------------------------------------------------ dispatch
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait); `pdl == false` is an ordinary launch.
+static bool pdl_enabled() {  // CMAX_PDL=0 turns programmatic dependent launch off (measurement)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CMAX_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Persistent-style grid for the run kernels: exactly the number of CTAs that are resident at once (occupancy x SMs),
 // each warp striding over the warp-tiles; the shared-memory carveout is raised to the maximum first (the kernels want
 // up to 6 CTAs x 33 KB per SM).  Cached per kernel instantiation (one process drives one GPU).
@@ -945,6 +1068,13 @@ static int run_grid(K kernel, int64_t n) {
 
 template <int MODEL, int NREF, bool COMPACT>
 static void launch_vote_runs(int variant, cudaStream_t s, const FusedArgs& a, float4* acc) {
+  if constexpr (MODEL == CMAX_MOTION_DENSE && COMPACT) {  // (3 stages of 16-byte tiles would not fit 48 KB of static shared memory)
+    if (variant == 4) {  // flow fetched one tile ahead
+      auto k = vote_runs_ahead_kernel<NREF, NREF == 1, COMPACT>;
+      k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, acc);
+      return;
+    }
+  }
   if (variant == 3) {  // batched flow loads
     auto k = vote_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, true>;
     k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, acc);
@@ -975,13 +1105,13 @@ template <int MODEL, int NREF, bool COMPACT>
 static void launch_grad_runs(int gvar, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
   if (gvar == 2) {  // batches of 4
     auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 4>;
-    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
+    launch_k(pdl_enabled(), k, dim3(run_grid(k, a.n)), dim3(kRunThreads), s, a, gq, gm);
   } else if (gvar == 3) {  // batches of 8
     auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 8>;
-    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
+    launch_k(pdl_enabled(), k, dim3(run_grid(k, a.n)), dim3(kRunThreads), s, a, gq, gm);
   } else {  // sequential walk
     auto k = grad_runs_kernel<MODEL, NREF, NREF == 1, COMPACT, 0>;
-    k<<<run_grid(k, a.n), kRunThreads, 0, s>>>(a, gq, gm);
+    launch_k(pdl_enabled(), k, dim3(run_grid(k, a.n)), dim3(kRunThreads), s, a, gq, gm);
   }
 }
 
@@ -1022,6 +1152,14 @@ static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.tp = p->d_params;
   a.cells = (int64_t)(p->Hp + 1) * (p->Wp + 1);
   a.zero256 = nullptr;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("CMAX_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    a.dbg = dbg;
+  }
   return a;
 }
 
@@ -1111,8 +1249,8 @@ static int vote_stage(const cmax_plan* p, int motion_model, const float* motion,
     CombineDev cd;
     memset(&cd, 0, sizeof(cd));
     if (fuse && fused_combine) cd = *fused_combine;
-    fold_kernel<<<grid, kStatBlock, 0, s>>>(w.acc, w.iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0, fuse ? fuse_spec->omit_boundary : 0,
-                                            w.sacc, w.stats, (fuse && fused_combine) ? 1 : 0, cd, w.ctas_done);
+    launch_k(pdl_enabled(), fold_kernel, grid, dim3(kStatBlock), s, w.acc, w.iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0,
+             fuse ? fuse_spec->omit_boundary : 0, w.sacc, w.stats, (fuse && fused_combine) ? 1 : 0, cd, w.ctas_done);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
   if (stats_fused) *stats_fused = fuse ? 1 : 0;
@@ -1165,7 +1303,8 @@ static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const doub
       }
     }
     dim3 grid((unsigned)image_grid(L.cells), n_ref);
-    gq_build_kernel<<<grid, 256, 0, s>>>(gsrc, w.affine, p->Hp, p->Wp, L.cells, crop, w.gq, zero_grad, (int64_t)n_zero);
+    launch_k(pdl_enabled(), gq_build_kernel, grid, dim3(256), s, gsrc, (const float*)w.affine, p->Hp, p->Wp, L.cells, crop, w.gq, zero_grad,
+             (int64_t)n_zero);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;

@@ -183,6 +183,33 @@ def test_fractional_coordinates_keep_the_16_byte_format(B, dev, golden_random):
     assert obj.plan.set_compact(True) is (bool((ev[:, :2] == ev[:, :2].floor()).all()))
 
 
+@pytest.mark.parametrize("order", ("asis", "pixel"))
+@pytest.mark.parametrize("fractional", (False, True))
+def test_fused_path_is_bit_exact_when_votes_do_not_collide(B, dev, order, fractional):
+    """One event per 4x4 block and |flow*dt| < 0.9: no two events share a pixel, so every IWE pixel is a single bilinear
+    weight and must equal the reference arithmetic bit for bit (warp product rounded before the subtraction, floor(x+1e-6),
+    fractions, weight products) -- in both packed-event formats and for every reference time."""
+    rng = np.random.default_rng(5)
+    H, W = 64, 96
+    rows, cols = np.meshgrid(np.arange(1, H - 2, 4), np.arange(1, W - 2, 4), indexing="ij")
+    n = rows.size
+    ev = np.zeros((n, 4), dtype=np.float32)
+    ev[:, 0] = rows.ravel() + (rng.uniform(0, 0.05, n) if fractional else 0)
+    ev[:, 1] = cols.ravel() + (rng.uniform(0, 0.05, n) if fractional else 0)
+    ev[:, 2] = np.sort(rng.uniform(0, 0.05, n))
+    ev = torch.from_numpy(ev)
+    flow = torch.from_numpy(rng.uniform(-0.9, 0.9, (2, H, W)).astype(np.float32))
+    obj = B.ContrastObjective(ev.to(dev), (H, W), cost="multi_focal_normalized_image_variance", motion_model="dense-flow", order=order)
+    assert obj.plan.set_compact(True) is (not fractional)
+    iwes = obj.iwe(flow.to(dev)).cpu()
+    for k, d in enumerate(("first", "last", "middle")):
+        ref = O.create_iwe(O.warp_dense(ev, flow, d), (H, W))
+        assert torch.equal(iwes[k], ref), (d, float((iwes[k] - ref).abs().max()))
+    theta = torch.tensor([0.7, -0.6])
+    obj2 = B.ContrastObjective(ev.to(dev), (H, W), cost="image_variance", motion_model="2d-translation", order=order)
+    assert torch.equal(obj2.iwe(theta.to(dev))[0].cpu(), O.create_iwe(O.warp_2dof(ev, theta, "first"), (H, W)))
+
+
 def test_c1_config(B, dev, golden_c1):
     """BASELINE config 1: 30k events, 346x260, 2-dof warp + variance; and the dense-flow metric path."""
     g = golden_c1
@@ -216,7 +243,7 @@ def _synthetic(n, H, W, seed=0, max_flow=10.0):
     return torch.from_numpy(ev), torch.from_numpy(flow)
 
 
-@pytest.mark.parametrize("variants", ((2, 2), (3, 3), (2, 4), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
+@pytest.mark.parametrize("variants", ((2, 2), (3, 3), (4, 4), (2, 4), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
 def test_one_million_events_vs_oracle(B, dev, variants):
     H, W = 260, 346
     ev, flow = _synthetic(1_000_000, H, W, seed=1)
