@@ -358,6 +358,42 @@ class ContrastObjective:
         return _ObjectiveFunction.apply(motion, self)
 
 
+class TileFlowObjective:
+    """cost(patch motion [2,hp,wp]) with the tile-flow -> dense-flow map of the reference in front of a dense-flow
+    `ContrastObjective` (what `objective_scipy` evaluates, src/solver/patch_contrast_pyramid.py:430-462: dense =
+    interpolate(motion) * t_scale -> calculate_cost).  The gradient comes back on the patch grid (hp*wp*2 numbers), so
+    the host round trip per optimiser step is a few KB."""
+
+    def __init__(self, objective: ContrastObjective, patch_size, sliding_window, patch_shift=(0, 0), t_scale: float = 1.0):
+        from . import ops
+        if objective.motion_model != "dense-flow":
+            raise ValueError("TileFlowObjective wraps a dense-flow ContrastObjective")
+        self.objective = objective
+        self.image_shape = objective.image_size
+        self.window = (int(sliding_window[0]), int(sliding_window[1]))
+        self.pad = ops.tile_flow_geometry(self.image_shape, patch_size, sliding_window, patch_shift)
+        self.t_scale = float(t_scale)
+
+    def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
+        from . import ops
+        _require_cuda(motion, "motion")
+        if motion.dim() != 3 or motion.shape[0] != 2:
+            raise ValueError(f"tile-flow motion must be [2,hp,wp], got {tuple(motion.shape)}")
+        dense = ops.tile_flow_upsample(motion, self.image_shape, self.pad, self.window)
+        if self.t_scale != 1.0:
+            dense = dense * self.t_scale
+        cost, gdense = self.objective.value_and_grad(dense, want_grad)
+        if not want_grad:
+            return cost, None
+        gm = ops.tile_flow_upsample_backward(gdense, motion.shape[-2:], self.pad, self.window)
+        if self.t_scale != 1.0:
+            gm = gm * self.t_scale
+        return cost, gm
+
+    def value(self, motion: torch.Tensor) -> torch.Tensor:
+        return self.value_and_grad(motion, want_grad=False)[0]
+
+
 class _ObjectiveFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, motion: torch.Tensor, obj: ContrastObjective):

@@ -197,3 +197,48 @@ class ImageStatFunction(torch.autograd.Function):
         if grad is None:
             return None, None, None
         return (grad[0] * g.to(torch.float32)).to(ctx.dtype), None, None
+
+
+# ------------------------------------------------------------------------------------------------ tile flow
+def tile_flow_geometry(image_shape, patch_size, sliding_window, patch_shift):
+    """(pad_h, pad_w) of the replicate padding, src/solver/patch_contrast_base.py:470-479."""
+    pad_h = int(patch_size[0] / 2 // sliding_window[0]) + patch_shift[0] // sliding_window[0] + 1
+    pad_w = int(patch_size[1] / 2 // sliding_window[1]) + patch_shift[1] // sliding_window[1] + 1
+    return pad_h, pad_w
+
+
+def tile_flow_upsample(motion: torch.Tensor, image_shape, pad, window) -> torch.Tensor:
+    m = _f32c(motion)
+    _, hp, wp = m.shape
+    H, W = int(image_shape[0]), int(image_shape[1])
+    dense = torch.empty(2, H, W, dtype=torch.float32, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.call("cmax_tile_flow_upsample", m.data_ptr(), hp, wp, int(pad[0]), int(pad[1]), int(window[0]), int(window[1]), H, W,
+                  dense.data_ptr(), _stream())
+    return dense
+
+
+def tile_flow_upsample_backward(grad_dense: torch.Tensor, grid, pad, window) -> torch.Tensor:
+    g = _f32c(grad_dense)
+    _, H, W = g.shape
+    hp, wp = int(grid[0]), int(grid[1])
+    gm = torch.empty(2, hp, wp, dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.call("cmax_tile_flow_upsample_backward", g.data_ptr(), hp, wp, int(pad[0]), int(pad[1]), int(window[0]), int(window[1]), H, W,
+                  gm.data_ptr(), _stream())
+    return gm
+
+
+class TileFlowFunction(torch.autograd.Function):
+    """[2,hp,wp] patch motion -> [2,H,W] dense flow (negated, replicate-padded, bilinear, cropped), differentiable."""
+
+    @staticmethod
+    def forward(ctx, motion, image_shape, pad, window):
+        ctx.meta = (tuple(motion.shape[-2:]), tuple(pad), tuple(window), motion.dtype)
+        return tile_flow_upsample(motion, image_shape, pad, window).to(motion.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        grid, pad, window, dtype = ctx.meta
+        return tile_flow_upsample_backward(g, grid, pad, window).to(dtype), None, None, None

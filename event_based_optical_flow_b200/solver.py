@@ -117,6 +117,16 @@ class B200CostMixin:
             return cost.calculate({"flow": coarse_flow, "omit_boundary": True})
         return None
 
+    def interpolate_dense_flow_from_patch_tensor(self, motion_array: torch.Tensor) -> torch.Tensor:
+        """Same contract as src/solver/patch_contrast_base.py:462-506, one CUDA kernel (and one for the adjoint) instead
+        of pad + torchvision resize + crop.  Falls back to the reference for CPU tensors / the 'nearest' filter."""
+        if not (isinstance(motion_array, torch.Tensor) and motion_array.is_cuda and getattr(self, "filter_type", "bilinear") == "bilinear"):
+            return super().interpolate_dense_flow_from_patch_tensor(motion_array)
+        from . import ops
+        pad = ops.tile_flow_geometry(self.image_shape, self.patch_size, self.sliding_window, self.patch_shift)
+        m = motion_array.reshape((self.motion_vector_size,) + tuple(self.patch_image_size))
+        return ops.TileFlowFunction.apply(m, tuple(self.image_shape), pad, tuple(self.sliding_window))
+
     def calculate_cost(self, events, warp, motion_model: str, coarse_flow=None, save_intermediate_result: bool = True):
         """Same contract as src/solver/patch_contrast_base.py:273-287."""
         fusable = (isinstance(events, torch.Tensor) and events.is_cuda and isinstance(warp, torch.Tensor)

@@ -132,6 +132,16 @@ size_t cmax_stats_workspace_bytes(int n_img, int Hp, int Wp);
 int cmax_image_stats(const float* images, int n_img, int Hp, int Wp, int stat, int omit_boundary, double* d_stats,
                      float* grad, void* workspace, cmax_stream_t stream);
 
+/* ------------------------------------------------------------------ tile flow   */
+/* PatchContrastMaximization.interpolate_dense_flow_from_patch_tensor (src/solver/patch_contrast_base.py:462-506):
+ * motion [2,hp,wp] (patch grid) -> dense [2,H,W] = crop(resize_bilinear(replicate_pad(-motion, pad_h, pad_w), x(sh,sw))),
+ * align_corners = false, central crop (offsets full/2 - H/2).  The backward is the exact adjoint (a gather per grid
+ * node, no atomics): grad_dense [2,H,W] -> grad_motion [2,hp,wp]. */
+int cmax_tile_flow_upsample(const float* motion, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W, float* dense,
+                            cmax_stream_t stream);
+int cmax_tile_flow_upsample_backward(const float* grad_dense, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W,
+                                     float* grad_motion, cmax_stream_t stream);
+
 /* ------------------------------------------------------------------ fused hot path */
 /* Event order inside a plan.  The order never changes results beyond fp32 summation order; it changes locality. */
 typedef enum {

@@ -405,3 +405,30 @@ def flow_gradient_dense(events: torch.Tensor, dt: torch.Tensor, gx: torch.Tensor
     out[0].scatter_add_(0, src, -dt * gx)
     out[1].scatter_add_(0, src, -dt * gy)
     return out.reshape(2, H, W)
+
+
+# --------------------------------------------------------------------------------------
+# tile (patch-grid) flow -> dense flow   (src/solver/patch_contrast_base.py:462-506)
+# --------------------------------------------------------------------------------------
+def tile_flow_geometry(image_shape, patch_size, sliding_window, patch_shift, grid):
+    """(pad_h, pad_w, full_h, full_w, h1, w1): replicate padding of the patch grid, size after the integer-factor
+    resize, and the offsets of the central crop.  src/solver/patch_contrast_base.py:470-479, 494-505."""
+    pad_h = int(patch_size[0] / 2 // sliding_window[0]) + patch_shift[0] // sliding_window[0] + 1
+    pad_w = int(patch_size[1] / 2 // sliding_window[1]) + patch_shift[1] // sliding_window[1] + 1
+    full_h = (grid[0] + 2 * pad_h) * sliding_window[0]
+    full_w = (grid[1] + 2 * pad_w) * sliding_window[1]
+    h1 = full_h // 2 - image_shape[0] // 2
+    w1 = full_w // 2 - image_shape[1] // 2
+    return pad_h, pad_w, full_h, full_w, h1, w1
+
+
+def upsample_tile_flow(motion: torch.Tensor, image_shape, patch_size, sliding_window, patch_shift) -> torch.Tensor:
+    """[2,hp,wp] patch motion -> [2,H,W] dense flow: NEGATE, replicate-pad, bilinear resize (align_corners=False) by
+    the sliding window, central crop.  Differentiable by torch autograd.  src/solver/patch_contrast_base.py:462-506
+    (torchvision `resize` on a tensor = F.interpolate(mode="bilinear", align_corners=False); its antialias flag has no
+    effect when up-sampling)."""
+    grid = tuple(motion.shape[-2:])
+    pad_h, pad_w, full_h, full_w, h1, w1 = tile_flow_geometry(image_shape, patch_size, sliding_window, patch_shift, grid)
+    padded = torch.nn.functional.pad(-motion[None], (pad_w, pad_w, pad_h, pad_h), mode="replicate")
+    dense = torch.nn.functional.interpolate(padded, size=(full_h, full_w), mode="bilinear", align_corners=False)[0]
+    return dense[..., h1:h1 + image_shape[0], w1:w1 + image_shape[1]]

@@ -140,3 +140,26 @@ def test_voxel_bins_partition_all_events():
         b = O.voxel_bin_of(dt, 10)
         assert int(b.min()) == 0 and int(b.max()) == 9
         assert bool((b[1:] >= b[:-1]).all())
+
+
+@pytest.fixture(scope="module")
+def golden_tileflow():
+    import os
+    from conftest import GOLDEN_DIR
+    return np.load(os.path.join(GOLDEN_DIR, "reference_tileflow.npz"))
+
+
+@pytest.mark.parametrize("case", ("s4", "s3", "s1", "sq", "odd"))
+def test_tile_flow_upsample_matches_reference(golden_tileflow, case):
+    """Tile-flow -> dense-flow and its autograd adjoint vs the reference's own method (patch_contrast_base.py:462-506)."""
+    g = golden_tileflow
+    meta = [int(v) for v in g[f"{case}/meta"]]
+    image_shape, patch_size, sliding_window, patch_shift = tuple(meta[0:2]), tuple(meta[2:4]), tuple(meta[4:6]), tuple(meta[6:8])
+    for tag, dt, tol in (("f32", torch.float32, 2e-6), ("f64", torch.float64, 1e-13)):
+        m = torch.from_numpy(g[f"{case}/{tag}/motion"]).to(dt).requires_grad_(True)
+        dense = O.upsample_tile_flow(m, image_shape, patch_size, sliding_window, patch_shift)
+        ref = g[f"{case}/{tag}/dense"]
+        assert dense.shape == ref.shape
+        np.testing.assert_allclose(dense.detach().numpy(), ref, rtol=tol, atol=tol * 8)
+        (gm,) = torch.autograd.grad((dense * torch.from_numpy(g[f"{case}/{tag}/grad_dense"]).to(dt)).sum(), m)
+        np.testing.assert_allclose(gm.numpy(), g[f"{case}/{tag}/grad_motion"], rtol=tol * 10, atol=tol * 100)
