@@ -13,8 +13,8 @@ Layout:
 from . import _lib
 from .costs import functions as cost_functions
 from .event_image_converter import EventImageConverter
-from .objective import COST_TABLE, ContrastObjective, EventPlan, TileFlowObjective, cm_objective
+from .objective import COST_TABLE, ContrastObjective, EventPlan, TileFlowObjective, TimeAwareObjective, cm_objective
 from .warp import MotionModelKeyError, Warp
 
 __all__ = ["Warp", "EventImageConverter", "MotionModelKeyError", "cost_functions", "EventPlan", "ContrastObjective",
-           "cm_objective", "COST_TABLE", "TileFlowObjective"]
+           "cm_objective", "COST_TABLE", "TileFlowObjective", "TimeAwareObjective"]

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200.so")
-SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_tileflow.cu")
+SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu")
 HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared")
@@ -27,6 +27,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libcmax_b200.so cannot be built (set NVCC=/path/to/nvcc)")
 
 
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+COMPILE_FLAGS = tuple(f for f in NVCC_FLAGS if f not in ("-shared",))
+
+
+def _header_mtime() -> float:
+    return max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS if os.path.exists(os.path.join(CSRC, h)))
+
+
+def _obj_path(src: str) -> str:
+    return os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+
+
+def _obj_stale(src: str) -> bool:
+    obj = _obj_path(src)
+    if not os.path.exists(obj):
+        return True
+    built = os.path.getmtime(obj)
+    return os.path.getmtime(os.path.join(CSRC, src)) > built or _header_mtime() > built
+
+
 def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
@@ -36,20 +56,31 @@ def is_stale() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into lib/libcmax_b200.so; returns the path.  No-op when up to date."""
+    """Compile csrc/*.cu into lib/libcmax_b200.so; returns the path.  No-op when up to date.  Every source is its own
+    translation unit (no relocatable device code), so stale objects are recompiled in parallel and then linked."""
     if not force and not is_stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    todo = [s for s in SOURCES if force or _obj_stale(s)]
+    procs = []
+    for src in todo:
+        cmd = [nvcc, *COMPILE_FLAGS, "-c", "-o", _obj_path(src), os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for src, proc in procs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src} ({proc.returncode}):\n{out}\n{err}")
+        if verbose:
+            print(err)
     tmp = LIB_PATH + ".tmp"
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-        print(" ".join(cmd))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", tmp, *[_obj_path(s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
-    if verbose:
-        print(proc.stderr)
+        raise RuntimeError(f"nvcc link failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
 

@@ -20,6 +20,7 @@ VOTE = {"bilinear_vote": 0, "count": 1}
 STAT = {"variance": 0, "gradmag": 1}
 FORM = {"plain": 0, "normalized": 1, "multifocal": 2}
 ORDER = {"asis": 0, "tile": 1, "pixel": 2}
+SCHEME = {"upwind": 0, "burgers": 1}
 
 
 class Ref(C.Structure):
@@ -48,6 +49,9 @@ _SIGNATURES = {
     "cmax_blur3": (_i, [_p, _p, _i, _i, _i, _f, _i, _p]),
     "cmax_tile_flow_upsample": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "cmax_tile_flow_upsample_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "cmax_flow_voxel_workspace_bytes": (_sz, [_i, _i]),
+    "cmax_flow_voxel": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
+    "cmax_flow_voxel_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "cmax_stats_workspace_bytes": (_sz, [_i, _i, _i]),
     "cmax_image_stats": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "cmax_plan_workspace_bytes": (_sz, [_i64, _i, _i, _i]),

@@ -394,6 +394,57 @@ class TileFlowObjective:
         return self.value_and_grad(motion, want_grad=False)[0]
 
 
+class TimeAwareObjective:
+    """cost(motion) for the time-aware configuration: motion -> [tile-flow upsample] -> dense flow at t0 -> flow voxel
+    (upwind / Burgers propagation, src/utils/flow_utils.py:99-161) -> voxel warp + IWE + cost, and the gradient back
+    through every stage -- what `TimeAwarePatchContrastMaximization.objective_scipy` evaluates
+    (src/solver/time_aware_patch_contrast.py:42-80, src/solver/patch_contrast_pyramid.py:430-462), every stage a CUDA
+    kernel of this library.  `objective` is a `ContrastObjective(motion_model="dense-flow-voxel", n_bins=time_bin)`;
+    `tile` = dict(patch_size, sliding_window, patch_shift) makes the motion a [2,hp,wp] patch grid, None a dense [2,H,W]
+    flow.  `scale_later` as in the reference: the voxel is built from motion / max(motion) and scaled back."""
+
+    def __init__(self, objective: ContrastObjective, scheme: str = "burgers", t0_location: str = "middle", tile: Optional[dict] = None,
+                 scale_later: bool = False):
+        from . import ops
+        if objective.motion_model != "dense-flow-voxel":
+            raise ValueError("TimeAwareObjective wraps a dense-flow-voxel ContrastObjective")
+        ops._voxel_args(scheme, t0_location)
+        self.objective = objective
+        self.time_bin = objective.n_bins
+        self.scheme, self.t0_location = scheme, t0_location
+        self.image_shape = objective.image_size
+        self.scale_later = bool(scale_later)
+        self.tile = None
+        if tile is not None:
+            window = (int(tile["sliding_window"][0]), int(tile["sliding_window"][1]))
+            self.tile = (ops.tile_flow_geometry(self.image_shape, tile["patch_size"], window, tile.get("patch_shift", (0, 0))), window)
+
+    def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
+        from . import ops
+        _require_cuda(motion, "motion")
+        m = motion.detach().to(torch.float32)
+        dense = ops.tile_flow_upsample(m, self.image_shape, *self.tile) if self.tile is not None else m.contiguous()
+        scale = m.max() if self.scale_later else None
+        d_in = dense / scale if scale is not None else dense
+        voxel = ops.flow_voxel(d_in, self.time_bin, self.scheme, self.t0_location)
+        v_in = voxel * scale if scale is not None else voxel
+        cost, gvox = self.objective.value_and_grad(v_in, want_grad)
+        if not want_grad:
+            return cost, None
+        g_d_in = ops.flow_voxel_backward(d_in, voxel, gvox * scale if scale is not None else gvox, self.scheme, self.t0_location)
+        gdense = g_d_in / scale if scale is not None else g_d_in
+        gm = ops.tile_flow_upsample_backward(gdense, m.shape[-2:], *self.tile) if self.tile is not None else gdense
+        if scale is not None:
+            # d/d scale of (voxel(dense/scale) * scale), routed to the arg-max element of the motion (torch's max backward)
+            gs = (gvox * voxel).sum() - (g_d_in * d_in).sum() / scale
+            flat = gm.reshape(-1)
+            flat[m.reshape(-1).argmax()] += gs
+        return cost, gm
+
+    def value(self, motion: torch.Tensor) -> torch.Tensor:
+        return self.value_and_grad(motion, want_grad=False)[0]
+
+
 class _ObjectiveFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, motion: torch.Tensor, obj: ContrastObjective):

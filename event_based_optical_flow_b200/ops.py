@@ -242,3 +242,59 @@ class TileFlowFunction(torch.autograd.Function):
     def backward(ctx, g):
         grid, pad, window, dtype = ctx.meta
         return tile_flow_upsample_backward(g, grid, pad, window).to(dtype), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------ time-aware flow voxel
+def _voxel_args(scheme: str, t0_location: str):
+    if t0_location not in ("first", "middle"):
+        raise NotImplementedError(f"{t0_location =} not supported")  # src/utils/flow_utils.py:119-122
+    if scheme not in _lib.SCHEME:
+        raise NotImplementedError(f"flow-voxel scheme {scheme!r} has no CUDA form (available: {sorted(_lib.SCHEME)})")
+    return _lib.SCHEME[scheme], 1 if t0_location == "middle" else 0
+
+
+def flow_voxel(dense: torch.Tensor, time_bin: int, scheme: str = "upwind", t0_location: str = "middle") -> torch.Tensor:
+    """[2,H,W] flow at t0 -> [time_bin,2,H,W] (construct_dense_flow_voxel_torch, src/utils/flow_utils.py:99-161)."""
+    sc, mid = _voxel_args(scheme, t0_location)
+    d = _f32c(dense)
+    if d.dim() != 3 or d.shape[0] != 2:
+        raise ValueError(f"dense flow must be [2,H,W], got {tuple(d.shape)}")
+    _, H, W = d.shape
+    vox = torch.empty(int(time_bin), 2, H, W, dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        _lib.call("cmax_flow_voxel", d.data_ptr(), H, W, int(time_bin), sc, mid, vox.data_ptr(), _stream())
+    return vox
+
+
+def flow_voxel_backward(dense: torch.Tensor, voxel: torch.Tensor, grad_voxel: torch.Tensor, scheme: str = "upwind",
+                        t0_location: str = "middle") -> torch.Tensor:
+    """Adjoint of `flow_voxel`: grad_voxel [T,2,H,W] -> grad_dense [2,H,W]; `dense`, `voxel` = the forward's input / output."""
+    sc, mid = _voxel_args(scheme, t0_location)
+    d, v, g = _f32c(dense), _f32c(voxel), _f32c(grad_voxel)
+    T, _, H, W = v.shape
+    if g.shape != v.shape:
+        raise ValueError(f"grad_voxel must have the voxel's shape {tuple(v.shape)}, got {tuple(g.shape)}")
+    out = torch.empty(2, H, W, dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        ws = torch.empty(_lib.load().cmax_flow_voxel_workspace_bytes(H, W), dtype=torch.uint8, device=d.device)
+        _lib.call("cmax_flow_voxel_backward", d.data_ptr(), v.data_ptr(), g.data_ptr(), H, W, T, sc, mid, out.data_ptr(), ws.data_ptr(),
+                  _stream())
+    return out
+
+
+class FlowVoxelFunction(torch.autograd.Function):
+    """Differentiable `flow_voxel` in the caller's dtype."""
+
+    @staticmethod
+    def forward(ctx, dense, time_bin, scheme, t0_location):
+        vox = flow_voxel(dense, time_bin, scheme, t0_location)
+        ctx.save_for_backward(dense.detach(), vox)
+        ctx.meta = (scheme, t0_location, dense.dtype)
+        return vox.to(dense.dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        dense, vox = ctx.saved_tensors
+        scheme, t0_location, dtype = ctx.meta
+        return flow_voxel_backward(dense, vox, g, scheme, t0_location).to(dtype), None, None, None

@@ -127,6 +127,29 @@ class B200CostMixin:
         m = motion_array.reshape((self.motion_vector_size,) + tuple(self.patch_image_size))
         return ops.TileFlowFunction.apply(m, tuple(self.image_shape), pad, tuple(self.sliding_window))
 
+    def motion_to_dense_flow(self, motion, t_scale: float = 1.0):
+        """Same contract as the reference's two `motion_to_dense_flow` methods -- the pyramid's
+        (src/solver/patch_contrast_pyramid.py:464-516: dict of per-scale motions, `t_scale`, scale = max of the dense flow)
+        and the time-aware solver's (src/solver/time_aware_patch_contrast.py:42-80: one motion array, scale = max of the
+        motion) -- with the upwind / Burgers voxel propagation (src/utils/flow_utils.py:99-161) as ONE CUDA launch per side
+        of t0 instead of ~25 torch kernels per time bin (and as many again in autograd).  Anything else (numpy callers,
+        CPU tensors, the other interpolation schemes) goes to the reference's own method."""
+        is_pyramid = isinstance(motion, dict)
+        finest = motion[self.current_scale] if is_pyramid else motion
+        fast = (isinstance(finest, torch.Tensor) and finest.is_cuda and getattr(self, "is_time_aware", False)
+                and getattr(self, "flow_interpolation", None) in ("upwind", "burgers"))
+        if not fast:
+            return super().motion_to_dense_flow(motion, t_scale) if is_pyramid else super().motion_to_dense_flow(motion)
+        from . import ops
+        dense = self.interpolate_dense_flow_from_patch_tensor(finest)
+        if is_pyramid:
+            scale = dense.max() if self.scale_later else 1.0
+            voxel = ops.FlowVoxelFunction.apply(dense * t_scale / scale, self.time_bin, self.flow_interpolation, self.t0_flow_location)
+            return voxel * scale / t_scale
+        scale = finest.max() if self.scale_later else 1.0
+        voxel = ops.FlowVoxelFunction.apply(dense / scale, self.time_bin, self.flow_interpolation, self.t0_flow_location)
+        return voxel * scale
+
     def calculate_cost(self, events, warp, motion_model: str, coarse_flow=None, save_intermediate_result: bool = True):
         """Same contract as src/solver/patch_contrast_base.py:273-287."""
         fusable = (isinstance(events, torch.Tensor) and events.is_cuda and isinstance(warp, torch.Tensor)

@@ -142,6 +142,24 @@ int cmax_tile_flow_upsample(const float* motion, int hp, int wp, int pad_h, int 
 int cmax_tile_flow_upsample_backward(const float* grad_dense, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W,
                                      float* grad_motion, cmax_stream_t stream);
 
+/* ------------------------------------------------------------------ time-aware flow voxel   */
+typedef enum {
+  CMAX_SCHEME_UPWIND = 0,  /* "upwind"   src/utils/flow_utils.py:439-493 */
+  CMAX_SCHEME_BURGERS = 1  /* "burgers"  src/utils/flow_utils.py:567-639 */
+} cmax_voxel_scheme;
+/* construct_dense_flow_voxel_torch (src/utils/flow_utils.py:99-161): dense [2,H,W] (the flow at t0) -> voxel
+ * [time_bin,2,H,W] by explicit upwind / inviscid-Burgers steps of dt = 1/time_bin, forward in time from level t0 up and
+ * backward (sign-flipped flow) from t0 down; t0 = time_bin/2 when t0_middle, else 0.  fp32, bit-identical to the
+ * reference's torch fp32 result.  One launch per 8 levels (both sides of t0 in the same launch).  The backward is the
+ * exact adjoint (torch's even split of d max(x,0)/dx at x == 0 included), gather form, no atomics: grad_voxel
+ * [time_bin,2,H,W] -> grad_dense [2,H,W].  `dense` and `voxel` are the forward's input and output.  workspace:
+ * cmax_flow_voxel_workspace_bytes(H,W) bytes (only touched when one side of t0 has more than 8 levels; may be NULL
+ * otherwise). */
+size_t cmax_flow_voxel_workspace_bytes(int H, int W);
+int cmax_flow_voxel(const float* dense, int H, int W, int time_bin, int scheme, int t0_middle, float* voxel, cmax_stream_t stream);
+int cmax_flow_voxel_backward(const float* dense, const float* voxel, const float* grad_voxel, int H, int W, int time_bin, int scheme,
+                             int t0_middle, float* grad_dense, void* workspace, cmax_stream_t stream);
+
 /* ------------------------------------------------------------------ fused hot path */
 /* Event order inside a plan.  The order never changes results beyond fp32 summation order; it changes locality. */
 typedef enum {

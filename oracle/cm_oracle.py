@@ -432,3 +432,84 @@ def upsample_tile_flow(motion: torch.Tensor, image_shape, patch_size, sliding_wi
     padded = torch.nn.functional.pad(-motion[None], (pad_w, pad_w, pad_h, pad_h), mode="replicate")
     dense = torch.nn.functional.interpolate(padded, size=(full_h, full_w), mode="bilinear", align_corners=False)[0]
     return dense[..., h1:h1 + image_shape[0], w1:w1 + image_shape[1]]
+
+
+# --------------------------------------------------------------------------------------
+# time-aware flow voxel   (src/utils/flow_utils.py:99-161, 439-493, 567-639)
+# --------------------------------------------------------------------------------------
+def _shift_rows(a: torch.Tensor, k: int) -> torch.Tensor:
+    """a[i + k] with the border row replicated (k = +1 / -1)."""
+    H = a.shape[-2]
+    idx = torch.clamp(torch.arange(H) + k, 0, H - 1)
+    return a.index_select(-2, idx)
+
+
+def _shift_cols(a: torch.Tensor, k: int) -> torch.Tensor:
+    W = a.shape[-1]
+    idx = torch.clamp(torch.arange(W) + k, 0, W - 1)
+    return a.index_select(-1, idx)
+
+
+def _one_sided(a: torch.Tensor):
+    """(row-backward, row-forward, col-backward, col-forward) differences of [H,W]; a replicated neighbour makes the
+    difference across the image border exactly zero (the reference pads `torch.diff` with zeros)."""
+    return (a - _shift_rows(a, -1), _shift_rows(a, 1) - a, a - _shift_cols(a, -1), _shift_cols(a, 1) - a)
+
+
+def flow_voxel_step(flow: torch.Tensor, dt: float, scheme: str) -> torch.Tensor:
+    """One explicit time step of a [2,H,W] flow (channel 0 = row component).  Negative dt = backward in time: the
+    reference flips the sign of the flow, steps by |dt| and flips back (flow_utils.py:459-462, 587-590).
+    upwind: flow_utils.py:464-493;  burgers: flow_utils.py:592-639.  The order of the additions follows the reference's
+    expression, so fp32 results are bit-identical to it."""
+    if dt == 0:
+        return flow
+    sgn = 1.0 if dt > 0 else -1.0
+    h = abs(dt)
+    f = flow * sgn
+    u, v = f[0], f[1]
+    zero = torch.zeros_like(u)
+    up, um = torch.maximum(u, zero), torch.minimum(u, zero)
+    vp, vm = torch.maximum(v, zero), torch.minimum(v, zero)
+    if scheme == "upwind":
+        out = []
+        for c in (u, v):
+            rb, rf, cb, cf = _one_sided(c)
+            out.append(c - h * (((up * rb + um * rf) + vp * cb) + vm * cf))
+        return torch.stack(out) * sgn
+    if scheme == "burgers":
+        u_b, u_f = _shift_rows(u, -1), _shift_rows(u, 1)
+        v_b, v_f = _shift_cols(v, -1), _shift_cols(v, 1)
+        bu = ((u * u) * torch.sign(u) + torch.maximum(torch.sign(u_b), zero) * ((-u_b) * u_b)
+              - torch.minimum(torch.sign(u_f), zero) * (u_f * u_f)) / 2.0
+        bv = ((v * v) * torch.sign(v) + torch.maximum(torch.sign(v_b), zero) * ((-v_b) * v_b)
+              - torch.minimum(torch.sign(v_f), zero) * (v_f * v_f)) / 2.0
+        _, _, u_cb, u_cf = _one_sided(u)
+        v_rb, v_rf, _, _ = _one_sided(v)
+        nu = u - h * ((vp * u_cb + vm * u_cf) + bu)
+        nv = v - h * ((up * v_rb + um * v_rf) + bv)
+        return torch.stack([nu, nv]) * sgn
+    raise NotImplementedError(f"scheme {scheme!r}")
+
+
+def flow_voxel(dense: torch.Tensor, time_bin: int, scheme: str = "upwind", t0_location: str = "middle") -> torch.Tensor:
+    """[2,H,W] flow at t0 -> [time_bin,2,H,W].  Differentiable by torch autograd.  flow_utils.py:99-161: level t0
+    (0 or time_bin // 2) holds the input; levels above are stepped forward by dt = 1/time_bin, levels below backward.
+    The reference's Burgers backward loop also runs for i = 0 and so writes level -1 (= time_bin - 1) one more backward
+    step away from level 0 (flow_utils.py:140-141); the forward loop then overwrites that level -- unless t0 is the
+    last level (time_bin 1, or time_bin 2 with t0 in the middle), where the write sticks."""
+    if t0_location not in ("first", "middle"):
+        raise NotImplementedError(f"t0_location {t0_location!r} not supported")
+    if scheme not in ("upwind", "burgers"):
+        raise NotImplementedError(f"scheme {scheme!r}")
+    T = int(time_bin)
+    h = 1.0 / T
+    t0 = 0 if t0_location == "first" else T // 2
+    levels = [None] * T
+    levels[t0] = dense
+    for i in range(t0, 0, -1):
+        levels[i - 1] = flow_voxel_step(levels[i], -h, scheme)
+    if scheme == "burgers":
+        levels[T - 1] = flow_voxel_step(levels[0], -h, scheme)
+    for i in range(t0, T - 1):
+        levels[i + 1] = flow_voxel_step(levels[i], h, scheme)
+    return torch.stack(levels)

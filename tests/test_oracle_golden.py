@@ -163,3 +163,40 @@ def test_tile_flow_upsample_matches_reference(golden_tileflow, case):
         np.testing.assert_allclose(dense.detach().numpy(), ref, rtol=tol, atol=tol * 8)
         (gm,) = torch.autograd.grad((dense * torch.from_numpy(g[f"{case}/{tag}/grad_dense"]).to(dt)).sum(), m)
         np.testing.assert_allclose(gm.numpy(), g[f"{case}/{tag}/grad_motion"], rtol=tol * 10, atol=tol * 100)
+
+
+FLOWVOXEL_CASES = ("up_mid10", "bg_mid10", "up_first7", "bg_first7", "bg_mid2", "bg_first2", "up_mid2", "up_mid3", "bg_mid3", "bg_first1",
+                   "up_first1", "bg_mid21", "up_first20", "bg_mvsec")
+
+
+@pytest.fixture(scope="module")
+def golden_flowvoxel():
+    import os
+    from conftest import GOLDEN_DIR
+    return np.load(os.path.join(GOLDEN_DIR, "reference_flowvoxel.npz"))
+
+
+@pytest.mark.parametrize("case", FLOWVOXEL_CASES)
+def test_flow_voxel_matches_reference(golden_flowvoxel, case):
+    """Upwind / Burgers flow voxel and its autograd adjoint vs the reference's construct_dense_flow_voxel_torch
+    (src/utils/flow_utils.py:99-161): BIT-EXACT voxel in fp32 and fp64, gradient to rounding."""
+    g = golden_flowvoxel
+    H, W, T, sc, mid = (int(v) for v in g[f"{case}/meta"])
+    scheme, t0 = ("burgers" if sc else "upwind"), ("middle" if mid else "first")
+    for tag, dt, tol in (("f32", torch.float32, 2e-6), ("f64", torch.float64, 1e-14)):
+        if f"{case}/voxel_{tag}" not in g.files:
+            continue
+        x = torch.from_numpy(g[f"{case}/flow"]).to(dt).requires_grad_(True)
+        vox = O.flow_voxel(x, T, scheme, t0)
+        assert np.array_equal(vox.detach().numpy(), g[f"{case}/voxel_{tag}"]), (case, tag)
+        (gr,) = torch.autograd.grad((vox * torch.from_numpy(g[f"{case}/cot"]).to(dt)).sum(), x)
+        ref = g[f"{case}/grad_{tag}"]
+        assert np.abs(gr.numpy() - ref).max() <= tol * max(np.abs(ref).max(), 1e-30), (case, tag)
+
+
+def test_flow_voxel_rejects_unknown_arguments():
+    x = torch.zeros(2, 4, 5)
+    with pytest.raises(NotImplementedError):
+        O.flow_voxel(x, 3, "upwind", "last")
+    with pytest.raises(NotImplementedError):
+        O.flow_voxel(x, 3, "nearest", "middle")

@@ -146,3 +146,59 @@ def test_scipy_lbfgs_recovers_translation():
     # ... and the same loop driven by the CPU oracle ends in the same place
     assert abs(best.fun - best_oracle.fun) <= 1e-3 * abs(best_oracle.fun), (best.fun, best_oracle.fun)
     assert np.allclose(best.x, best_oracle.x, atol=5e-2), (best.x, best_oracle.x)
+
+
+@pytest.mark.parametrize("pyramid", [False, True])
+def test_mixin_time_aware_motion_to_dense_flow(pyramid):
+    """The time-aware seam: `motion_to_dense_flow` of the mixin (tile-flow upsample + Burgers voxel, both CUDA) against
+    the reference's composition restated with the oracle's torch functions, value and gradient, for both reference
+    signatures (time_aware_patch_contrast.py:42-80 and patch_contrast_pyramid.py:464-516)."""
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.solver import B200CostMixin
+    dev = torch.device("cuda:0")
+    ev, motion, shape = _problem(H=64, W=96, patch=(4, 6))
+    window = (16, 16)
+
+    class RefTimeAware(_ReferenceSeam):
+        is_time_aware, scale_later, time_bin, flow_interpolation, t0_flow_location = True, True, 10, "burgers", "middle"
+        image_shape, patch_size, sliding_window, patch_shift = shape, window, window, (0, 0)
+        motion_vector_size, patch_image_size, filter_type, current_scale = 2, (4, 6), "bilinear", 1
+
+        def interpolate_dense_flow_from_patch_tensor(self, m):
+            return O.upsample_tile_flow(m, self.image_shape, self.patch_size, self.sliding_window, self.patch_shift)
+
+        def motion_to_dense_flow(self, m, t_scale=1.0):
+            if isinstance(m, dict):
+                dense = self.interpolate_dense_flow_from_patch_tensor(m[self.current_scale])
+                scale = dense.max()
+                return O.flow_voxel(dense * t_scale / scale, self.time_bin, self.flow_interpolation, self.t0_flow_location) * scale / t_scale
+            dense = self.interpolate_dense_flow_from_patch_tensor(m)
+            scale = m.max()
+            return O.flow_voxel(dense / scale, self.time_bin, self.flow_interpolation, self.t0_flow_location) * scale
+
+    class Fast(B200CostMixin, RefTimeAware):
+        pass
+
+    ref = RefTimeAware(B, shape, "multi_focal_normalized_gradient_magnitude", 1)
+    fast = Fast(B, shape, "multi_focal_normalized_gradient_magnitude", 1)
+    cot = torch.from_numpy(np.random.default_rng(1).standard_normal((10, 2) + shape))
+    out = {}
+    for tag, slv, d in (("ref", ref, "cpu"), ("fast", fast, dev)):
+        m = motion.clone().to(d).requires_grad_(True)
+        vox = slv.motion_to_dense_flow({1: m}, 0.7) if pyramid else slv.motion_to_dense_flow(m)
+        assert vox.shape == (10, 2) + shape and vox.dtype == torch.float64
+        (g,) = torch.autograd.grad((vox * cot.to(d)).sum(), m)
+        out[tag] = (vox.detach().cpu().numpy(), g.cpu().numpy())
+    np.testing.assert_allclose(out["fast"][0], out["ref"][0], rtol=1e-5, atol=2e-5)
+    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-4 * np.linalg.norm(out["ref"][1])
+    # ... and the whole objective through the mixin's calculate_cost on the voxel it produced
+    evd = ev.to(dev)
+    m = motion.clone().to(dev).requires_grad_(True)
+    loss = fast.calculate_cost(evd, fast.motion_to_dense_flow(m), "dense-flow-voxel", m)
+    (g,) = torch.autograd.grad(loss, m)
+    m32 = motion.clone().float().requires_grad_(True)
+    val = O.objective(ev.float(), ref.motion_to_dense_flow(m32), shape, motion_model="dense-flow-voxel",
+                      cost="multi_focal_normalized_gradient_magnitude", sigma=1.0)
+    (g_ref,) = torch.autograd.grad(val, m32)
+    assert abs(float(loss) - float(val)) <= 2e-5 * abs(float(val))
+    assert np.linalg.norm(g.cpu().numpy() - g_ref.numpy()) <= 5e-4 * np.linalg.norm(g_ref.numpy())
