@@ -182,7 +182,8 @@ def run_b200(args) -> None:
     t_range = global_time_range(ev, group)
     obj = ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow", sigma=0.0, order=args.order,
                             process_group=group, t_range=t_range, exchange=args.exchange)
-    obj.plan.set_variant(args.vote_variant, args.grad_variant)
+    if args.vote_variant >= 0 or args.grad_variant >= 0:  # default: what the plan chose (strip kernels when the batch qualifies)
+        obj.plan.set_variant(args.vote_variant if args.vote_variant >= 0 else 5, args.grad_variant if args.grad_variant >= 0 else 5)
     compact = obj.plan.set_compact(not args.no_compact)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
@@ -410,8 +411,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--order", choices=("asis", "tile", "pixel"), default="pixel")
-    ap.add_argument("--vote-variant", type=int, default=2)
-    ap.add_argument("--grad-variant", type=int, default=2)
+    ap.add_argument("--vote-variant", type=int, default=-1, help="-1 = the plan's choice (5 = strip kernels when the batch qualifies, else 2)")
+    ap.add_argument("--grad-variant", type=int, default=-1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
     ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer", help="multi-GPU: NCCL all-reduce or NVLink peer-memory kernels")

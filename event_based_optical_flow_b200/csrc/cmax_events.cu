@@ -8,6 +8,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "cmax_plan.cuh"
 
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(256) validate_kernel(const float* __restrict__
 // (PIXEL order).  Also counts events per tile for the chunk list of the privatised kernels.
 __global__ void __launch_bounds__(256) sort_keys_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
                                                         int tiles_x, int by_pixel, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ idx, uint32_t* __restrict__ tile_counts) {
+                                                        uint32_t* __restrict__ idx, uint32_t* __restrict__ tile_counts,
+                                                        uint32_t* __restrict__ key_counts) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     int r, c;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) sort_keys_kernel(const float* __restrict_
     keys[i] = by_pixel ? (tile * (uint32_t)(kTile * kTile) + (uint32_t)((r % kTile) * kTile + (c % kTile))) : tile;
     idx[i] = (uint32_t)i;
     atomicAdd(&tile_counts[tile], 1u);
+    if (key_counts != nullptr) atomicAdd(&key_counts[keys[i]], 1u);
   }
 }
 
@@ -175,6 +178,44 @@ __global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ 
   }
 }
 
+// ---- strips: the packed format of the strip kernels (cmax_lean.cu).  Events are in source-pixel order, so the events of
+// one pixel are a run; every run is cut into STRIPS of kRunE events and the last strip of a run is padded, so that a
+// strip never mixes two source pixels.  One thread of a strip kernel walks one strip: the source pixel -- hence its float
+// coordinates, flat index and flow vector -- is a per-strip constant read from a 4-byte header instead of a per-event
+// key that has to be compared, and an event is just its 4-byte (normalised) time.  A warp-tile is 32 strips:
+//   [32 headers: row << 17 | col << 4 | count][32 x float4: times 0..3 of lane's strip][32 x float4: times 4..7]
+// = 1152 bytes, one TMA bulk copy; both float4 blocks are read with conflict-free LDS.128.  4.5 bytes per event instead
+// of 8, plus the padding (half a strip per occupied pixel on average: ~6 % at 55 events per pixel).
+__global__ void __launch_bounds__(256) strip_counts_kernel(const uint32_t* __restrict__ key_counts, int64_t n_keys,
+                                                           uint32_t* __restrict__ key_strips) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_keys; k += (int64_t)gridDim.x * blockDim.x)
+    key_strips[k] = k < n_keys ? (key_counts[k] + kRunE - 1) / kRunE : 0u;
+}
+
+__global__ void __launch_bounds__(256) pack_strips_kernel(const float4* __restrict__ ev, const uint32_t* __restrict__ sorted_keys, int64_t n,
+                                                          const uint32_t* __restrict__ key_counts, const uint32_t* __restrict__ key_first,
+                                                          const uint32_t* __restrict__ key_strip0, int H, int W,
+                                                          const cmax_time_params_t* __restrict__ tp, int with_dt,
+                                                          unsigned char* __restrict__ out) {
+  const float ref = tp->ref[0], period = tp->period[0];
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t key = sorted_keys[j];
+    const uint32_t rank = (uint32_t)j - key_first[key];
+    const uint32_t strip = key_strip0[key] + rank / kRunE, slot = rank % kRunE;
+    const float4 e = ev[j];
+    unsigned char* tile = out + (size_t)(strip / 32) * kStripTileBytes;
+    const uint32_t lane = strip % 32;
+    const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
+    reinterpret_cast<float*>(tile + 128 + (slot / 4) * 512 + lane * 16)[slot % 4] = tz;
+    if (slot == 0) {
+      int r, c;
+      source_pixel(e.x, e.y, H, W, &r, &c);
+      const uint32_t left = key_counts[key] - rank;
+      reinterpret_cast<uint32_t*>(tile)[lane] = ((uint32_t)r << 17) | ((uint32_t)c << 4) | (left < (uint32_t)kRunE ? left : (uint32_t)kRunE);
+    }
+  }
+}
+
 // slots of the packed copy: whole warp-tiles of kWarpTile events
 static inline int64_t packed_slots(int64_t n) { return std::max<int64_t>(1, (n + kWarpTile - 1) / kWarpTile) * kWarpTile; }
 
@@ -189,6 +230,8 @@ static int bits_for(uint64_t v) {
 struct PlanLayout {
   size_t off_packed;
   size_t off_params, off_minmax, off_status, off_events, off_keys[2], off_idx[2], off_counts, off_chunks, off_temp, temp_bytes, total;
+  size_t off_kcnt, off_kstr, off_kfirst, off_kstrip0, off_strips, off_scan_temp, scan_temp_bytes;
+  int64_t n_keys, strip_capacity;  // strips the region holds (whole warp-tiles)
   int tiles_x, tiles_y, n_tiles, max_chunks, key_bits;
 };
 
@@ -223,6 +266,22 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
     }
     L.temp_bytes = temp;
     L.off_temp = off; off = align_up(off + temp + 256, 256);
+    if (order == CMAX_ORDER_PIXEL) {  // strips (see pack_strips_kernel): allowed to be up to 1.5x the events
+      L.n_keys = (int64_t)L.n_tiles * kTile * kTile;
+      L.strip_capacity = ((n + n / 2) / kRunE + 31) / 32 * 32 + 32;
+      for (size_t* o : {&L.off_kcnt, &L.off_kstr, &L.off_kfirst, &L.off_kstrip0}) {
+        *o = off; off = align_up(off + (size_t)(L.n_keys + 1) * sizeof(uint32_t), 256);
+      }
+      size_t st = 0;
+      const cudaError_t e2 = cub::DeviceScan::ExclusiveSum(nullptr, st, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(L.n_keys + 1), (cudaStream_t)0);
+      if (e2 != cudaSuccess) {
+        cuda_fail(e2, "cub::DeviceScan::ExclusiveSum (temp-storage query)");
+        return false;
+      }
+      L.scan_temp_bytes = st;
+      L.off_scan_temp = off; off = align_up(off + st + 256, 256);
+      L.off_strips = off; off = align_up(off + (size_t)(L.strip_capacity / 32) * kStripTileBytes, 256);
+    }
   }
   L.total = off;
   *out = L;
@@ -361,8 +420,11 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
     cub::DoubleBuffer<uint32_t> dv(reinterpret_cast<uint32_t*>(ws + L.off_idx[0]), reinterpret_cast<uint32_t*>(ws + L.off_idx[1]));
     const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
     PLAN_CHECK(cudaMemsetAsync(counts, 0, (size_t)L.n_tiles * sizeof(uint32_t), s));
+    const bool try_strips = order == CMAX_ORDER_PIXEL && p->compact_ok && H < (1 << 13) && W < (1 << 13);
+    uint32_t* kcnt = try_strips ? reinterpret_cast<uint32_t*>(ws + L.off_kcnt) : nullptr;
+    if (try_strips) PLAN_CHECK(cudaMemsetAsync(kcnt, 0, (size_t)(L.n_keys + 1) * sizeof(uint32_t), s));
     sort_keys_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, L.tiles_x, order == CMAX_ORDER_PIXEL, dk.Current(),
-                                          dv.Current(), counts);
+                                          dv.Current(), counts, kcnt);
     size_t temp = L.temp_bytes + 256;
     PLAN_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.off_temp, temp, dk, dv, (int)n, 0, L.key_bits, s));  // stable
     gather_events_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, dv.Current(), sorted);
@@ -395,6 +457,29 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
     p->chunks = d_chunks;
     p->n_chunks = (int)h_chunks.size();
     p->order = order;
+    if (try_strips) {
+      uint32_t* kstr = reinterpret_cast<uint32_t*>(ws + L.off_kstr);
+      uint32_t* kfirst = reinterpret_cast<uint32_t*>(ws + L.off_kfirst);
+      uint32_t* kstrip0 = reinterpret_cast<uint32_t*>(ws + L.off_kstrip0);
+      strip_counts_kernel<<<(int)std::min<int64_t>(kNumSMs * 4, (L.n_keys + 256) / 256), 256, 0, s>>>(kcnt, L.n_keys, kstr);
+      size_t st = L.scan_temp_bytes + 256;
+      PLAN_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.off_scan_temp, st, kcnt, kfirst, (int)(L.n_keys + 1), s));
+      st = L.scan_temp_bytes + 256;
+      PLAN_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.off_scan_temp, st, kstr, kstrip0, (int)(L.n_keys + 1), s));
+      uint32_t h_strips = 0;
+      PLAN_CHECK(cudaMemcpyAsync(&h_strips, kstrip0 + L.n_keys, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+      PLAN_CHECK(cudaStreamSynchronize(s));
+      if ((int64_t)h_strips <= L.strip_capacity - 32) {  // dense enough: the padding stays below 50 %
+        p->strips = ws + L.off_strips;
+        p->n_strips = (int64_t)h_strips;
+        p->sorted_keys = dk.Current();
+        p->key_counts = kcnt;
+        p->key_first = kfirst;
+        p->key_strip0 = kstrip0;
+        p->vote_variant = 5;
+        p->grad_variant = 5;
+      }
+    }
   }
 #undef PLAN_CHECK
   {
@@ -422,8 +507,8 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
-  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 4, "cmax_plan_set_variant: vote_variant must be in [0,4]");
-  CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 4, "cmax_plan_set_variant: grad_variant must be in [0,4]");
+  CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 5, "cmax_plan_set_variant: vote_variant must be in [0,5]");
+  CMAX_REQUIRE(grad_variant >= 0 && grad_variant <= 5, "cmax_plan_set_variant: grad_variant must be in [0,5]");
   plan->vote_variant = vote_variant;
   plan->grad_variant = grad_variant;
   return CMAX_OK;
@@ -474,6 +559,13 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
     else
       repack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
                                                                  plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
+    if (plan->strips != nullptr) {
+      const int64_t tiles = (plan->n_strips + 31) / 32;
+      CMAX_CUDA_CHECK(cudaMemsetAsync(plan->strips, 0, (size_t)tiles * kStripTileBytes, as_stream(stream)));
+      pack_strips_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->sorted_keys, plan->n,
+                                                               plan->key_counts, plan->key_first, plan->key_strip0, plan->H, plan->W,
+                                                               plan->d_params, plan->packed_has_dt, static_cast<unsigned char*>(plan->strips));
+    }
     CMAX_CUDA_CHECK(cudaGetLastError());
   }
   return CMAX_OK;

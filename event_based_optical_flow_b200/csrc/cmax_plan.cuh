@@ -11,6 +11,7 @@ constexpr int kHalo = 16;
 constexpr int kWin = kTile + 2 * kHalo;  // 64
 constexpr int kRunE = 8;                  // consecutive events one thread of a run kernel walks
 constexpr int kWarpTile = 32 * kRunE;    // events per warp-tile of the packed copy
+constexpr int kStripTileBytes = 128 + 32 * kRunE * 4;  // 32 strip headers + 32 strips of kRunE times (cmax_events.cu)
 constexpr int kChunk = 8192;             // events per CTA work item (bounds the fixed-point range, see cmax_fused.cu)
 
 struct Chunk {
@@ -34,6 +35,14 @@ struct cmax_plan {
   // (tz, row<<16|col) in the same warp-tile order; else 16 bytes (x, y, tz, bits(src)).
   int compact_ok;  // eligibility (from validation)
   int compact;     // format currently packed
+  // strips: source-pixel runs cut into padded strips of kRunE events (pack_strips_kernel in cmax_events.cu); NULL when
+  // the batch does not qualify (not pixel-ordered, fractional coordinates, or too sparse for the padding to pay)
+  void* strips;
+  int64_t n_strips;
+  const uint32_t* sorted_keys;
+  const uint32_t* key_counts;
+  const uint32_t* key_first;
+  const uint32_t* key_strip0;
   int64_t n;
   int H, W, pad_h, pad_w, Hp, Wp;
   float t_min, t_max;

@@ -243,7 +243,7 @@ def _synthetic(n, H, W, seed=0, max_flow=10.0):
     return torch.from_numpy(ev), torch.from_numpy(flow)
 
 
-@pytest.mark.parametrize("variants", ((2, 2), (3, 3), (4, 4), (2, 4), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
+@pytest.mark.parametrize("variants", ((5, 5), (5, 2), (2, 5), (2, 2), (3, 3), (4, 4), (2, 4), (0, 0), (1, 0), (0, 1), (2, 1), (0, 2)))
 def test_one_million_events_vs_oracle(B, dev, variants):
     H, W = 260, 346
     ev, flow = _synthetic(1_000_000, H, W, seed=1)
