@@ -55,6 +55,17 @@ def synth_flows(k: int, seed: int) -> np.ndarray:
     return torch.nn.functional.interpolate(grid, size=(H, W), mode="bilinear", align_corners=False).numpy()
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two event kernels at this workload, from the
+# committed `ncu --set full` capture profiles/r01_ncu_r1m.txt (strip kernels) / r01_ncu_r1k.txt (run kernels)
+TRAFFIC_SOURCE = "profiles/r01_ncu_r1m.txt (strips) / r01_ncu_r1k.txt (runs): dram__bytes_read.sum + dram__bytes_write.sum per launch"
+_TRAFFIC = {"K1 vote (vote_strips_kernel)": 26.09e6, "K3 grad (grad_strips_kernel)": 26.81e6,
+            "K1 vote (vote_runs_kernel)": 42.18e6, "K3 grad (grad_runs_kernel)": 42.91e6}
+
+
+def traffic_of(kernel: str):
+    return _TRAFFIC.get(kernel)
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
     """Polls SM clock + throttle reasons through NVML while the timed regions run."""
@@ -185,6 +196,7 @@ def run_b200(args) -> None:
     if args.vote_variant >= 0 or args.grad_variant >= 0:  # default: what the plan chose (strip kernels when the batch qualifies)
         obj.plan.set_variant(args.vote_variant if args.vote_variant >= 0 else 5, args.grad_variant if args.grad_variant >= 0 else 5)
     compact = obj.plan.set_compact(not args.no_compact)
+    strips = args.vote_variant in (-1, 5) and args.grad_variant in (-1, 5) and args.order == "pixel"  # (dense synthetic batch: the plan builds strips)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
 
@@ -347,8 +359,8 @@ def run_b200(args) -> None:
             stage_ms /= 10
             # algorithmic bytes per launch (DESIGN.md "Kernels"): K1 = 16 B/event + flow read 8 HW + IWE write 4 HW;
             # K3 = 16 B/event + flow read 8 HW + dL/dIWE read 4 HW + gradient write 8 HW
-            kernels = {"vote_fused_kernel(K1)": {"ms": k1, "bytes": 16 * n + 12 * HWp},
-                       "grad_fused_kernel(K3)": {"ms": k3, "bytes": 16 * n + 20 * HWp}}
+            kernels = {"K1 vote (vote_strips_kernel)" if strips else "K1 vote (vote_runs_kernel)": {"ms": k1, "bytes": 16 * n + 12 * HWp},
+                       "K3 grad (grad_strips_kernel)" if strips else "K3 grad (grad_runs_kernel)": {"ms": k3, "bytes": 16 * n + 20 * HWp}}
             for v in kernels.values():
                 v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
         step_bytes = 32 * n + 32 * HWp  # per CM iteration, single reference time, dense flow
@@ -356,7 +368,7 @@ def run_b200(args) -> None:
         if kernels:
             dom = max(kernels, key=lambda k: kernels[k]["ms"])
             roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": kernels[dom]["GBps"] / peak, "traffic": traffic_of(dom), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
                     "kernels": kernels, "stages_in_situ_ms": {"vote(K1+fold)": stage_ms[0], "cost(combine+gq)": stage_ms[1],
                                                               "grad(memset+K3)": stage_ms[2]}, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
         else:
@@ -372,14 +384,14 @@ def run_b200(args) -> None:
 
         clocks = sampler.finish() if sampler else None
         # K1 vote, fold(+variance+cost), gradient pictures, K3 grad; the eager 3-stage path adds the combine kernel
-        per_step_kernels = (4 if graph is not None else 5) if world == 1 else (6 if args.exchange == 'peer' else 5)
+        per_step_kernels = 4 if world == 1 else (6 if args.exchange == 'peer' else 5)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "config2: 5M events per GPU, 260x346 dense flow, variance cost+grad", "events_per_gpu": n,
                        "image": [H, W], "flow": "smooth (16x16 grid upsampled), |f|<=10px, fresh per step",
-                       "event_order": args.order, "packed_event_bytes": 8 if compact else 16, "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
+                       "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16), "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
                        "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
                                        ("NCCL all-reduce" if args.exchange == "nccl" else "NVLink peer-memory kernels + in-stream barriers"))
