@@ -384,7 +384,7 @@ def run_b200(args) -> None:
 
         clocks = sampler.finish() if sampler else None
         # K1 vote, fold(+variance+cost), gradient pictures, K3 grad; the eager 3-stage path adds the combine kernel
-        per_step_kernels = 4 if world == 1 else (6 if args.exchange == 'peer' else 5)
+        per_step_kernels = 4 if world == 1 else {'peer': 6, 'push': 8, 'nccl': 5}[args.exchange]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -394,7 +394,8 @@ def run_b200(args) -> None:
                        "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16), "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
                        "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
-                                       ("NCCL all-reduce" if args.exchange == "nccl" else "NVLink peer-memory kernels + in-stream barriers"))
+                                       {"nccl": "NCCL all-reduce", "peer": "NVLink peer-memory reads + in-stream barriers",
+                                        "push": "NVLink pushes into per-rank mailboxes + flags (no barrier kernels)"}[args.exchange])
                        if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host pinned flow -> device, value_and_grad through the Python API, cost+grad -> host, sync; events resident"},
@@ -427,7 +428,8 @@ def main():
     ap.add_argument("--grad-variant", type=int, default=-1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
-    ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer", help="multi-GPU: NCCL all-reduce or NVLink peer-memory kernels")
+    ap.add_argument("--exchange", choices=("nccl", "peer", "push"), default="peer",
+                    help="multi-GPU: NCCL all-reduce, NVLink peer reads behind barriers, or NVLink pushes into mailboxes with flags")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:

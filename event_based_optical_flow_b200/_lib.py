@@ -70,9 +70,10 @@ _SIGNATURES = {
     "cmax_objective": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, _p, _p, _p]),
     "cmax_objective_iwe_offset": (_sz, [_p]),
     "cmax_objective_full_iwe_offset": (_sz, [_p]),
-    "cmax_objective_reduce_iwe": (_i, [_p, C.POINTER(CostSpec), C.POINTER(_p), _i, _p, _p, _p, C.POINTER(C.c_int32), _p]),
+    "cmax_objective_reduce_iwe": (_i, [_p, C.POINTER(CostSpec), C.POINTER(_p), _i, _p, _p, _p, C.POINTER(C.c_int32), _p, _p, _p]),
+    "cmax_push": (_i, [_p, _i64, C.POINTER(_p), C.POINTER(_p), _i, _p, _p, _p]),
     "cmax_objective_cost_after_reduce": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _i, _p, _p]),
-    "cmax_reduce_peers": (_i, [C.POINTER(_p), _i, _i64, _p, _p]),
+    "cmax_reduce_peers": (_i, [C.POINTER(_p), _i, _i64, _p, _p, _p, _p]),
     "cmax_combine_cost": (_i, [_p, _i, _i, _i, _p, C.POINTER(_f), _i, _i, _p, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

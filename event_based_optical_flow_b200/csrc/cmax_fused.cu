@@ -813,22 +813,115 @@ struct PeerPtrs {
   int n;
 };
 
+// ---- push exchange: flags instead of barrier kernels.  Every rank owns a MAILBOX in symmetric memory: one slot per
+// source rank and one 32-bit flag per source rank.  A producer (push_kernel) stores its partial result into its slot of
+// EVERY rank's mailbox (posted NVLink stores, no round trip), fences at system scope, and its last CTA then stores the new
+// epoch into its flag on every rank.  A consumer kernel starts by waiting until all flags of its own mailbox carry the
+// current epoch and then reads only LOCAL memory.  Two mailboxes alternate (IWE, gradient), which is what makes reuse
+// safe without a barrier: a rank can only start overwriting its IWE slots for evaluation e+1 after it has seen every
+// peer's gradient flag of evaluation e, and a peer raises that flag (stream order) after its IWE reduction of e.
+struct PushPtrs {
+  float* slot[CMAX_MAX_PEERS];
+  uint32_t* flag[CMAX_MAX_PEERS];
+  int n;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Block until flags[0..n) have all reached *epoch (called by every CTA of a consumer kernel).  A peer that never
+// arrives (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which surfaces as a CUDA error.
+__device__ __forceinline__ void wait_flags(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch, int n) {
+  if (flags == nullptr) return;
+  if ((int)threadIdx.x < n) {
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(epoch);
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - e) < 0) {
+      if (clock64() - t0 > 8000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) push_kernel(const float* __restrict__ src, int64_t n, PushPtrs dst, uint32_t* __restrict__ epoch,
+                                                   uint32_t* __restrict__ counter) {
+  __shared__ bool last;
+  if ((n & 3) == 0) {  // (slots and sources are 256-byte aligned)
+    const int64_t n4 = n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(src)[i];
+      for (int q = 0; q < dst.n; ++q) reinterpret_cast<float4*>(dst.slot[q])[i] = v;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const float v = src[i];
+      for (int q = 0; q < dst.n; ++q) dst.slot[q][i] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // one system-scope fence per CTA (fences are cumulative: the stores of the whole CTA, ordered before this thread by
+    // the barrier, are visible system-wide before the CTA is counted); a fence per thread costs ~20 us per launch
+    __threadfence_system();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence_system();
+    const uint32_t e = *epoch + 1u;
+    *epoch = e;
+    *counter = 0u;
+    for (int q = 0; q < dst.n; ++q) st_release_sys(dst.flag[q], e);
+  }
+}
+
+__global__ void wait_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch, int n) { wait_flags(flags, epoch, n); }
+
 __global__ void __launch_bounds__(kStatBlock) peer_iwe_kernel(PeerPtrs peers, float* __restrict__ iwe, int Hp, int Wp, int want_var, int omit,
                                                               StatAcc* __restrict__ sacc, double* __restrict__ stats, int want_combine,
-                                                              CombineDev cd, unsigned int* __restrict__ ctas_done) {
+                                                              CombineDev cd, unsigned int* __restrict__ ctas_done,
+                                                              const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch) {
   __shared__ double red[kStatBlock / 32];
   __shared__ bool all_done;
+  wait_flags(flags, epoch, peers.n);  // push exchange: every rank's partial image has landed in this rank's mailbox
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
   double s = 0.0, q = 0.0;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + img * HW + p);  // L2-coherent: the data was written by another GPU
-    iwe[img * HW + p] = v;
+  auto account = [&](int64_t p, float v) {
     const int rr = (int)(p / Wp), c = (int)(p % Wp);
     if (want_var && (!omit || (rr >= 1 && rr <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
       s += (double)v;
       q += (double)v * (double)v;
+    }
+  };
+  if ((HW & 3) == 0) {
+    // 16-byte loads, all ranks' loads of a thread in flight together: one NVLink round trip per thread instead of 4 n
+    for (int64_t p4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p4 < (HW >> 2); p4 += (int64_t)gridDim.x * blockDim.x) {
+      float4 part[CMAX_MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
+        if (r < peers.n) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.p[r] + img * HW) + p4);  // L2-coherent: written by another GPU
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
+        if (r < peers.n) {  // rank order: every rank computes the bit-identical sum
+          v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
+        }
+      reinterpret_cast<float4*>(iwe + img * HW)[p4] = v;
+      account(4 * p4, v.x); account(4 * p4 + 1, v.y); account(4 * p4 + 2, v.z); account(4 * p4 + 3, v.w);
+    }
+  } else {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + img * HW + p);
+      iwe[img * HW + p] = v;
+      account(p, v);
     }
   }
   if (want_var) {
@@ -849,11 +942,29 @@ __global__ void __launch_bounds__(kStatBlock) peer_iwe_kernel(PeerPtrs peers, fl
 }
 
 // out[i] = sum over ranks of peers[r][i], rank order (the motion-gradient exchange)
-__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs peers, int64_t n, float* __restrict__ out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + i);
-    out[i] = v;
+__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs peers, int64_t n, float* __restrict__ out, const uint32_t* __restrict__ flags,
+                                                       const uint32_t* __restrict__ epoch) {
+  wait_flags(flags, epoch, peers.n);
+  if ((n & 3) == 0) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      float4 part[CMAX_MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
+        if (r < peers.n) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.p[r]) + i);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
+        if (r < peers.n) {
+          v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
+        }
+      reinterpret_cast<float4*>(out)[i] = v;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      float v = 0.f;
+      for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + i);
+      out[i] = v;
+    }
   }
 }
 
@@ -1210,7 +1321,9 @@ int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motio
 }
 
 int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
-                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, cmax_stream_t stream) {
+                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, const uint32_t* d_flags,
+                              const uint32_t* d_epoch, cmax_stream_t stream) {
+  CMAX_REQUIRE((d_flags == nullptr) == (d_epoch == nullptr), "cmax_objective_reduce_iwe: d_flags and d_epoch go together");
   CMAX_REQUIRE(plan != nullptr && workspace != nullptr && h_peer_iwe != nullptr && d_cost != nullptr, "cmax_objective_reduce_iwe: NULL argument");
   CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_objective_reduce_iwe: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
   int rc = check_spec("cmax_objective_reduce_iwe", spec, plan->n_ref);
@@ -1230,9 +1343,10 @@ int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spe
   CombineDev cd;
   memset(&cd, 0, sizeof(cd));
   if (fuse) cd = combine_for(p, spec, d_orig_stat, d_cost, w);
-  dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), p->n_ref);
+  const int64_t work = (L.HW & 3) == 0 ? L.HW / 4 : L.HW;  // threads with work (16-byte loads when the image allows)
+  dim3 grid((unsigned)std::min<int64_t>((work + kStatBlock - 1) / kStatBlock, kNumSMs * 4), p->n_ref);
   peer_iwe_kernel<<<grid, kStatBlock, 0, s>>>(peers, w.iwe_full, p->Hp, p->Wp, fuse ? 1 : 0, fuse ? spec->omit_boundary : 0, w.sacc, w.stats,
-                                              fuse ? 1 : 0, cd, w.ctas_done);
+                                              fuse ? 1 : 0, cd, w.ctas_done, d_flags, d_epoch);
   CMAX_CUDA_CHECK(cudaGetLastError());
   if (combined) *combined = fuse ? 1 : 0;
   return CMAX_OK;
@@ -1247,7 +1361,33 @@ int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_sp
   return cost_stage(plan, spec, d_orig_stat, workspace, combined, combined, want_grad, d_cost, nullptr, 0, stream, true);
 }
 
-int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, cmax_stream_t stream) {
+int cmax_push(const float* src, int64_t n, float* const* h_peer_slots, uint32_t* const* h_peer_flags, int n_peers, uint32_t* d_epoch,
+              uint32_t* d_counter, cmax_stream_t stream) {
+  CMAX_REQUIRE(h_peer_slots != nullptr && h_peer_flags != nullptr && d_epoch != nullptr && d_counter != nullptr, "cmax_push: NULL argument");
+  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_push: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
+  CMAX_REQUIRE(n >= 0 && (n == 0 || src != nullptr), "cmax_push: bad source");
+  PushPtrs dst;
+  dst.n = n_peers;
+  for (int r = 0; r < CMAX_MAX_PEERS; ++r) {
+    dst.slot[r] = r < n_peers ? h_peer_slots[r] : nullptr;
+    dst.flag[r] = r < n_peers ? h_peer_flags[r] : nullptr;
+  }
+  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(dst.flag[r] != nullptr && (n == 0 || dst.slot[r] != nullptr), "cmax_push: peer %d pointer is NULL", r);
+  const int grid = n == 0 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(((n + 3) / 4 + 255) / 256, (int64_t)kNumSMs * 2));
+  push_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, n, dst, d_epoch, d_counter);
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  return CMAX_OK;
+}
+
+int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, const uint32_t* d_flags, const uint32_t* d_epoch,
+                      cmax_stream_t stream) {
+  CMAX_REQUIRE((d_flags == nullptr) == (d_epoch == nullptr), "cmax_reduce_peers: d_flags and d_epoch go together");
+  if (n == 0 && d_flags != nullptr) {  // nothing to sum: just consume the flags (closes a value-only evaluation)
+    CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_reduce_peers: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
+    wait_kernel<<<1, 32, 0, as_stream(stream)>>>(d_flags, d_epoch, n_peers);
+    CMAX_CUDA_CHECK(cudaGetLastError());
+    return CMAX_OK;
+  }
   CMAX_REQUIRE(h_peer_bufs != nullptr && out != nullptr, "cmax_reduce_peers: NULL argument");
   CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_reduce_peers: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
   CMAX_REQUIRE(n >= 0, "cmax_reduce_peers: n must be >= 0");
@@ -1256,7 +1396,7 @@ int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, f
   for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_bufs[r] : nullptr;
   for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_reduce_peers: peer %d pointer is NULL", r);
   if (n > 0) {
-    peer_sum_kernel<<<image_grid(n), 256, 0, as_stream(stream)>>>(peers, n, out);
+    peer_sum_kernel<<<image_grid((n & 3) == 0 ? n / 4 : n), 256, 0, as_stream(stream)>>>(peers, n, out, d_flags, d_epoch);
     CMAX_CUDA_CHECK(cudaGetLastError());
   }
   return CMAX_OK;

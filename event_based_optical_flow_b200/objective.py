@@ -177,8 +177,8 @@ class ContrastObjective:
         self.stat, self.form = stat, form
         self.ref_keys = tuple(k for k, _ in refs)
         self.group = process_group
-        if exchange not in ("nccl", "peer"):
-            raise ValueError(f"exchange must be 'nccl' or 'peer', got {exchange}")
+        if exchange not in ("nccl", "peer", "push"):
+            raise ValueError(f"exchange must be 'nccl', 'peer' or 'push', got {exchange}")
         self.exchange = exchange if process_group is not None else "nccl"
         if orig_events is None and isinstance(events, torch.Tensor):
             orig_events = events
@@ -206,7 +206,7 @@ class ContrastObjective:
         self._symm = None
         with torch.cuda.device(self.device):
             nbytes = self.lib.cmax_objective_workspace_bytes(self.plan.handle, C.byref(self.spec))
-            if self.exchange == "peer":
+            if self.exchange in ("peer", "push"):
                 self._setup_peer_exchange(nbytes)
             else:
                 self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
@@ -221,17 +221,35 @@ class ContrastObjective:
 
     # -- NVLink peer-memory exchange: the workspace and the partial-gradient buffer are symmetric allocations
     def _setup_peer_exchange(self, nbytes: int) -> None:
+        """One symmetric allocation per rank: [objective workspace][partial gradient][IWE mailbox: one slot per source rank]
+        [gradient mailbox][IWE flags][gradient flags].  "peer" reads the peers' partial buffers after an in-stream barrier;
+        "push" writes into the peers' mailboxes and raises flags (see cmax_push in include/cmax_b200.h)."""
         import torch.distributed._symmetric_memory as symm_mem
         world = torch.distributed.get_world_size(self.group)
+        rank = torch.distributed.get_rank(self.group)
         if world > _lib.MAX_PEERS:
-            raise ValueError(f"exchange='peer' supports up to {_lib.MAX_PEERS} ranks (one NVLink domain), got {world}")
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass  # newer torch enables it implicitly
+            raise ValueError(f"exchange={self.exchange!r} supports up to {_lib.MAX_PEERS} ranks (one NVLink domain), got {world}")
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                symm_mem.enable_symm_mem_for_group(self.group.group_name)
+            except Exception:
+                pass  # newer torch enables it implicitly
         n_motion = int(np.prod(self.motion_shape))
-        grad_off = (nbytes + 255) // 256 * 256
-        total = grad_off + 4 * n_motion + 256
+        Hp, Wp = self.padded_size
+        n_iwe = len(self.directions) * Hp * Wp
+        al = lambda v: (v + 255) // 256 * 256  # noqa: E731
+        grad_off = al(nbytes)
+        box_iwe = al(grad_off + 4 * n_motion)
+        iwe_slot = al(4 * n_iwe)
+        box_grad = box_iwe + world * iwe_slot
+        grad_slot = al(4 * n_motion)
+        flags_iwe = box_grad + world * grad_slot
+        flags_grad = flags_iwe + 256
+        total = flags_grad + 256
+        if self.exchange == "peer":
+            total = box_iwe  # no mailboxes
         self._ws = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         if self._ws.data_ptr() % 256 != 0:
             raise RuntimeError("symmetric allocation is not 256-byte aligned")
@@ -239,10 +257,26 @@ class ContrastObjective:
         self._symm = symm_mem.rendezvous(self._ws, self.group)
         bases = [int(p) for p in self._symm.buffer_ptrs]
         iwe_off = int(self.lib.cmax_objective_iwe_offset(self.plan.handle))
-        self._peer_iwe = (C.c_void_p * world)(*[b + iwe_off for b in bases])
-        self._peer_grad = (C.c_void_p * world)(*[b + grad_off for b in bases])
         self._n_peers = world
+        self._n_iwe, self._n_motion = n_iwe, n_motion
         self._grad_part = self._ws[grad_off:grad_off + 4 * n_motion].view(torch.float32).view(self.motion_shape)
+        arr = lambda vals: (C.c_void_p * world)(*vals)  # noqa: E731
+        if self.exchange == "peer":
+            self._peer_iwe = arr([b + iwe_off for b in bases])
+            self._peer_grad = arr([b + grad_off for b in bases])
+        else:
+            me = bases[rank]
+            self._iwe_local_ptr = me + iwe_off
+            # where THIS rank writes on every rank q, and what it reads locally
+            self._push_iwe_slots = arr([b + box_iwe + rank * iwe_slot for b in bases])
+            self._push_iwe_flags = arr([b + flags_iwe + 4 * rank for b in bases])
+            self._push_grad_slots = arr([b + box_grad + rank * grad_slot for b in bases])
+            self._push_grad_flags = arr([b + flags_grad + 4 * rank for b in bases])
+            self._peer_iwe = arr([me + box_iwe + r * iwe_slot for r in range(world)])
+            self._peer_grad = arr([me + box_grad + r * grad_slot for r in range(world)])
+            self._flags_iwe_ptr, self._flags_grad_ptr = me + flags_iwe, me + flags_grad
+            # local bookkeeping words: [epoch IWE, epoch gradient, CTA counter IWE, CTA counter gradient]
+            self._push_words = torch.zeros(64, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize(self.device)
         torch.distributed.barrier(group=self.group)
 
@@ -295,17 +329,37 @@ class ContrastObjective:
                       grad.data_ptr() if grad is not None else None, stream)
             return
         fused = self._vote(m, stream)
+        if self.exchange == "push":
+            w = self._push_words.data_ptr()
+            ep_iwe, ep_grad, cnt_iwe, cnt_grad = w, w + 4, w + 8, w + 12
+            _lib.call("cmax_push", self._iwe_local_ptr, self._n_iwe, self._push_iwe_slots, self._push_iwe_flags, self._n_peers, ep_iwe, cnt_iwe, stream)
+            combined = C.c_int32(0)
+            _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
+                      self._ws_ptr, cost.data_ptr(), C.byref(combined), self._flags_iwe_ptr, ep_iwe, stream)
+            _lib.call("cmax_objective_cost_after_reduce", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, combined.value,
+                      want, cost.data_ptr(), stream)
+            if grad is not None:
+                _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
+                _lib.call("cmax_push", self._grad_part.data_ptr(), self._n_motion, self._push_grad_slots, self._push_grad_flags, self._n_peers,
+                          ep_grad, cnt_grad, stream)
+                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), self._flags_grad_ptr, ep_grad, stream)
+            else:
+                # value only: the gradient phase still runs empty (flags only), so that no rank overwrites its IWE slots
+                # (next evaluation) while a slower peer is still reading them
+                _lib.call("cmax_push", None, 0, self._push_grad_slots, self._push_grad_flags, self._n_peers, ep_grad, cnt_grad, stream)
+                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, 0, None, self._flags_grad_ptr, ep_grad, stream)
+            return
         if self.exchange == "peer":
             self._symm.barrier(channel=0)  # every rank's partial IWE is complete and visible
             combined = C.c_int32(0)
             _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
-                      self._ws_ptr, cost.data_ptr(), C.byref(combined), stream)
+                      self._ws_ptr, cost.data_ptr(), C.byref(combined), None, None, stream)
             _lib.call("cmax_objective_cost_after_reduce", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, combined.value,
                       want, cost.data_ptr(), stream)
             if grad is not None:
                 _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
                 self._symm.barrier(channel=1)
-                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), stream)
+                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), None, None, stream)
             else:
                 # value only: still close the evaluation with a barrier, so that no rank overwrites its partial IWE (next
                 # evaluation's fold) while a slower peer is reading it
@@ -338,7 +392,7 @@ class ContrastObjective:
         with torch.cuda.device(self.device):
             self._vote(m, _stream_ptr())
             out = self._iwe_view.clone()
-            if self.group is not None and self.exchange == "peer":
+            if self.group is not None and self.exchange in ("peer", "push"):
                 torch.distributed.all_reduce(out, group=self.group)  # off the hot path: plain NCCL
         return out
 

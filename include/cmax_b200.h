@@ -254,11 +254,23 @@ int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motio
 size_t cmax_objective_iwe_offset(const cmax_plan_t* plan);
 size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan);
 int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
-                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, cmax_stream_t stream);
+                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, const uint32_t* d_flags,
+                              const uint32_t* d_epoch, cmax_stream_t stream);
 int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
                                      int combined, int want_grad, double* d_cost, cmax_stream_t stream);
 /* out[i] = sum_r h_peer_bufs[r][i], rank order (n floats). */
-int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, cmax_stream_t stream);
+int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, const uint32_t* d_flags, const uint32_t* d_epoch,
+                      cmax_stream_t stream);
+/* ---- push exchange (flags instead of barrier kernels).  Every rank owns a mailbox in symmetric memory: one slot and one
+ * 32-bit flag per source rank.  cmax_push copies n floats from `src` into this rank's slot of EVERY rank's mailbox
+ * (h_peer_slots[q] = address of that slot on rank q, own rank included; posted NVLink stores), fences, and its last CTA
+ * stores the new epoch (*d_epoch + 1, written back to d_epoch) into this rank's flag on every rank (h_peer_flags[q]).
+ * n == 0 sends the flag only.  d_counter: a zeroed uint32 the kernel uses and resets.  The consumers above take
+ * (d_flags = this rank's own flag array, d_epoch): every CTA first waits until all n_peers flags have reached *d_epoch,
+ * then reads LOCAL slots only (pass the local slot addresses as h_peer_iwe / h_peer_bufs).  cmax_reduce_peers with n == 0
+ * just waits.  Alternating two mailboxes (IWE, gradient) per evaluation makes slot reuse safe without any barrier. */
+int cmax_push(const float* src, int64_t n, float* const* h_peer_slots, uint32_t* const* h_peer_flags, int n_peers, uint32_t* d_epoch,
+              uint32_t* d_counter, cmax_stream_t stream);
 
 /* Scalar combination of per-image statistics (exposed for the modular cost plugins).
  * d_stats: n_ref x 4 doubles from cmax_image_stats; h_weights: n_ref multi-focal weights (NULL = 1).
