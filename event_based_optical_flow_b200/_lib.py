@@ -46,6 +46,8 @@ _SIGNATURES = {
     "cmax_warp_events_backward": (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "cmax_vote": (_i, [_p, _i64, _i, _p, _i, _i, _i, _i, _i, _p, _p]),
     "cmax_vote_backward": (_i, [_p, _i64, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "cmax_vote_backward2": (_i, [_p, _i64, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "cmax_warp_events_tangent": (_i, [_p, _i64, _i, _i, _i, _i, _p, _i, _p, _p, _p]),
     "cmax_blur3": (_i, [_p, _p, _i, _i, _i, _f, _i, _p]),
     "cmax_tile_flow_upsample": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "cmax_tile_flow_upsample_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

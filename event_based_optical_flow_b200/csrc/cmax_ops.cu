@@ -167,6 +167,69 @@ __global__ void __launch_bounds__(256) vote_backward_kernel(const float* __restr
   }
 }
 
+// Second order of the bilinear vote (Hessian-vector products).  vote_backward is
+//   grad_xy = wt * (dx, dy),  dx = (1-fy)(g10-g00) + fy(g11-g01),  dy = (1-fx)(g01-g00) + fx(g11-g10)
+// a function of (xy, G) that is bilinear in G and piecewise bilinear in xy.  For a cotangent u = (ux, uy) on grad_xy:
+//   d<grad_xy, u>/dG[c]  = wt * (ux dw_c/dx' + uy dw_c/dy')       -> scattered into out_gimage (a "tangent vote")
+//   d<grad_xy, u>/d(x',y') = wt * d_r * (uy, ux),  d_r = (g11-g01) - (g10-g00)   (d2w/dx'2 = d2w/dy'2 = 0 inside a cell)
+__global__ void __launch_bounds__(256) vote_backward2_kernel(const float* __restrict__ xy, int64_t n, int stride,
+                                                             const float* __restrict__ weight, int Hp, int Wp, int ph, int pw,
+                                                             const float* __restrict__ G, const float* __restrict__ u, int u_stride,
+                                                             float* __restrict__ out_gimage, float* __restrict__ out_gxy) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    const float xw = __ldg(xy + i * stride), yw = __ldg(xy + i * stride + 1);
+    const Vote v = vote_geometry(xw, yw, ph, pw);
+    const bool r0 = v.row >= 0 && v.row < Hp, r1 = v.row + 1 >= 0 && v.row + 1 < Hp;
+    const bool c0 = v.col >= 0 && v.col < Wp, c1 = v.col + 1 >= 0 && v.col + 1 < Wp;
+    const int64_t base = (int64_t)v.row * Wp + v.col;
+    const float s = weight ? __ldg(weight + i) : 1.0f;
+    const float ux = s * __ldg(u + i * u_stride), uy = s * __ldg(u + i * u_stride + 1);
+    if (out_gimage != nullptr) {
+      float* p = out_gimage + base;
+      if (r0 && c0) atomicAdd(p, -(1.0f - v.fy) * ux - (1.0f - v.fx) * uy);
+      if (r1 && c0) atomicAdd(p + Wp, (1.0f - v.fy) * ux - v.fx * uy);
+      if (r0 && c1) atomicAdd(p + 1, -v.fy * ux + (1.0f - v.fx) * uy);
+      if (r1 && c1) atomicAdd(p + Wp + 1, v.fy * ux + v.fx * uy);
+    }
+    if (out_gxy != nullptr) {
+      const float* p = G + base;
+      const float g00 = (r0 && c0) ? __ldg(p) : 0.f;
+      const float g10 = (r1 && c0) ? __ldg(p + Wp) : 0.f;
+      const float g01 = (r0 && c1) ? __ldg(p + 1) : 0.f;
+      const float g11 = (r1 && c1) ? __ldg(p + Wp + 1) : 0.f;
+      const float d_r = (g11 - g01) - (g10 - g00);
+      out_gxy[2 * i] = d_r * uy;
+      out_gxy[2 * i + 1] = d_r * ux;
+    }
+  }
+}
+
+// Tangent of the warp w.r.t. the motion (= the adjoint of warp_events_backward w.r.t. its incoming gradient):
+// out[e] = d(x', y')_e / d motion . tangent  =  -dt (T0[src], T1[src])   (2-dof: +dt (T[0], T[1]))
+__global__ void __launch_bounds__(256) warp_events_tangent_kernel(WarpArgs a, const float* __restrict__ tangent, float* __restrict__ out) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  const int HW = a.H * a.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += step) {
+    const float* e = a.ev + i * a.stride;
+    const float x = __ldg(e), y = __ldg(e + 1), t = __ldg(e + 2);
+    float dt;
+    int src, bin;
+    const bool ok = warp_site(x, y, t, a.H, a.W, a.model, a.tp, a.ref, &dt, &src, &bin);
+    float ox = 0.f, oy = 0.f;
+    if (a.model == CMAX_MOTION_2DOF) {
+      ox = dt * __ldg(tangent);
+      oy = dt * __ldg(tangent + 1);
+    } else if (ok && bin >= 0) {
+      const float* f = tangent + (int64_t)bin * 2 * HW;
+      ox = -(dt * __ldg(f + src));
+      oy = -(dt * __ldg(f + HW + src));
+    }
+    out[2 * i] = ox;
+    out[2 * i + 1] = oy;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ blur
 __device__ __forceinline__ int reflect(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
@@ -298,6 +361,39 @@ int cmax_vote_backward(const float* xy, int64_t n, int xy_stride, const float* w
   if (n > 0) {
     vote_backward_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(xy, n, xy_stride, weight, Hp, Wp, pad_h, pad_w,
                                                                               grad_image, grad_xy, grad_weight);
+    CMAX_CUDA_CHECK(cudaGetLastError());
+  }
+  return CMAX_OK;
+}
+
+int cmax_vote_backward2(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h, int pad_w,
+                        const float* grad_image, const float* u, int u_stride, float* out_grad_image, float* out_grad_xy,
+                        cmax_stream_t stream) {
+  CMAX_REQUIRE(n >= 0 && xy_stride >= 2 && u_stride >= 2, "cmax_vote_backward2: need n >= 0 and strides >= 2");
+  CMAX_REQUIRE(Hp > 0 && Wp > 0, "cmax_vote_backward2: bad image size %dx%d", Hp, Wp);
+  CMAX_REQUIRE(out_grad_xy == nullptr || grad_image != nullptr, "cmax_vote_backward2: out_grad_xy needs grad_image");
+  CMAX_REQUIRE(n == 0 || (xy != nullptr && u != nullptr), "cmax_vote_backward2: NULL pointer");
+  cudaStream_t s = as_stream(stream);
+  if (out_grad_image != nullptr) CMAX_CUDA_CHECK(cudaMemsetAsync(out_grad_image, 0, (size_t)Hp * Wp * sizeof(float), s));
+  if (n > 0) {
+    vote_backward2_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(xy, n, xy_stride, weight, Hp, Wp, pad_h, pad_w, grad_image, u, u_stride,
+                                                              out_grad_image, out_grad_xy);
+    CMAX_CUDA_CHECK(cudaGetLastError());
+  }
+  return CMAX_OK;
+}
+
+int cmax_warp_events_tangent(const float* events, int64_t n, int ev_stride, int H, int W, int motion_model, const cmax_time_params_t* d_params,
+                             int ref_index, const float* tangent_motion, float* out, cmax_stream_t stream) {
+  CMAX_REQUIRE(n >= 0 && ev_stride >= 3, "cmax_warp_events_tangent: need n >= 0 and ev_stride >= 3");
+  CMAX_REQUIRE(motion_model == CMAX_MOTION_DENSE || motion_model == CMAX_MOTION_VOXEL || motion_model == CMAX_MOTION_2DOF,
+               "cmax_warp_events_tangent: motion model %d not supported", motion_model);
+  CMAX_REQUIRE(d_params != nullptr && tangent_motion != nullptr && (n == 0 || (events != nullptr && out != nullptr)),
+               "cmax_warp_events_tangent: NULL pointer");
+  CMAX_REQUIRE(ref_index >= 0 && ref_index < CMAX_MAX_REFS, "cmax_warp_events_tangent: ref_index out of range");
+  if (n > 0) {
+    WarpArgs a{events, n, ev_stride, H, W, motion_model, ref_index, nullptr, d_params};
+    warp_events_tangent_kernel<<<grid_for(n, 256, 8), 256, 0, as_stream(stream)>>>(a, tangent_motion, out);
     CMAX_CUDA_CHECK(cudaGetLastError());
   }
   return CMAX_OK;

@@ -182,6 +182,9 @@ class ContrastObjective:
         self.exchange = exchange if process_group is not None else "nccl"
         if orig_events is None and isinstance(events, torch.Tensor):
             orig_events = events
+        # second order (Hessian-vector products) runs on the modular operators, which take the caller's event array
+        self._events_ref = events.detach() if isinstance(events, torch.Tensor) else None
+        self._modular_tp = None
         self.plan = events if isinstance(events, EventPlan) else EventPlan(events, image_size, outer_padding, order, t_range)
         self.device = self.plan.device
         self.image_size = self.plan.image_size
@@ -411,6 +414,58 @@ class ContrastObjective:
             return
         self._evaluate(motion_f32, cost_out, grad_out, stream)
 
+    # -- second order: the same cost composed from the modular operators (warp -> vote -> blur -> statistic, one C-ABI
+    #    call each, every backward differentiable once more), so that torch can differentiate the gradient itself
+    def modular_cost(self, motion: torch.Tensor) -> torch.Tensor:
+        """The cost as a twice-differentiable function of `motion` (same value as `value(motion)` up to fp32 summation
+        order).  Composition and sign conventions of src/solver/patch_contrast_base.py:289-352 and src/costs/*.py."""
+        from . import ops
+        if self.group is not None:
+            raise NotImplementedError("Hessian-vector products are not implemented for sharded objectives")
+        if self._events_ref is None:
+            raise NotImplementedError("Hessian-vector products need the objective to be built from the event tensor (not from an EventPlan)")
+        ev = self._events_ref
+        if ev.shape[1] == 3:
+            ev = torch.cat([ev, ev.new_zeros(len(ev), 1)], dim=1)
+        ev = ev[:, :4].to(torch.float32)
+        if self._modular_tp is None:
+            self._modular_tp = ops.time_params(ev, self.directions, self.n_bins)
+        stats = []
+        for r in range(len(self.directions)):
+            warped = ops.WarpFunction.apply(ev, motion, self.motion_model, self.image_size, self._modular_tp, r)
+            iwe = ops.VoteFunction.apply(warped, None, self.padded_size, self.plan.pad, "bilinear_vote")
+            if self.sigma > 0:
+                iwe = ops.BlurFunction.apply(iwe, self.sigma)
+            stats.append(ops.ImageStatFunction.apply(iwe, self.stat, self.omit_boundary).double())
+        sign = int(self.spec.direction_sign)
+        if self.form == "plain":
+            total = -sign * stats[0]
+        else:
+            orig = self._orig_stat[0]
+            weights = [float(self.spec.weights[r]) if self.form == "multifocal" else 1.0 for r in range(len(stats))]
+            if sign > 0:
+                total = sum(w * orig / c for w, c in zip(weights, stats))
+            elif self.form == "normalized":
+                total = stats[0] / orig
+            else:
+                total = -sum(w * c / orig for w, c in zip(weights, stats))
+        return self._post_sign * total
+
+    def differentiable_grad(self, motion: torch.Tensor) -> torch.Tensor:
+        """d cost / d motion as a differentiable function of `motion` (for double backward)."""
+        with torch.enable_grad():
+            cost = self.modular_cost(motion)
+            (grad,) = torch.autograd.grad(cost, motion, create_graph=True)
+        return grad.to(motion.dtype)
+
+    def hvp(self, motion: torch.Tensor, vector: torch.Tensor) -> torch.Tensor:
+        """Hessian-vector product d/d eps grad cost(motion + eps * vector) at eps = 0 (what scipy's Newton-CG asks for)."""
+        _require_cuda(motion, "motion")
+        m = motion.detach().clone().requires_grad_(True)
+        grad = self.differentiable_grad(m)
+        (hv,) = torch.autograd.grad(grad, m, vector.to(grad.dtype))
+        return hv
+
     def __call__(self, motion: torch.Tensor) -> torch.Tensor:
         """Autograd-aware scalar in motion's dtype: drop-in for the reference's `calculate_cost` result."""
         return _ObjectiveFunction.apply(motion, self)
@@ -504,18 +559,29 @@ class TimeAwareObjective:
 
 
 class _ObjectiveFunction(torch.autograd.Function):
+    """cost(motion) on the fused kernels.  First order (every scipy / torch optimiser except the Newton family): the
+    backward hands out the analytic gradient the forward already computed.  Second order: when the backward itself is
+    being recorded (`create_graph=True`, which is how `torch.autograd.functional.vhp` obtains the Hessian-vector product
+    for Newton-CG / trust-*, scipy_autograd/torch_wrapper.py:51-73), the gradient is rebuilt as a differentiable function of
+    `motion` from the modular CUDA operators, every one of which has a second-order kernel (ops.py)."""
+
     @staticmethod
     def forward(ctx, motion: torch.Tensor, obj: ContrastObjective):
         need = ctx.needs_input_grad[0]
         cost, grad = obj.value_and_grad(motion, want_grad=need)
         ctx.grad = grad
+        ctx.obj = obj
         ctx.dtype = motion.dtype
+        ctx.save_for_backward(motion)
         return cost.to(motion.dtype if motion.dtype.is_floating_point else torch.float32)
 
     @staticmethod
     def backward(ctx, g):
         if ctx.grad is None:
             return None, None
+        if torch.is_grad_enabled():
+            (motion,) = ctx.saved_tensors
+            return ctx.obj.differentiable_grad(motion) * g, None
         return (ctx.grad.to(ctx.dtype) * g.to(ctx.dtype)), None
 
 

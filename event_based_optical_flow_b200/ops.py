@@ -79,12 +79,45 @@ class WarpFunction(torch.autograd.Function):
         return out.to(events.dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, grad_out):
         (events,) = ctx.saved_tensors
+        gm = _WarpBackward.apply(grad_out, events, ctx.meta)
+        return None, gm, None, None, None, None
+
+
+def warp_events_tangent(events: torch.Tensor, motion_model: str, image_size, tp: torch.Tensor, ref_index: int,
+                        tangent_motion: torch.Tensor) -> torch.Tensor:
+    """[n,2] = d(x', y') / d motion . tangent_motion (the warp is linear in the motion)."""
+    ev, tm = _f32c(events), _f32c(tangent_motion)
+    H, W = image_size
+    out = torch.empty(ev.shape[0], 2, dtype=torch.float32, device=ev.device)
+    with torch.cuda.device(ev.device):
+        _lib.call("cmax_warp_events_tangent", ev.data_ptr(), ev.shape[0], ev.shape[1], H, W, _lib.MOTION[motion_model], tp.data_ptr(), ref_index,
+                  tm.data_ptr(), out.data_ptr(), _stream())
+    return out
+
+
+class _WarpBackward(torch.autograd.Function):
+    """grad_out [n,C] -> grad_motion, as a differentiable (linear) function of grad_out: what a Hessian-vector product
+    differentiates (scipy_autograd/torch_wrapper.py:51-73)."""
+
+    @staticmethod
+    def forward(ctx, grad_out, events, meta):
+        motion_model, mshape, image_size, tp, ref_index, mdtype = meta
+        ctx.save_for_backward(events)
+        ctx.meta = meta
+        ctx.gshape, ctx.gdtype = grad_out.shape, grad_out.dtype
+        return warp_events_backward(events, motion_model, mshape, image_size, tp, ref_index, grad_out).to(mdtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        (events,) = ctx.saved_tensors
         motion_model, mshape, image_size, tp, ref_index, mdtype = ctx.meta
-        gm = warp_events_backward(events, motion_model, mshape, image_size, tp, ref_index, grad_out)
-        return None, gm.to(mdtype), None, None, None, None
+        t = warp_events_tangent(events, motion_model, image_size, tp, ref_index, u)
+        full = torch.zeros(ctx.gshape, dtype=ctx.gdtype, device=t.device)
+        full[:, :2] = t.to(ctx.gdtype)
+        return full, None, None
 
 
 # ------------------------------------------------------------------------------------------------ vote
@@ -120,21 +153,60 @@ class VoteFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xy, weight, padded_size, pad, method):
         img = vote(xy, padded_size, pad, weight, method)
-        ctx.save_for_backward(xy.detach(), weight.detach() if weight is not None else None)
+        ctx.save_for_backward(xy, weight.detach() if weight is not None else None)  # xy stays attached: the second order differentiates through it
         ctx.meta = (tuple(padded_size), tuple(pad), method, xy.dtype, xy.shape, weight is not None and ctx.needs_input_grad[1])
         return img.to(xy.dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, grad_image):
         xy, weight = ctx.saved_tensors
         padded_size, pad, method, dtype, shape, want_w = ctx.meta
         if method != "bilinear_vote":  # the count image is piecewise constant in the coordinates
             return torch.zeros(shape, dtype=dtype, device=xy.device), None, None, None, None
-        gxy, gw = vote_backward(xy, padded_size, pad, weight, grad_image, want_w)
+        if want_w:  # weights with a gradient: first order only
+            gxy, gw = vote_backward(xy, padded_size, pad, weight, grad_image, True)
+            full = torch.zeros(shape, dtype=dtype, device=xy.device)
+            full[:, :2] = gxy.to(dtype)
+            return full, gw.to(weight.dtype), None, None, None
+        return _VoteBackward.apply(xy, grad_image, weight, (padded_size, pad, dtype, shape)), None, None, None, None
+
+
+def vote_backward2(xy, padded_size, pad, weight, grad_image, u):
+    """Adjoint of `vote_backward` w.r.t. (grad_image, xy) for the cotangent u [n,>=2] of grad_xy."""
+    x, g, uu = _f32c(xy), _f32c(grad_image), _f32c(u)
+    Hp, Wp = padded_size
+    g_img = torch.empty(Hp, Wp, dtype=torch.float32, device=x.device)
+    g_xy = torch.empty(x.shape[0], 2, dtype=torch.float32, device=x.device)
+    w = _f32c(weight) if weight is not None else None
+    with torch.cuda.device(x.device):
+        _lib.call("cmax_vote_backward2", x.data_ptr(), x.shape[0], x.shape[1], w.data_ptr() if w is not None else None, Hp, Wp, pad[0], pad[1],
+                  g.data_ptr(), uu.data_ptr(), uu.shape[1], g_img.data_ptr(), g_xy.data_ptr(), _stream())
+    return g_img, g_xy
+
+
+class _VoteBackward(torch.autograd.Function):
+    """(xy, grad_image) -> grad_xy, differentiable once more (bilinear in grad_image, piecewise bilinear in xy)."""
+
+    @staticmethod
+    def forward(ctx, xy, grad_image, weight, meta):
+        padded_size, pad, dtype, shape = meta
+        ctx.save_for_backward(xy, grad_image, weight)
+        ctx.meta = meta
+        ctx.gi_dtype = grad_image.dtype
+        gxy, _ = vote_backward(xy, padded_size, pad, weight, grad_image, False)
         full = torch.zeros(shape, dtype=dtype, device=xy.device)
         full[:, :2] = gxy.to(dtype)
-        return full, (gw.to(weight.dtype) if gw is not None else None), None, None, None
+        return full
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        xy, grad_image, weight = ctx.saved_tensors
+        padded_size, pad, dtype, shape = ctx.meta
+        g_img, g_xy = vote_backward2(xy, padded_size, pad, weight, grad_image, u)
+        full = torch.zeros(shape, dtype=dtype, device=xy.device)
+        full[:, :2] = g_xy.to(dtype)
+        return full, g_img.to(ctx.gi_dtype), None, None
 
 
 # ------------------------------------------------------------------------------------------------ blur
@@ -150,16 +222,17 @@ def blur3(images: torch.Tensor, sigma: float, transpose: bool = False) -> torch.
 
 
 class BlurFunction(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, image, sigma):
-        ctx.sigma = sigma
-        ctx.dtype = image.dtype
-        return blur3(image[None], sigma)[0].to(image.dtype)
+    """Linear, so its backward is the same Function with the transpose flag flipped (differentiable to any order)."""
 
     @staticmethod
-    @once_differentiable
+    def forward(ctx, image, sigma, transpose=False):
+        ctx.sigma, ctx.transpose = sigma, transpose
+        ctx.dtype = image.dtype
+        return blur3(image[None], sigma, transpose=transpose)[0].to(image.dtype)
+
+    @staticmethod
     def backward(ctx, g):
-        return blur3(g[None], ctx.sigma, transpose=True)[0].to(ctx.dtype), None
+        return BlurFunction.apply(g, ctx.sigma, not ctx.transpose).to(ctx.dtype), None, None
 
 
 # ------------------------------------------------------------------------------------------------ statistics
@@ -185,18 +258,29 @@ class ImageStatFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, image, stat, omit_boundary):
-        stats, grad = image_stats(image[None], stat, omit_boundary, want_grad=ctx.needs_input_grad[0])
-        ctx.save_for_backward(grad)
-        ctx.dtype = image.dtype
+        stats, _ = image_stats(image[None], stat, omit_boundary, want_grad=False)
+        ctx.save_for_backward(image)
+        ctx.meta = (stat, omit_boundary)
         return stats[0, 0].to(image.dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        if grad is None:
-            return None, None, None
-        return (grad[0] * g.to(torch.float32)).to(ctx.dtype), None, None
+        (image,) = ctx.saved_tensors
+        return g * _StatGrad.apply(image, *ctx.meta), None, None
+
+
+class _StatGrad(torch.autograd.Function):
+    """image -> d stat / d image.  Both statistics are quadratic forms in the image (unbiased variance, mean squared Sobel
+    magnitude), so this map is LINEAR and symmetric: its adjoint is itself."""
+
+    @staticmethod
+    def forward(ctx, image, stat, omit_boundary):
+        ctx.meta = (stat, omit_boundary)
+        return image_stats(image[None], stat, omit_boundary, want_grad=True)[1][0].to(image.dtype)
+
+    @staticmethod
+    def backward(ctx, u):
+        return _StatGrad.apply(u, *ctx.meta), None, None
 
 
 # ------------------------------------------------------------------------------------------------ tile flow
@@ -238,10 +322,24 @@ class TileFlowFunction(torch.autograd.Function):
         return tile_flow_upsample(motion, image_shape, pad, window).to(motion.dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g):
+        return _TileFlowBackward.apply(g, ctx.meta, tuple(g.shape[-2:])), None, None, None
+
+
+class _TileFlowBackward(torch.autograd.Function):
+    """The (linear) adjoint of the upsample; its own adjoint is the upsample."""
+
+    @staticmethod
+    def forward(ctx, g, meta, image_shape):
+        grid, pad, window, dtype = meta
+        ctx.meta, ctx.image_shape, ctx.gdtype = meta, image_shape, g.dtype
+        return tile_flow_upsample_backward(g, grid, pad, window).to(dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
         grid, pad, window, dtype = ctx.meta
-        return tile_flow_upsample_backward(g, grid, pad, window).to(dtype), None, None, None
+        return tile_flow_upsample(u, ctx.image_shape, pad, window).to(ctx.gdtype), None, None
 
 
 # ------------------------------------------------------------------------------------------------ time-aware flow voxel

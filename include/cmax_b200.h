@@ -121,6 +121,19 @@ int cmax_vote(const float* xy, int64_t n, int xy_stride, const float* weight, in
 /* Adjoint of the bilinear vote: grad_image [Hp,Wp] -> grad_xy [n,2] (and grad_weight [n] if non-NULL). */
 int cmax_vote_backward(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h,
                        int pad_w, const float* grad_image, float* grad_xy, float* grad_weight, cmax_stream_t stream);
+/* ---- second order (Hessian-vector products for Newton-CG / trust-*: scipy_autograd/torch_wrapper.py:51-73 runs
+ * torch.autograd.functional.vhp through warp -> vote -> cost).
+ * cmax_vote_backward2: the adjoint of cmax_vote_backward as a function of (xy, grad_image).  u [n,u_stride] (columns 0,1)
+ * is the cotangent of grad_xy.  out_grad_image [Hp,Wp] (ZEROED BY THE CALLEE; may be NULL) = d<grad_xy,u>/d grad_image, a
+ * vote with the weight derivatives; out_grad_xy [n,2] (may be NULL) = d<grad_xy,u>/d xy = weight * d_r * (u_y, u_x), the
+ * only non-zero second derivative of a bilinear weight being the mixed one. */
+int cmax_vote_backward2(const float* xy, int64_t n, int xy_stride, const float* weight, int Hp, int Wp, int pad_h, int pad_w,
+                        const float* grad_image, const float* u, int u_stride, float* out_grad_image, float* out_grad_xy,
+                        cmax_stream_t stream);
+/* Tangent of cmax_warp_events w.r.t. the motion = the adjoint of cmax_warp_events_backward w.r.t. grad_out:
+ * out [n,2] = d(x',y')/d motion . tangent_motion (same shape as the motion). */
+int cmax_warp_events_tangent(const float* events, int64_t n, int ev_stride, int H, int W, int motion_model, const cmax_time_params_t* d_params,
+                             int ref_index, const float* tangent_motion, float* out, cmax_stream_t stream);
 /* 3x3 Gaussian, reflect padding (torchvision gaussian_blur(kernel_size=3) at src/event_image_converter.py:153-158)
  * and its transpose.  n_img images of [Hp,Wp]; in != out. */
 int cmax_blur3(const float* in, float* out, int n_img, int Hp, int Wp, float sigma, int transpose, cmax_stream_t stream);
