@@ -70,12 +70,16 @@ __device__ __forceinline__ LeanGeom lean_geometry(f32x2 w, int off_r, int off_c)
   g.ci = __float_as_int(ty) + off_c;
   return g;
 }
-// accumulator cell of the vote, or `outside` when the event touches no pixel / is strip padding
-__device__ __forceinline__ int lean_cell(const LeanGeom& g, bool real, int Hp, int Wp, int outside) {
-  const bool inside = ((unsigned)g.ri <= (unsigned)Hp) & ((unsigned)g.ci <= (unsigned)Wp) & real;
-  return inside ? g.ri * (Wp + 1) + g.ci : outside;
+// accumulator cell of the vote, or `outside` when the event touches no pixel / is strip padding (k >= count).
+// Three chained predicate compares and ONE select (ptxas turns the C expression into three selects).
+__device__ __forceinline__ int lean_cell(const LeanGeom& g, int k, int count, int Hp, int Wp, int outside) {
+  int c;
+  const int idx = g.ri * (Wp + 1) + g.ci;
+  asm("{\n .reg .pred p;\n setp.le.u32 p, %1, %2;\n setp.le.and.u32 p, %3, %4, p;\n setp.lt.and.s32 p, %5, %6, p;\n selp.s32 %0, %7, %8, p;\n}"
+      : "=r"(c)
+      : "r"(g.ri), "r"(Hp), "r"(g.ci), "r"(Wp), "r"(k), "r"(count), "r"(idx), "r"(outside));
+  return c;
 }
-
 // warped coordinate pair of one event for reference time r
 template <int MODEL, int NREF, bool PRE_DT>
 __device__ __forceinline__ f32x2 lean_warp(f32x2 xy, float tz, f32x2 f, int src, int HW, const float* __restrict__ motion,
@@ -98,7 +102,7 @@ struct StripVote {
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void strip_vote_step(float tz, bool real, const StripHead& h, f32x2 f, StripVote<NREF>& st, const FusedArgs& a,
+__device__ __forceinline__ void strip_vote_step(float tz, int k, const StripHead& h, f32x2 f, StripVote<NREF>& st, const FusedArgs& a,
                                                 int HW, int off_r, int off_c, const RefRegs<NREF>& rr, const TimeSmem& s,
                                                 float4* __restrict__ acc) {
 #pragma unroll
@@ -107,16 +111,16 @@ __device__ __forceinline__ void strip_vote_step(float tz, bool real, const Strip
     int bin;
     const f32x2 w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, h.src, HW, a.motion, rr, s, r, dt, bin);
     const LeanGeom g = lean_geometry(w, off_r, off_c);
-    const int c = lean_cell(g, real, a.Hp, a.Wp, -1);
-    {  // a new accumulator cell: flush the old one (predicated), restart the sums
-      const bool change = c != st.cell[r];
+    const int c = lean_cell(g, k, h.count, a.Hp, a.Wp, -1);
+    const bool change = c != st.cell[r];
+    {  // a new accumulator cell: flush the old one (predicated)
       float w0, w1, w2, w3;
       upk2(st.w01[r], w0, w1);
       upk2(st.w23[r], w2, w3);
       red_add_v4_if(change && st.cell[r] >= 0, acc + r * a.cells + st.cell[r], w0, w1, w2, w3);
       st.cell[r] = c;
-      clear_if(change, st.w01[r]);
-      clear_if(change, st.w23[r]);
+      clear_if(change, st.w01[r]);  // (ptxas has no predicated packed arithmetic: a predicated FMUL2 / FFMA2 pair becomes
+      clear_if(change, st.w23[r]);  //  both operations plus four selects, measured in SASS -- clearing is cheaper)
     }
     // (w00, w10) += (1-fx, fx) * (1-fy);  (w01, w11) += (1-fx, fx) * fy        event_image_converter.py:365-369
     // (what an out-of-image event adds here is dropped by the next cell change: a cell of -1 is never flushed)
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, f
       st.w01[r] = st.w23[r] = 0ull;
     }
 #pragma unroll
-    for (int k = 0; k < kRunE; ++k) strip_vote_step<MODEL, NREF, PRE_DT>(tz[k], k < h.count, h, f, st, a, HW, off_r, off_c, rr, s, acc);
+    for (int k = 0; k < kRunE; ++k) strip_vote_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, st, a, HW, off_r, off_c, rr, s, acc);
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
       float w0, w1, w2, w3;
@@ -187,7 +191,7 @@ struct StripGrad {
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void strip_grad_step(float tz, bool real, const StripHead& h, f32x2 f, StripGrad<MODEL, NREF>& st,
+__device__ __forceinline__ void strip_grad_step(float tz, int k, const StripHead& h, f32x2 f, StripGrad<MODEL, NREF>& st,
                                                 const FusedArgs& a, int HW, int off_r, int off_c, int outside, const RefRegs<NREF>& rr,
                                                 const TimeSmem& s, const float4* __restrict__ gq, float* __restrict__ gmotion) {
 #pragma unroll
@@ -196,7 +200,7 @@ __device__ __forceinline__ void strip_grad_step(float tz, bool real, const Strip
     int bin;
     const f32x2 w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, h.src, HW, a.motion, rr, s, r, dt, bin);
     const LeanGeom g = lean_geometry(w, off_r, off_c);
-    const int c = lean_cell(g, real, a.Hp, a.Wp, outside);  // `outside` = the extra all-zero cell
+    const int c = lean_cell(g, k, h.count, a.Hp, a.Wp, outside);  // `outside` = the extra all-zero cell
     if (c != st.cell[r]) {
       st.cell[r] = c;
       const float4 q = __ldg(gq + r * a.cells + c);
@@ -210,7 +214,7 @@ __device__ __forceinline__ void strip_grad_step(float tz, bool real, const Strip
     const f32x2 d = pk2(fmaf(fy, st.d_r[r], st.d_x0[r]), fmaf(fx, st.d_r[r], st.d_c0[r]));
     const float ndt = -dt;
     if (MODEL == CMAX_MOTION_VOXEL) {
-      const int slot = (bin >= 0 && real) ? bin * 2 * HW + h.src : -1;
+      const int slot = (bin >= 0 && k < h.count) ? bin * 2 * HW + h.src : -1;
       if (slot != st.slot[r]) {
         if (st.slot[r] >= 0) {
           float g0, g1;
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     }
 #pragma unroll
     for (int k = 0; k < kRunE; ++k)
-      strip_grad_step<MODEL, NREF, PRE_DT>(tz[k], k < h.count, h, f, st, a, HW, off_r, off_c, outside, rr, s, gq, gmotion);
+      strip_grad_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, st, a, HW, off_r, off_c, outside, rr, s, gq, gmotion);
     if (MODEL == CMAX_MOTION_DENSE) {  // one flush per strip: the strip IS one source pixel
       float g0, g1;
       upk2(st.g[0], g0, g1);
