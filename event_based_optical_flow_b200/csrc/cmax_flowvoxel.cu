@@ -135,6 +135,10 @@ __device__ __forceinline__ void fv_adj(const float* __restrict__ U, const float*
   gv = wv - dt * tv;
 }
 
+// c / w for 0 <= c < 2^16 and 1 <= w < 2^8 without the ~20-instruction integer division: the exact quotient's distance to
+// the next integer is >= 0.5 / w, far above the fp32 rounding error of the product
+__device__ __forceinline__ int fast_div(int c, float inv_w) { return (int)(((float)c + 0.5f) * inv_w); }
+
 // region geometry shared by both kernels: the CTA's tile with a halo of k pixels
 struct FvRegion {
   int gi0, gj0, rh, rw;
@@ -156,8 +160,9 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_kernel(FvFwdArgs a) {
   const int64_t HW = (int64_t)H * W;
   const FvRegion R = fv_region(k);
   const int n_cells = R.rh * R.rw;
+  const float inv_rw = 1.0f / (float)R.rw;
   for (int c = threadIdx.x; c < n_cells; c += kFvThreads) {
-    const int li = c / R.rw, lj = c % R.rw, gi = R.gi0 + li, gj = R.gj0 + lj;
+    const int li = fast_div(c, inv_rw), lj = c - li * R.rw, gi = R.gi0 + li, gj = R.gj0 + lj;
     float u = 0.f, v = 0.f;
     if (gi >= 0 && gi < H && gj >= 0 && gj < W) {
       const int64_t p = (int64_t)gi * W + gj;
@@ -181,8 +186,10 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_kernel(FvFwdArgs a) {
     float* NV = lev[s & 1][1];
     float* out = job.out[s - 1];
     const int ih = R.rh - 2 * s, iw = R.rw - 2 * s;  // cells still valid at this level
+    const float inv_iw = 1.0f / (float)iw;
     for (int q = threadIdx.x; q < ih * iw; q += kFvThreads) {
-      const int li = s + q / iw, lj = s + q % iw, gi = R.gi0 + li, gj = R.gj0 + lj;
+      const int qi = fast_div(q, inv_iw);
+      const int li = s + qi, lj = s + (q - qi * iw), gi = R.gi0 + li, gj = R.gj0 + lj;
       if (gi < 0 || gi >= H || gj < 0 || gj >= W) continue;
       const int c = li * R.rw + lj;
       float nu, nv;
@@ -207,8 +214,10 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArg
   const int64_t HW = (int64_t)H * W;
   const FvRegion R = fv_region(k);
   const int n_cells = R.rh * R.rw;
+  const float inv_rw = 1.0f / (float)R.rw;
   for (int c = threadIdx.x; c < n_cells; c += kFvThreads) {
-    const int gi = R.gi0 + c / R.rw, gj = R.gj0 + c % R.rw;
+    const int ci = fast_div(c, inv_rw);
+    const int gi = R.gi0 + ci, gj = R.gj0 + (c - ci * R.rw);
     float u = 0.f, v = 0.f;
     if (gi >= 0 && gi < H && gj >= 0 && gj < W) {
       const int64_t p = (int64_t)gi * W + gj;
@@ -222,7 +231,8 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArg
     __syncthreads();  // the previous level is complete, and fbuf is free again
     const float* F = job.f[s - 1];
     for (int c = threadIdx.x; c < n_cells; c += kFvThreads) {
-      const int gi = R.gi0 + c / R.rw, gj = R.gj0 + c % R.rw;
+      const int ci = fast_div(c, inv_rw);
+      const int gi = R.gi0 + ci, gj = R.gj0 + (c - ci * R.rw);
       float u = 0.f, v = 0.f;
       if (gi >= 0 && gi < H && gj >= 0 && gj < W) {
         const int64_t p = (int64_t)gi * W + gj;
@@ -239,8 +249,10 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArg
     float* NV = wbuf[s & 1][1];
     const float* GV = job.gv[s - 1];
     const int ih = R.rh - 2 * s, iw = R.rw - 2 * s;
+    const float inv_iw = 1.0f / (float)iw;
     for (int q = threadIdx.x; q < ih * iw; q += kFvThreads) {
-      const int li = s + q / iw, lj = s + q % iw, gi = R.gi0 + li, gj = R.gj0 + lj;
+      const int qi = fast_div(q, inv_iw);
+      const int li = s + qi, lj = s + (q - qi * iw), gi = R.gi0 + li, gj = R.gj0 + lj;
       if (gi < 0 || gi >= H || gj < 0 || gj >= W) continue;
       const int c = li * R.rw + lj;
       float gu, gv;

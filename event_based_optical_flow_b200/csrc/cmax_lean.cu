@@ -80,18 +80,39 @@ __device__ __forceinline__ int lean_cell(const LeanGeom& g, int k, int count, in
       : "r"(g.ri), "r"(Hp), "r"(g.ci), "r"(Wp), "r"(k), "r"(count), "r"(idx), "r"(outside));
   return c;
 }
-// warped coordinate pair of one event for reference time r
+// warped coordinate pair of one event for reference time r (dense / 2-dof: the flow vector f is a per-strip constant)
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ f32x2 lean_warp(f32x2 xy, float tz, f32x2 f, int src, int HW, const float* __restrict__ motion,
-                                           const RefRegs<NREF>& rr, const TimeSmem& s, int r, float& dt, int& bin) {
+__device__ __forceinline__ f32x2 lean_warp(f32x2 xy, float tz, f32x2 f, const RefRegs<NREF>& rr, int r, float& dt) {
   dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
-  bin = 0;
-  if (MODEL == CMAX_MOTION_2DOF) return add2(xy, mul2_rounded(f, dt));   // src/warp.py:507-514
-  if (MODEL == CMAX_MOTION_DENSE) return sub2(xy, mul2_rounded(f, dt));  // src/warp.py:306-307
-  bin = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);  // src/warp.py:346-357
-  if (bin < 0) return xy;
-  const float* fb = motion + (int64_t)bin * 2 * HW;
-  return sub2(xy, mul2_rounded(pk2(__ldg(fb + src), __ldg(fb + HW + src)), dt));
+  if (MODEL == CMAX_MOTION_2DOF) return add2(xy, mul2_rounded(f, dt));  // src/warp.py:507-514
+  return sub2(xy, mul2_rounded(f, dt));                                   // src/warp.py:306-307
+}
+
+// Time-aware (voxel) model: the flow vector depends on the event's time bin.  The events of a strip are in time order, so
+// the bin never decreases along the strip: the first event does the full search (time_bin), every later one only checks
+// whether it crossed the next edge, and the flow vector is re-fetched only when the bin moved (src/warp.py:346-357).
+struct VoxelWalk {
+  int bin;    // -1 = none yet / in no bin
+  f32x2 f;
+};
+template <int NREF, bool PRE_DT>
+__device__ __forceinline__ f32x2 voxel_warp(f32x2 xy, float tz, int k, bool real, int src, int HW, const float* __restrict__ motion,
+                                            const RefRegs<NREF>& rr, const TimeSmem& s, int r, VoxelWalk& vw, float& dt) {
+  dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
+  int b = vw.bin;
+  if (k == 0 || b < 0) {
+    b = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
+  } else if (real) {  // (strip padding carries dt = 0 and is masked by the caller: leave the walk alone)
+    while (b < s.n_bins - 1 && dt >= s.edges[r][b + 1]) ++b;
+  }
+  if (b != vw.bin) {
+    vw.bin = b;
+    if (b >= 0) {
+      const float* fb = motion + (int64_t)b * 2 * HW;
+      vw.f = pk2(__ldg(fb + src), __ldg(fb + HW + src));
+    }
+  }
+  return b >= 0 ? sub2(xy, mul2_rounded(vw.f, dt)) : xy;
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -99,6 +120,7 @@ template <int NREF>
 struct StripVote {
   int cell[NREF];
   f32x2 w01[NREF], w23[NREF];  // (w00, w10), (w01, w11) of the current accumulator cell
+  VoxelWalk vw[NREF];          // voxel model only
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
@@ -108,8 +130,9 @@ __device__ __forceinline__ void strip_vote_step(float tz, int k, const StripHead
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float dt;
-    int bin;
-    const f32x2 w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, h.src, HW, a.motion, rr, s, r, dt, bin);
+    f32x2 w;
+    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, h.src, HW, a.motion, rr, s, r, st.vw[r], dt);
+    else w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, rr, r, dt);
     const LeanGeom g = lean_geometry(w, off_r, off_c);
     const int c = lean_cell(g, k, h.count, a.Hp, a.Wp, -1);
     const bool change = c != st.cell[r];
@@ -167,6 +190,8 @@ __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, f
     for (int r = 0; r < NREF; ++r) {
       st.cell[r] = -1;
       st.w01[r] = st.w23[r] = 0ull;
+      st.vw[r].bin = -1;
+      st.vw[r].f = 0ull;
     }
 #pragma unroll
     for (int k = 0; k < kRunE; ++k) strip_vote_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, st, a, HW, off_r, off_c, rr, s, acc);
@@ -188,6 +213,7 @@ struct StripGrad {
   float d_x0[NREF], d_c0[NREF], d_r[NREF];  // corner differences of the current cell's gradient quad
   int slot[NACC];                           // voxel model: flat index of the (bin, pixel) slot being accumulated, -1 = none
   f32x2 g[NACC];                            // sum of -dt * (dL/dx', dL/dy')
+  VoxelWalk vw[NREF];                       // voxel model only
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
@@ -197,8 +223,10 @@ __device__ __forceinline__ void strip_grad_step(float tz, int k, const StripHead
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float dt;
-    int bin;
-    const f32x2 w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, h.src, HW, a.motion, rr, s, r, dt, bin);
+    f32x2 w;
+    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, h.src, HW, a.motion, rr, s, r, st.vw[r], dt);
+    else w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, rr, r, dt);
+    const int bin = (MODEL == CMAX_MOTION_VOXEL) ? st.vw[r].bin : 0;
     const LeanGeom g = lean_geometry(w, off_r, off_c);
     const int c = lean_cell(g, k, h.count, a.Hp, a.Wp, outside);  // `outside` = the extra all-zero cell
     if (c != st.cell[r]) {
@@ -268,6 +296,8 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     for (int r = 0; r < NREF; ++r) {
       st.cell[r] = -2;
       st.d_x0[r] = st.d_c0[r] = st.d_r[r] = 0.f;
+      st.vw[r].bin = -1;
+      st.vw[r].f = 0ull;
     }
 #pragma unroll
     for (int q = 0; q < StripGrad<MODEL, NREF>::NACC; ++q) {

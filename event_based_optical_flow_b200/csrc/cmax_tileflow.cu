@@ -52,43 +52,56 @@ __global__ void __launch_bounds__(256) tile_flow_upsample_kernel(const float* __
   }
 }
 
-// Adjoint: one CTA per (channel, grid row a).  Phase 1: T[j] = sum_i Wr[i,a] G[c,i,j] over the image rows in the support
-// of node row a (threads over j, coalesced reads of G).  Phase 2: gm[c,a,b] = - sum_j Wc[j,b] T[j] (one warp per b).
+// Adjoint: one CTA per grid node (c, a, b): gm[c,a,b] = - sum_i sum_j Wr[i,a] Wc[j,b] G[c,i,j] over the node's support
+// rectangle (~2 sh x 2 sw pixels; the whole padding band for border nodes).  The separable weights of the rectangle are
+// staged in shared memory once, the products are summed by a block reduction in a fixed order: hp*wp*2 CTAs (512 for a
+// 16x16 grid), independent loads, no atomics.  (The first version used one CTA per grid ROW with a row loop of dependent
+// loads behind a branch: 85 us at 480x640 against ~8 us for the forward.)
+__device__ __forceinline__ void node_support(int a, int n, int pad, int s, int crop0, int extent, int* lo, int* hi) {
+  // output indices (before the crop) whose two taps can touch node a: padded nodes [a+pad-1, a+pad+1] scaled by s; the
+  // border nodes also own the whole replicate-padding band
+  const int lo_full = (a == 0) ? 0 : (a + pad - 1) * s;
+  const int hi_full = (a == n - 1) ? (n + 2 * pad) * s - 1 : (a + pad + 2) * s - 1;
+  *lo = max(lo_full - crop0, 0);
+  *hi = min(hi_full - crop0, extent - 1);
+}
+
 __global__ void __launch_bounds__(256) tile_flow_upsample_backward_kernel(const float* __restrict__ gdense, TileGeom g,
                                                                           float* __restrict__ gmotion) {
-  extern __shared__ float T[];  // [W]
-  const int c = blockIdx.y, a = blockIdx.x;
-  const int64_t HW = (int64_t)g.H * g.W;
-  const float* G = gdense + c * HW;
-  // rows of the image whose taps can touch node row a: padded rows [a+pad-1, a+pad+1] scaled by sh, widened to the
-  // whole padding band for the border nodes (replicate padding folds it onto them)
-  int lo_full = (a == 0) ? 0 : (a + g.pad_h - 1) * g.sh;
-  int hi_full = (a == g.hp - 1) ? (g.hp + 2 * g.pad_h) * g.sh - 1 : (a + g.pad_h + 2) * g.sh - 1;
-  const int i_lo = max(lo_full - g.h1, 0), i_hi = min(hi_full - g.h1, g.H - 1);
-  for (int j = threadIdx.x; j < g.W; j += blockDim.x) {
-    float acc = 0.f;
-    for (int i = i_lo; i <= i_hi; ++i) {
-      int a0, a1;
-      float l;
-      axis_taps(i + g.h1, g.sh, g.hp, g.pad_h, &a0, &a1, &l);
-      const float w = (a0 == a ? 1.0f - l : 0.f) + (a1 == a ? l : 0.f);
-      if (w != 0.f) acc += w * __ldg(G + (int64_t)i * g.W + j);
+  extern __shared__ float wts[];  // [rows of the support][cols of the support]
+  __shared__ float red[8];
+  const int b = blockIdx.x, a = blockIdx.y, c = blockIdx.z;
+  int i_lo, i_hi, j_lo, j_hi;
+  node_support(a, g.hp, g.pad_h, g.sh, g.h1, g.H, &i_lo, &i_hi);
+  node_support(b, g.wp, g.pad_w, g.sw, g.w1, g.W, &j_lo, &j_hi);
+  const int nr = max(i_hi - i_lo + 1, 0), nc = max(j_hi - j_lo + 1, 0);
+  float* wr = wts;
+  float* wc = wts + nr;
+  for (int t = threadIdx.x; t < nr + nc; t += blockDim.x) {
+    int t0, t1;
+    float l;
+    if (t < nr) {
+      axis_taps(i_lo + t + g.h1, g.sh, g.hp, g.pad_h, &t0, &t1, &l);
+      wr[t] = (t0 == a ? 1.0f - l : 0.f) + (t1 == a ? l : 0.f);
+    } else {
+      axis_taps(j_lo + (t - nr) + g.w1, g.sw, g.wp, g.pad_w, &t0, &t1, &l);
+      wc[t - nr] = (t0 == b ? 1.0f - l : 0.f) + (t1 == b ? l : 0.f);
     }
-    T[j] = acc;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  for (int b = wid; b < g.wp; b += n_warps) {
-    float acc = 0.f;
-    for (int j = lane; j < g.W; j += 32) {
-      int b0, b1;
-      float l;
-      axis_taps(j + g.w1, g.sw, g.wp, g.pad_w, &b0, &b1, &l);
-      const float w = (b0 == b ? 1.0f - l : 0.f) + (b1 == b ? l : 0.f);
-      acc += w * T[j];
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) gmotion[(c * g.hp + a) * g.wp + b] = -acc;
+  const float* G = gdense + (int64_t)c * g.H * g.W;
+  float acc = 0.f;
+  for (int t = threadIdx.x; t < nr * nc; t += blockDim.x) {
+    const int ii = t / nc, jj = t - ii * nc;
+    acc += (wr[ii] * wc[jj]) * __ldg(G + (int64_t)(i_lo + ii) * g.W + (j_lo + jj));
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    gmotion[(c * g.hp + a) * g.wp + b] = -tot;
   }
 }
 
@@ -131,9 +144,9 @@ int cmax_tile_flow_upsample_backward(const float* grad_dense, int hp, int wp, in
   TileGeom g;
   const int rc = make_geom("cmax_tile_flow_upsample_backward", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
   if (rc) return rc;
-  CMAX_REQUIRE((size_t)W * sizeof(float) <= 48 * 1024, "cmax_tile_flow_upsample_backward: image wider than %d pixels", 48 * 1024 / 4);
-  dim3 grid(hp, 2);
-  tile_flow_upsample_backward_kernel<<<grid, 256, (size_t)W * sizeof(float), as_stream(stream)>>>(grad_dense, g, grad_motion);
+  CMAX_REQUIRE((size_t)(H + W) * sizeof(float) <= 48 * 1024, "cmax_tile_flow_upsample_backward: image larger than %d pixels in H + W", 48 * 1024 / 4);
+  dim3 grid(wp, hp, 2);
+  tile_flow_upsample_backward_kernel<<<grid, 256, (size_t)(H + W) * sizeof(float), as_stream(stream)>>>(grad_dense, g, grad_motion);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
 }
