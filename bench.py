@@ -56,8 +56,8 @@ def synth_flows(k: int, seed: int) -> np.ndarray:
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two event kernels at this workload, from the
-# committed `ncu --set full` capture profiles/r01_ncu_r1m.txt (strip kernels) / r01_ncu_r1k.txt (run kernels)
-TRAFFIC_SOURCE = "profiles/r01_ncu_r1m.txt (strips) / r01_ncu_r1k.txt (runs): dram__bytes_read.sum + dram__bytes_write.sum per launch"
+# committed `ncu --set full` capture profiles/r01_ncu_r1o.txt (strip kernels) / r01_ncu_r1k.txt (run kernels)
+TRAFFIC_SOURCE = "profiles/r01_ncu_r1o.txt (strips) / r01_ncu_r1k.txt (runs): dram__bytes_read.sum + dram__bytes_write.sum per launch"
 _TRAFFIC = {"K1 vote (vote_strips_kernel)": 26.09e6, "K3 grad (grad_strips_kernel)": 26.81e6,
             "K1 vote (vote_runs_kernel)": 42.18e6, "K3 grad (grad_runs_kernel)": 42.91e6}
 

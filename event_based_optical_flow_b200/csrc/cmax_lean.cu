@@ -351,7 +351,13 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
 // ------------------------------------------------------------------------------------------------ dispatch
 static int strips_grid_size(int per_sm, int64_t n_strips) {
   const int64_t tiles = (n_strips + 31) / 32, ctas = (tiles + kRunWarps - 1) / kRunWarps;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm));
+  static int waves = -1;  // CMAX_STRIPS_WAVES=k: k x the resident CTAs instead of 1 x (0 = one tile per warp); measurement
+  if (waves < 0) {
+    const char* e = getenv("CMAX_STRIPS_WAVES");
+    waves = e ? atoi(e) : 1;
+  }
+  if (waves == 0) return (int)std::max<int64_t>(1, ctas);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm * waves));
 }
 template <typename K>
 static int strips_grid(K kernel, int64_t n_strips) {
