@@ -10,6 +10,7 @@ receive a gradient (the reference only ever asks for d cost / d motion, scipy_au
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -353,7 +354,9 @@ class ContrastObjective:
                 _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, 0, None, self._flags_grad_ptr, ep_grad, stream)
             return
         if self.exchange == "peer":
-            self._symm.barrier(channel=0)  # every rank's partial IWE is complete and visible
+            skip = os.environ.get("CMAX_TIMING_SKIP_BARRIER") == "1"  # measurement only: results are then undefined
+            if not skip:
+                self._symm.barrier(channel=0)  # every rank's partial IWE is complete and visible
             combined = C.c_int32(0)
             _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
                       self._ws_ptr, cost.data_ptr(), C.byref(combined), None, None, stream)
@@ -361,7 +364,8 @@ class ContrastObjective:
                       want, cost.data_ptr(), stream)
             if grad is not None:
                 _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
-                self._symm.barrier(channel=1)
+                if not skip:
+                    self._symm.barrier(channel=1)
                 _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), None, None, stream)
             else:
                 # value only: still close the evaluation with a barrier, so that no rank overwrites its partial IWE (next
