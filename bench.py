@@ -282,26 +282,24 @@ def run_b200(args) -> None:
     e2e_flow = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
 
     def e2e_steps(count: int):
-        t0 = time.perf_counter()
+        """Host wall-clock of `count` end-to-end steps.  The L2 flush (hygiene, not part of a step) is enqueued and waited
+        for BEFORE the clock of each step starts, so no flush time has to be estimated and subtracted."""
+        total = 0.0
         for k in range(count):
             flush_l2()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             e2e_flow.copy_(host_flows[k % N_FLOWS], non_blocking=True)   # H2D from pinned host memory
             obj.step_into(e2e_flow, e2e_cost, e2e_grad)                  # the allocation-free public entry point
             out_host.copy_(out_dev, non_blocking=True)                   # D2H: gradient + cost
             torch.cuda.synchronize()
-        return time.perf_counter() - t0
-
-    def flush_only(count: int):
-        t0 = time.perf_counter()
-        for k in range(count):
-            flush_l2()
-            torch.cuda.synchronize()
-        return time.perf_counter() - t0
+            total += time.perf_counter() - t0
+        return total
 
     e2e_steps(max(3, args.warmup))
     if world > 1:
         dist.barrier()
-    e2e_s = e2e_steps(args.steps) - flush_only(args.steps)   # the L2 flush is hygiene, not part of the step
+    e2e_s = e2e_steps(args.steps)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
