@@ -195,18 +195,29 @@ __global__ void __launch_bounds__(256) strip_counts_kernel(const uint32_t* __res
 __global__ void __launch_bounds__(256) pack_strips_kernel(const float4* __restrict__ ev, const uint32_t* __restrict__ sorted_keys, int64_t n,
                                                           const uint32_t* __restrict__ key_counts, const uint32_t* __restrict__ key_first,
                                                           const uint32_t* __restrict__ key_strip0, int H, int W,
-                                                          const cmax_time_params_t* __restrict__ tp, int with_dt,
+                                                          const cmax_time_params_t* __restrict__ tp, int with_dt, int tile_bytes,
                                                           unsigned char* __restrict__ out) {
   const float ref = tp->ref[0], period = tp->period[0];
+  const int n_bins = tp->n_bins, n_ref = tp->n_ref;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
     const uint32_t key = sorted_keys[j];
     const uint32_t rank = (uint32_t)j - key_first[key];
     const uint32_t strip = key_strip0[key] + rank / kRunE, slot = rank % kRunE;
     const float4 e = ev[j];
-    unsigned char* tile = out + (size_t)(strip / 32) * kStripTileBytes;
+    unsigned char* tile = out + (size_t)(strip / 32) * tile_bytes;
     const uint32_t lane = strip % 32;
     const float tz = with_dt ? normalised_dt(e.z, ref, period, 1) : e.z;
     reinterpret_cast<float*>(tile + 128 + (slot / 4) * 512 + lane * 16)[slot % 4] = tz;
+    if (n_bins > 0) {
+      // time-aware plans: the time bin of every event for every reference time is iteration-invariant too
+      // (src/warp.py:342-352) -- one byte each, 255 = in no bin
+      for (int r = 0; r < n_ref; ++r) {
+        const float dt = normalised_dt(e.z, tp->ref[r], tp->period[r], 1);
+        const float inv = (float)n_bins / (tp->dt_max[r] - tp->dt_min[r]);
+        const int b = time_bin(dt, tp->edges[r], n_bins, tp->dt_min[r], inv);
+        tile[kStripTileBytes + r * kStripBinBytes + lane * kRunE + slot] = (unsigned char)(b < 0 ? 255 : b);
+      }
+    }
     if (slot == 0) {
       int r, c;
       source_pixel(e.x, e.y, H, W, &r, &c);
@@ -280,7 +291,7 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
       }
       L.scan_temp_bytes = st;
       L.off_scan_temp = off; off = align_up(off + st + 256, 256);
-      L.off_strips = off; off = align_up(off + (size_t)(L.strip_capacity / 32) * kStripTileBytes, 256);
+      L.off_strips = off; off = align_up(off + (size_t)(L.strip_capacity / 32) * (kStripTileBytes + CMAX_MAX_REFS * kStripBinBytes), 256);
     }
   }
   L.total = off;
@@ -561,10 +572,12 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
                                                                  plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
     if (plan->strips != nullptr) {
       const int64_t tiles = (plan->n_strips + 31) / 32;
-      CMAX_CUDA_CHECK(cudaMemsetAsync(plan->strips, 0, (size_t)tiles * kStripTileBytes, as_stream(stream)));
+      plan->strip_tile_bytes = kStripTileBytes + (n_bins > 0 ? n_ref * kStripBinBytes : 0);
+      CMAX_CUDA_CHECK(cudaMemsetAsync(plan->strips, 0, (size_t)tiles * plan->strip_tile_bytes, as_stream(stream)));
       pack_strips_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->sorted_keys, plan->n,
                                                                plan->key_counts, plan->key_first, plan->key_strip0, plan->H, plan->W,
-                                                               plan->d_params, plan->packed_has_dt, static_cast<unsigned char*>(plan->strips));
+                                                               plan->d_params, plan->packed_has_dt, plan->strip_tile_bytes,
+                                                               static_cast<unsigned char*>(plan->strips));
     }
     CMAX_CUDA_CHECK(cudaGetLastError());
   }

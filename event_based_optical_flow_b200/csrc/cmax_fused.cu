@@ -989,7 +989,7 @@ static void launch_vote_runs(int variant, cudaStream_t s, const FusedArgs& a, fl
 
 template <int MODEL, int NREF>
 static void launch_vote(int variant, int grid, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
-  if (variant == 5 && a.strips != nullptr) {
+  if (variant == 5 && a.strips != nullptr && a.strip_tile_bytes == strips_tile_bytes_for(MODEL, NREF)) {
     launch_vote_strips(MODEL, NREF, s, a, acc);
   } else if (variant >= 2) {
     if (a.compact) launch_vote_runs<MODEL, NREF, true>(variant, s, a, acc);
@@ -1022,7 +1022,7 @@ static void launch_grad_runs(int gvar, cudaStream_t s, const FusedArgs& a, const
 
 template <int MODEL, int NREF>
 static void launch_grad(int gvar, int grid, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gm) {
-  if (gvar == 5 && a.strips != nullptr) {
+  if (gvar == 5 && a.strips != nullptr && a.strip_tile_bytes == strips_tile_bytes_for(MODEL, NREF)) {
     launch_grad_strips(MODEL, NREF, pdl_enabled(), s, a, gq, gm);
   } else if (gvar >= 2) {
     if (a.compact) launch_grad_runs<MODEL, NREF, true>(gvar, s, a, gq, gm);
@@ -1060,6 +1060,7 @@ static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.cells = (int64_t)(p->Hp + 1) * (p->Wp + 1) + 1;
   a.strips = p->strips;
   a.n_strips = p->n_strips;
+  a.strip_tile_bytes = p->strip_tile_bytes;
   a.zero256 = nullptr;
   {
     static int dbg = -1;

@@ -13,6 +13,8 @@
 // the four bilinear weights are accumulated with two FFMA2, and K3 reads the gradient quad of an out-of-image or padding
 // event from an all-zero extra cell, which removes every validity select from its accumulation.
 // Results equal the run kernels' up to fp32 summation order; warped coordinates stay bit-exact.
+#include <stddef.h>
+
 #include "cmax_runs.cuh"
 
 namespace cmax {
@@ -37,8 +39,14 @@ __device__ __forceinline__ float small_int_to_float(unsigned v) { return __fsub_
 struct StripTile {
   uint32_t head[32];   // row << 17 | col << 4 | count (0..8 events of this strip are real)
   float4 t[2][32];     // t[h][lane] = times 4h .. 4h+3 of lane's strip (normalised dt for a single reference time)
+  uint2 bins[CMAX_MAX_REFS][32];  // time-aware plans only, first n_ref entries: byte k of bins[r][lane] = time bin of event k (255: none)
 };
-static_assert(sizeof(StripTile) == kStripTileBytes, "strip tile layout");
+static_assert(offsetof(StripTile, bins) == kStripTileBytes && sizeof(uint2) * 32 == kStripBinBytes, "strip tile layout");
+// bytes of one warp-tile as the plan packed it for this kernel instantiation
+template <int MODEL, int NREF>
+struct StripTileBytes {
+  static constexpr uint32_t value = kStripTileBytes + (MODEL == CMAX_MOTION_VOXEL ? NREF * kStripBinBytes : 0);
+};
 
 // Per-strip constants.
 struct StripHead {
@@ -88,31 +96,29 @@ __device__ __forceinline__ f32x2 lean_warp(f32x2 xy, float tz, f32x2 f, const Re
   return sub2(xy, mul2_rounded(f, dt));                                   // src/warp.py:306-307
 }
 
-// Time-aware (voxel) model: the flow vector depends on the event's time bin.  The events of a strip are in time order, so
-// the bin never decreases along the strip: the first event does the full search (time_bin), every later one only checks
-// whether it crossed the next edge, and the flow vector is re-fetched only when the bin moved (src/warp.py:346-357).
+// Time-aware (voxel) model: the flow vector depends on the event's time bin (src/warp.py:346-357).  The bin of every event
+// for every reference time is iteration-invariant, so the plan packed it next to the times (one byte each); the events
+// of a strip are in time order, so the bin changes at most a few times along a strip and the flow vector is re-fetched
+// only then.
 struct VoxelWalk {
   int bin;    // -1 = none yet / in no bin
   f32x2 f;
 };
 template <int NREF, bool PRE_DT>
-__device__ __forceinline__ f32x2 voxel_warp(f32x2 xy, float tz, int k, bool real, int src, int HW, const float* __restrict__ motion,
-                                            const RefRegs<NREF>& rr, const TimeSmem& s, int r, VoxelWalk& vw, float& dt) {
+__device__ __forceinline__ f32x2 voxel_warp(f32x2 xy, float tz, int k, bool real, uint2 bins, int src, int HW, const float* __restrict__ motion,
+                                            const RefRegs<NREF>& rr, int r, VoxelWalk& vw, float& dt) {
   dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
-  int b = vw.bin;
-  if (k == 0 || b < 0) {
-    b = time_bin(dt, s.edges[r], s.n_bins, s.dt_min[r], s.inv_width[r]);
-  } else if (real) {  // (strip padding carries dt = 0 and is masked by the caller: leave the walk alone)
-    while (b < s.n_bins - 1 && dt >= s.edges[r][b + 1]) ++b;
-  }
-  if (b != vw.bin) {
+  const unsigned word = k < 4 ? bins.x : bins.y;
+  int b = (int)((word >> (8 * (k & 3))) & 0xFFu);
+  b = (b == 255) ? -1 : b;
+  if (real && b != vw.bin) {  // (strip padding is masked by the caller: leave the walk alone)
     vw.bin = b;
     if (b >= 0) {
       const float* fb = motion + (int64_t)b * 2 * HW;
       vw.f = pk2(__ldg(fb + src), __ldg(fb + HW + src));
     }
   }
-  return b >= 0 ? sub2(xy, mul2_rounded(vw.f, dt)) : xy;
+  return vw.bin >= 0 ? sub2(xy, mul2_rounded(vw.f, dt)) : xy;
 }
 
 // ------------------------------------------------------------------------------------------------ K1
@@ -124,14 +130,14 @@ struct StripVote {
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void strip_vote_step(float tz, int k, const StripHead& h, f32x2 f, StripVote<NREF>& st, const FusedArgs& a,
-                                                int HW, int off_r, int off_c, const RefRegs<NREF>& rr, const TimeSmem& s,
+__device__ __forceinline__ void strip_vote_step(float tz, int k, const StripHead& h, f32x2 f, const uint2 (&bins)[NREF], StripVote<NREF>& st,
+                                                const FusedArgs& a, int HW, int off_r, int off_c, const RefRegs<NREF>& rr,
                                                 float4* __restrict__ acc) {
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float dt;
     f32x2 w;
-    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, h.src, HW, a.motion, rr, s, r, st.vw[r], dt);
+    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, bins[r], h.src, HW, a.motion, rr, r, st.vw[r], dt);
     else w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, rr, r, dt);
     const LeanGeom g = lean_geometry(w, off_r, off_c);
     const int c = lean_cell(g, k, h.count, a.Hp, a.Wp, -1);
@@ -158,15 +164,14 @@ __device__ __forceinline__ void strip_vote_step(float tz, int k, const StripHead
 
 template <int MODEL, int NREF, bool PRE_DT>
 __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, float4* __restrict__ acc) {
-  __shared__ TimeSmem s;
-  __shared__ TilePipe<kStripTileBytes> pipes[kRunWarps];
-  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
+  constexpr uint32_t kTile = StripTileBytes<MODEL, NREF>::value;
+  __shared__ TilePipe<kTile> pipes[kRunWarps];
   if (a.zero256 != nullptr && blockIdx.x == 0 && threadIdx.x < 64) a.zero256[threadIdx.x] = 0u;  // StatAcc block + CTA counter
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
   const int lane = threadIdx.x & 31;
   const int off_r = a.pad_h + 1 - 0x4B400000, off_c = a.pad_w + 1 - 0x4B400000;
-  TilePipe<kStripTileBytes>& pipe = pipes[threadIdx.x >> 5];
+  TilePipe<kTile>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
   const int64_t n_tiles = (a.n_strips + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
@@ -185,6 +190,9 @@ __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, f
     if (MODEL == CMAX_MOTION_DENSE) f = pk2(__ldg(a.motion + h.src), __ldg(a.motion + HW + h.src));
     const float4 ta = T->t[0][lane], tb = T->t[1][lane];
     const float tz[kRunE] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+    uint2 bins[NREF];
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) bins[r] = (MODEL == CMAX_MOTION_VOXEL) ? T->bins[r][lane] : make_uint2(0u, 0u);
     StripVote<NREF> st;
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, f
       st.vw[r].f = 0ull;
     }
 #pragma unroll
-    for (int k = 0; k < kRunE; ++k) strip_vote_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, st, a, HW, off_r, off_c, rr, s, acc);
+    for (int k = 0; k < kRunE; ++k) strip_vote_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, bins, st, a, HW, off_r, off_c, rr, acc);
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
       float w0, w1, w2, w3;
@@ -217,14 +225,14 @@ struct StripGrad {
 };
 
 template <int MODEL, int NREF, bool PRE_DT>
-__device__ __forceinline__ void strip_grad_step(float tz, int k, const StripHead& h, f32x2 f, StripGrad<MODEL, NREF>& st,
-                                                const FusedArgs& a, int HW, int off_r, int off_c, int outside, const RefRegs<NREF>& rr,
-                                                const TimeSmem& s, const float4* __restrict__ gq, float* __restrict__ gmotion) {
+__device__ __forceinline__ void strip_grad_step(float tz, int k, const StripHead& h, f32x2 f, const uint2 (&bins)[NREF],
+                                                StripGrad<MODEL, NREF>& st, const FusedArgs& a, int HW, int off_r, int off_c, int outside,
+                                                const RefRegs<NREF>& rr, const float4* __restrict__ gq, float* __restrict__ gmotion) {
 #pragma unroll
   for (int r = 0; r < NREF; ++r) {
     float dt;
     f32x2 w;
-    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, h.src, HW, a.motion, rr, s, r, st.vw[r], dt);
+    if constexpr (MODEL == CMAX_MOTION_VOXEL) w = voxel_warp<NREF, PRE_DT>(h.xy, tz, k, k < h.count, bins[r], h.src, HW, a.motion, rr, r, st.vw[r], dt);
     else w = lean_warp<MODEL, NREF, PRE_DT>(h.xy, tz, f, rr, r, dt);
     const int bin = (MODEL == CMAX_MOTION_VOXEL) ? st.vw[r].bin : 0;
     const LeanGeom g = lean_geometry(w, off_r, off_c);
@@ -262,16 +270,15 @@ __device__ __forceinline__ void strip_grad_step(float tz, int k, const StripHead
 
 template <int MODEL, int NREF, bool PRE_DT>
 __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, const float4* __restrict__ gq, float* __restrict__ gmotion) {
-  __shared__ TimeSmem s;
-  __shared__ TilePipe<kStripTileBytes> pipes[kRunWarps];
+  constexpr uint32_t kTile = StripTileBytes<MODEL, NREF>::value;
+  __shared__ TilePipe<kTile> pipes[kRunWarps];
   __shared__ double red2[2][kRunWarps];
-  if (MODEL == CMAX_MOTION_VOXEL) stage_time<NREF, true>(a.tp, s);
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
   const int lane = threadIdx.x & 31;
   const int off_r = a.pad_h + 1 - 0x4B400000, off_c = a.pad_w + 1 - 0x4B400000;
   const int outside = (int)a.cells - 1;
-  TilePipe<kStripTileBytes>& pipe = pipes[threadIdx.x >> 5];
+  TilePipe<kTile>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
   const int64_t n_tiles = (a.n_strips + 31) / 32;
   const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
@@ -291,6 +298,9 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     if (MODEL == CMAX_MOTION_DENSE) f = pk2(__ldg(a.motion + h.src), __ldg(a.motion + HW + h.src));
     const float4 ta = T->t[0][lane], tb = T->t[1][lane];
     const float tz[kRunE] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+    uint2 bins[NREF];
+#pragma unroll
+    for (int r = 0; r < NREF; ++r) bins[r] = (MODEL == CMAX_MOTION_VOXEL) ? T->bins[r][lane] : make_uint2(0u, 0u);
     StripGrad<MODEL, NREF> st;
 #pragma unroll
     for (int r = 0; r < NREF; ++r) {
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     }
 #pragma unroll
     for (int k = 0; k < kRunE; ++k)
-      strip_grad_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, st, a, HW, off_r, off_c, outside, rr, s, gq, gmotion);
+      strip_grad_step<MODEL, NREF, PRE_DT>(tz[k], k, h, f, bins, st, a, HW, off_r, off_c, outside, rr, gq, gmotion);
     if (MODEL == CMAX_MOTION_DENSE) {  // one flush per strip: the strip IS one source pixel
       float g0, g1;
       upk2(st.g[0], g0, g1);
@@ -402,6 +412,11 @@ static void grad_strips_m(int n_ref, bool pdl, cudaStream_t s, const FusedArgs& 
     default: grad_strips_mn<MODEL, 4>(pdl, s, a, gq, gm); break;
 #endif
   }
+}
+
+// tile size the strip kernels of (motion_model, n_ref) expect; the caller checks it against what the plan packed
+int strips_tile_bytes_for(int motion_model, int n_ref) {
+  return kStripTileBytes + (motion_model == CMAX_MOTION_VOXEL ? n_ref * kStripBinBytes : 0);
 }
 
 void launch_vote_strips(int motion_model, int n_ref, cudaStream_t s, const FusedArgs& a, float4* acc) {

@@ -12,6 +12,7 @@ constexpr int kWin = kTile + 2 * kHalo;  // 64
 constexpr int kRunE = 8;                  // consecutive events one thread of a run kernel walks
 constexpr int kWarpTile = 32 * kRunE;    // events per warp-tile of the packed copy
 constexpr int kStripTileBytes = 128 + 32 * kRunE * 4;  // 32 strip headers + 32 strips of kRunE times (cmax_events.cu)
+constexpr int kStripBinBytes = 32 * kRunE;              // time-aware plans: + one byte per event and reference time (its time bin)
 constexpr int kChunk = 8192;             // events per CTA work item (bounds the fixed-point range, see cmax_fused.cu)
 
 struct Chunk {
@@ -39,6 +40,7 @@ struct cmax_plan {
   // the batch does not qualify (not pixel-ordered, fractional coordinates, or too sparse for the padding to pay)
   void* strips;
   int64_t n_strips;
+  int strip_tile_bytes;  // kStripTileBytes, + n_ref * kStripBinBytes when the plan was packed for a flow voxel (n_bins > 0)
   const uint32_t* sorted_keys;
   const uint32_t* key_counts;
   const uint32_t* key_first;

@@ -15,6 +15,7 @@ struct FusedArgs {
   int compact;
   const void* strips;    // the plan's strips (cmax_plan.cuh), read by the strip kernels; NULL when the batch has none
   int64_t n_strips;
+  int strip_tile_bytes;
   int64_t n;
   int H, W, Hp, Wp, pad_h, pad_w;
   const float* motion;
@@ -153,6 +154,15 @@ __device__ __forceinline__ void pipe_issue(TilePipe<BYTES, NS>& p, int stage, co
   }
 }
 
+// the same with the tile size taken at run time from a template-sized landing zone
+template <uint32_t BYTES, int NS>
+__device__ __forceinline__ void pipe_issue_n(TilePipe<BYTES, NS>& p, int stage, const void* __restrict__ packed, int64_t tile, uint32_t bytes, int lane) {
+  if (lane == 0) {
+    mbar_expect_tx(&p.bar[stage], bytes);
+    bulk_g2s(p.buf[stage], static_cast<const unsigned char*>(packed) + tile * bytes, bytes, &p.bar[stage]);
+  }
+}
+
 // Per-reference-time scalars kept in registers (dense / 2-dof); the voxel model also needs the bin edges (shared).
 template <int NREF>
 struct RefRegs {
@@ -220,6 +230,7 @@ static inline int run_grid(K kernel, int64_t n) {
 
 
 // strip kernels (cmax_lean.cu)
+int strips_tile_bytes_for(int motion_model, int n_ref);
 void launch_vote_strips(int motion_model, int n_ref, cudaStream_t s, const FusedArgs& a, float4* acc);
 void launch_grad_strips(int motion_model, int n_ref, bool pdl, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gmotion);
 

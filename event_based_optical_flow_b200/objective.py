@@ -328,6 +328,7 @@ class ContrastObjective:
         model = _lib.MOTION[self.motion_model]
         orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
         want = 1 if grad is not None else 0
+        self.plan.set_refs(self.directions, self.n_bins)  # no-op unless another objective re-packed the shared plan
         if self.group is None:  # single GPU: the three stages in one C-ABI call (4 kernels for the metric configuration)
             _lib.call("cmax_objective", self.plan.handle, model, m.data_ptr(), C.byref(self.spec), orig, self._ws_ptr, cost.data_ptr(),
                       grad.data_ptr() if grad is not None else None, stream)
