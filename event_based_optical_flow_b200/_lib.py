@@ -60,6 +60,7 @@ _SIGNATURES = {
     "cmax_plan_create": (_i, [C.POINTER(_p), _p, _i64, _i, _i, _i, _i, _i, _f, _f, _i, _p, _sz, _p]),
     "cmax_plan_destroy": (None, [_p]),
     "cmax_plan_info": (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(C.c_int32)]),
+    "cmax_plan_strips": (_i, [_p, C.POINTER(_i64)]),
     "cmax_plan_set_refs": (_i, [_p, C.POINTER(Ref), _i, _i, _p]),
     "cmax_plan_set_variant": (_i, [_p, _i, _i]),
     "cmax_plan_set_stage_mask": (_i, [_p, _i]),

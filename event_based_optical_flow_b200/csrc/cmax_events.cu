@@ -516,6 +516,12 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
   return CMAX_OK;
 }
 
+int cmax_plan_strips(const cmax_plan_t* plan, int64_t* h_n_strips) {
+  CMAX_REQUIRE(plan != nullptr && h_n_strips != nullptr, "cmax_plan_strips: NULL argument");
+  *h_n_strips = plan->strips != nullptr ? plan->n_strips : 0;
+  return CMAX_OK;
+}
+
 int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_variant: plan is NULL");
   CMAX_REQUIRE(vote_variant >= 0 && vote_variant <= 5, "cmax_plan_set_variant: vote_variant must be in [0,5]");

@@ -103,6 +103,13 @@ class EventPlan:
             raise RuntimeError("EventPlan already closed")
         return self._handle
 
+    @property
+    def n_strips(self) -> int:
+        """Strips the plan cut the batch into; 0 = the strip kernels are not available for this batch (see cmax_plan_strips)."""
+        n = C.c_int64(0)
+        _lib.call("cmax_plan_strips", self.handle, C.byref(n))
+        return int(n.value)
+
     def set_refs(self, directions: Sequence[Direction], n_bins: int = 0) -> None:
         directions = tuple(directions)
         if (directions, n_bins) == (self.refs, self.n_bins):

@@ -192,11 +192,17 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
 void cmax_plan_destroy(cmax_plan_t* plan);
 /* (t_min, t_max, n, order) the plan uses. */
 int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_t* h_n, int32_t* h_order);
+/* Number of 8-event strips the plan cut the batch into (0 = the batch did not qualify: not pixel-ordered, fractional
+ * coordinates, image side >= 8192, or so sparse that padding every pixel's run to whole strips would cost more than 50 %).
+ * Variant 5 (the default when there are strips) runs the strip kernels, see cmax_plan_set_variant. */
+int cmax_plan_strips(const cmax_plan_t* plan, int64_t* h_n_strips);
 /* Select reference times / voxel bins for subsequent calls (enqueues one tiny kernel). */
 int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream);
 /* Kernel variants (all give the same results up to fp32 summation order; kept selectable so that profiles/ can show
  * each design choice measured against the others):
- *   vote_variant 2 (default) = each thread walks a run of consecutive events and sums the weights of events that
+ *   vote_variant / grad_variant 5 (default when the plan has strips, else they fall back to 2) = the strip kernels: one
+ *                  thread per 8-event strip of ONE source pixel (per-strip coordinates / flow / time bins, 4.5 B per event);
+ *   vote_variant 2 = each thread walks a run of consecutive events and sums the weights of events that
  *                  fall into the same accumulator cell in registers: one red.v4 per cell change;
  *                3 = the same with the flow loads of a warp-tile batched (16 more registers);
  *                0 = one red.v4 per event into the per-corner accumulators; 1 = four scalar red.f32 per event

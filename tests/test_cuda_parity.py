@@ -358,3 +358,45 @@ def test_directions_of_fused_costs(B, dev, golden_random):
             arg["iwe"] = arg["backward_iwe"]
             plug = float(cost.calculate(arg))
             assert abs(fused - plug) <= 1e-5 * abs(plug), (cn, direction, fused, plug)
+
+
+# ------------------------------------------------------------------------------------------------ strip kernels, all instantiations
+@pytest.mark.parametrize("model,cost,sigma", [("dense-flow", "multi_focal_normalized_gradient_magnitude", 1.0),
+                                              ("dense-flow", "gradient_magnitude", 0.0),
+                                              ("dense-flow-voxel", "image_variance", 0.0),
+                                              ("dense-flow-voxel", "multi_focal_normalized_image_variance", 1.0),
+                                              ("2d-translation", "image_variance", 0.0),
+                                              ("2d-translation", "multi_focal_normalized_gradient_magnitude", 1.0)])
+def test_strip_kernels_every_model_vs_oracle_and_run_kernels(B, dev, model, cost, sigma):
+    """A batch dense enough for the plan to build strips (65 events per pixel): the strip kernels (variant 5, the default
+    there) for every motion model with 1 and 3 reference times against the oracle and against the run kernels (variant 2)."""
+    rng = np.random.default_rng(17)
+    H, W, n, T = 48, 64, 200_000, 6
+    ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1).astype(np.float32)
+    ev = torch.from_numpy(ev)
+    if model == "dense-flow":
+        motion = torch.from_numpy(rng.uniform(-6, 6, (2, H, W)).astype(np.float32))
+    elif model == "dense-flow-voxel":
+        motion = torch.from_numpy(rng.uniform(-6, 6, (T, 2, H, W)).astype(np.float32))
+    else:
+        motion = torch.tensor([9.0, -5.0])
+    kw = dict(cost=cost, motion_model=model, sigma=sigma, n_bins=T if model == "dense-flow-voxel" else None)
+    obj = B.ContrastObjective(ev.to(dev), (H, W), order="pixel", **kw)
+    assert obj.plan.n_strips > 0, "this batch must qualify for strips"
+    assert obj.plan.n_strips * 8 <= 1.5 * n
+    v5, g5 = obj.value_and_grad(motion.to(dev))
+    obj.plan.set_variant(2, 2)
+    v2, g2 = obj.value_and_grad(motion.to(dev))
+    ref_v, ref_g = O.objective_value_and_grad(ev, motion, (H, W), **{k: v for k, v in kw.items() if k != "n_bins"})
+    ref_v64, _ = O.objective_value_and_grad(ev.double(), motion.double(), (H, W), **{k: v for k, v in kw.items() if k != "n_bins"})
+    assert abs(float(v5) - float(ref_v64)) <= 2e-5 * abs(float(ref_v64)), (float(v5), float(ref_v64))
+    assert abs(float(v5) - float(v2)) <= 1e-6 * abs(float(v2))
+    assert _rel(g5.cpu().numpy(), ref_g.numpy()) <= 1e-4
+    assert _rel(g5.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
+    # the un-blurred IWE stack of the strip K1 against the oracle's images
+    obj.plan.set_variant(5, 5)
+    iwe = obj.iwe(motion.to(dev)).cpu()
+    _, images = O.objective(ev, motion, (H, W), motion_model=model, cost=cost, sigma=0.0, return_images=True)
+    assert iwe.shape[0] == len(obj.ref_keys)
+    for r, key in enumerate(obj.ref_keys):
+        torch.testing.assert_close(iwe[r], images[key], rtol=1e-5, atol=2e-4)
