@@ -1,22 +1,12 @@
-"""Cost plugin registry, keyed by `.name` exactly like the reference (src/costs/__init__.py:23-38)."""
+"""Cost plugins on the CUDA operators.  `functions` maps a plugin's `name` to its class, the table the reference's solver
+indexes with the YAML's `cost:` string (src/costs/__init__.py:35); every subclass of `CostBase` that defines `name`
+registers itself on import."""
+from .base import REGISTRY as functions
 from .base import CostBase
 from .contrast import (GradientMagnitude, ImageVariance, MultiFocalNormalizedGradientMagnitude,
                        MultiFocalNormalizedImageVariance, NormalizedGradientMagnitude, NormalizedImageVariance)
+from .hybrid import HybridCost
 from .total_variation import TotalVariation
 
-
-def inheritors(klass):
-    subclasses = set()
-    work = [klass]
-    while work:
-        parent = work.pop()
-        for child in parent.__subclasses__():
-            if child not in subclasses:
-                subclasses.add(child)
-                work.append(child)
-    return subclasses
-
-
-functions = {k.name: k for k in inheritors(CostBase) if hasattr(k, "name")}
-
-from .hybrid import HybridCost  # noqa: E402  (needs `functions`)
+__all__ = ["functions", "CostBase", "HybridCost", "TotalVariation", "ImageVariance", "GradientMagnitude", "NormalizedImageVariance",
+           "NormalizedGradientMagnitude", "MultiFocalNormalizedImageVariance", "MultiFocalNormalizedGradientMagnitude"]

@@ -30,9 +30,7 @@ class ImageVariance(CostBase):
     def __init__(self, direction="minimize", store_history: bool = False, *args, **kwargs):
         super().__init__(direction=direction, store_history=store_history)
 
-    @CostBase.register_history
-    @CostBase.catch_key_error
-    def calculate(self, arg: dict) -> torch.Tensor:
+    def _loss(self, arg: dict) -> torch.Tensor:
         iwe = require_cuda_image(arg["iwe"], self.name)
         return self.calculate_torch(iwe, arg["omit_boundary"])
 
@@ -53,9 +51,7 @@ class GradientMagnitude(CostBase):
         super().__init__(direction=direction, store_history=store_history)
         self.precision = precision
 
-    @CostBase.register_history
-    @CostBase.catch_key_error
-    def calculate(self, arg: dict) -> torch.Tensor:
+    def _loss(self, arg: dict) -> torch.Tensor:
         iwe = require_cuda_image(arg["iwe"], self.name)
         return self.calculate_torch(iwe, arg["omit_boundary"])
 
@@ -77,9 +73,7 @@ class NormalizedImageVariance(CostBase):
     def __init__(self, direction="minimize", store_history: bool = False, *args, **kwargs):
         super().__init__(direction=direction, store_history=store_history)
 
-    @CostBase.register_history
-    @CostBase.catch_key_error
-    def calculate(self, arg: dict) -> torch.Tensor:
+    def _loss(self, arg: dict) -> torch.Tensor:
         iwe = require_cuda_image(arg["iwe"], self.name)
         orig_iwe = require_cuda_image(arg["orig_iwe"], self.name)
         return self.calculate_torch(iwe, orig_iwe, arg["omit_boundary"])
@@ -104,9 +98,7 @@ class NormalizedGradientMagnitude(CostBase):
         self.gradient_magnitude = GradientMagnitude(direction=direction, store_history=store_history,
                                                     cuda_available=cuda_available, precision=precision)
 
-    @CostBase.register_history
-    @CostBase.catch_key_error
-    def calculate(self, arg: dict) -> torch.Tensor:
+    def _loss(self, arg: dict) -> torch.Tensor:
         iwe = require_cuda_image(arg["iwe"], self.name)
         orig_iwe = require_cuda_image(arg["orig_iwe"], self.name)
         return self.calculate_torch(iwe, orig_iwe, arg["omit_boundary"])
@@ -130,9 +122,7 @@ class _MultiFocal(CostBase):
         super().__init__(direction=direction, store_history=store_history)
         self._inner = self._inner_cls(direction=direction, cuda_available=cuda_available, precision=precision)
 
-    @CostBase.register_history
-    @CostBase.catch_key_error
-    def calculate(self, arg: dict) -> torch.Tensor:
+    def _loss(self, arg: dict) -> torch.Tensor:
         orig_iwe = arg["orig_iwe"]
         forward_iwe = require_cuda_image(arg["forward_iwe"], self.name)
         middle_iwe = arg["middle_iwe"] if "middle_iwe" in arg.keys() else None

@@ -51,58 +51,64 @@ def _resolve_direction(direction):
     raise ValueError(e)
 
 
-class Warp(object):
-    """Warp functions class (CUDA).  Args as src/warp.py:35-44."""
+# motion models whose parameters are the two translation components (the only parametric family of this release of the
+# reference, src/warp.py:64-128); "dense-flow" is accepted by the bookkeeping helpers as "a rigid translation everywhere"
+_TRANSLATION_MODELS = ("2d-translation", "rigid-optical-flow")
+_TRANSLATION_KEYS = ("trans_x", "trans_y")
+
+
+def _check_parametric(motion_model: str, allow_dense: bool) -> None:
+    if motion_model in _TRANSLATION_MODELS:
+        return
+    if allow_dense and motion_model == "dense-flow":
+        logger.warning(f"Assume only rigid transformation {motion_model = }, not meaningful.")
+        return
+    raise MotionModelKeyError(motion_model)
+
+
+class Warp:
+    """Event warping on the CUDA kernels.  Constructor arguments as the reference's (src/warp.py:35-44):
+    image_size (H, W), calculate_feature, normalize_t, calib_param."""
+
+    _SETTABLE = ("image_size", "calculate_feature", "normalize_t", "calib_param")
 
     def __init__(self, image_size: tuple, calculate_feature: bool = False, normalize_t: bool = False,
                  calib_param: Optional[np.ndarray] = None):
         self.update_property(image_size, calculate_feature, normalize_t, calib_param)
-        self.feature_2dof = FeatureCalculatorMock()
-        self.feature_dense = FeatureCalculatorMock()
+        self.feature_2dof = self.feature_dense = FeatureCalculatorMock()
 
     def update_property(self, image_size=None, calculate_feature=None, normalize_t=None, calib_param=None):
-        if image_size is not None:
-            self.image_size = image_size
-        if calculate_feature is not None:
-            self.calculate_feature = calculate_feature
-        if normalize_t is not None:
-            self.normalize_t = normalize_t
-        if calib_param is not None:
-            logger.info("Set camera matrix K.")
-            self.calib_param = calib_param
+        """Set whichever properties are given (None = keep)."""
+        for attr, value in zip(self._SETTABLE, (image_size, calculate_feature, normalize_t, calib_param)):
+            if value is None:
+                continue
+            if attr == "calib_param":
+                logger.info("Set camera matrix K.")
+            setattr(self, attr, value)
 
-    # -- bookkeeping helpers, host-side only (src/warp.py:64-128)
+    # -- host-side bookkeeping between parameter dicts, motion vectors and flow fields (src/warp.py:64-153)
     def get_key_names(self, motion_model: str) -> list:
-        if motion_model == "dense-flow":
-            logger.warning(f"Assume only rigid transformation {motion_model = }, not meaningful.")
-            return ["trans_x", "trans_y"]
-        elif motion_model in ["2d-translation", "rigid-optical-flow"]:
-            return ["trans_x", "trans_y"]
-        raise MotionModelKeyError(motion_model)
+        _check_parametric(motion_model, allow_dense=True)
+        return list(_TRANSLATION_KEYS)
 
     def get_motion_vector_size(self, motion_model: str) -> int:
-        params = {k: 0.0 for k in self.get_key_names(motion_model)}
-        return len(self.motion_model_to_motion(motion_model, params))
+        zeros = dict.fromkeys(self.get_key_names(motion_model), 0.0)
+        return len(self.motion_model_to_motion(motion_model, zeros))
 
     def motion_model_to_motion(self, motion_model: str, params: dict) -> np.ndarray:
-        if motion_model == "dense-flow":
-            logger.warning(f"Assume only rigid transformation {motion_model = }")
-            motion = np.array([params["trans_x"], params["trans_y"]])
-            return self.get_flow_from_motion(motion, "2d-translation")
-        elif motion_model in ["2d-translation", "rigid-optical-flow"]:
-            return np.array([params["trans_x"], params["trans_y"]])
-        raise MotionModelKeyError(motion_model)
+        _check_parametric(motion_model, allow_dense=True)
+        theta = np.array([params[k] for k in _TRANSLATION_KEYS])
+        return self.get_flow_from_motion(theta, "2d-translation") if motion_model == "dense-flow" else theta
 
     def motion_model_from_motion(self, motion: np.ndarray, motion_model: str) -> dict:
-        if motion_model in ["dense-flow", "2d-translation", "rigid-optical-flow"]:
-            return {"trans_x": motion[0], "trans_y": motion[1]}
-        raise MotionModelKeyError(motion_model)
+        if motion_model != "dense-flow":
+            _check_parametric(motion_model, allow_dense=False)
+        return {k: motion[i] for i, k in enumerate(_TRANSLATION_KEYS)}
 
     def get_flow_from_motion(self, motion, motion_model: str):
         """Dense flow [2,H,W] equivalent to a parametric motion: the displacement a unit-dt event undergoes
         (src/warp.py:130-153).  For the 2-dof model this is the constant field -theta."""
-        if motion_model not in ["2d-translation", "rigid-optical-flow"]:
-            raise MotionModelKeyError(motion_model)
+        _check_parametric(motion_model, allow_dense=False)
         H, W = self.image_size
         if isinstance(motion, torch.Tensor):
             return -(motion.reshape(2, 1, 1).expand(2, H, W)).clone()
