@@ -7,7 +7,11 @@
 
 A step = one CM iteration over the resident event batch with a fresh flow field.  Workload = BASELINE config 2
 (5 M synthetic events per GPU, 260x346 dense flow, variance cost + gradient); for N > 1 every rank holds its own
-5 M-event contiguous shard (weak scaling) and the partial IWE / gradient are all-reduced over NCCL each step.
+5 M-event contiguous shard (weak scaling) and the partial IWE / gradient are summed across the ranks each step
+(--exchange: NVLink peer-memory kernels behind in-stream barriers by default, NCCL all-reduce or the push exchange on request).
+`value` is timed on the device (CUDA events, L2 flushed before every step, the step replayed from a CUDA graph); `e2e` is the
+same step through the public API with the flow coming from pinned host memory and gradient + cost going back every step;
+`roofline` times each event kernel alone against MEASURED_PEAKS.json; `cpu_baseline` is the oracle port on the host cores.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
