@@ -174,3 +174,38 @@ def test_sharded_composition_gloo_world2():
         out = m.dict()
         mp.spawn(_gloo_worker, args=(world, port, out), nprocs=world, join=True)
         assert len(out) == world and out[0] == out[1]
+
+
+def test_cost_plugin_contract_on_the_host():
+    """The plugin contract the reference's solvers rely on (src/costs/base.py:11-77, src/costs/hybrid.py:12-79), as far as it
+    needs no GPU: KeyError for a missing arg-dict key, history bookkeeping, hybrid weights / 'inv' / member histories."""
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.costs import CostBase, HybridCost
+    for name, cls in B.cost_functions.items():
+        assert issubclass(cls, CostBase) and cls.name == name
+        with pytest.raises(KeyError):
+            cls().calculate({})
+    assert "hybrid" not in B.cost_functions  # like the reference's table, which is built before HybridCost is imported
+    with pytest.raises(NotImplementedError):
+        B.cost_functions["image_variance"]().calculate({"iwe": np.zeros((8, 8)), "omit_boundary": True})  # numpy: not a CUDA plugin's job
+    flow = torch.arange(5.0)[None, :, None].expand(2, 5, 5).contiguous()
+    tv = B.cost_functions["total_variation"](direction="minimize", store_history=True)
+    a = float(tv.calculate({"flow": flow, "omit_boundary": True}))
+    tv.disable_history_register()
+    tv.calculate({"flow": flow, "omit_boundary": True})
+    tv.enable_history_register()
+    tv.calculate({"flow": 2 * flow, "omit_boundary": True})
+    hist = tv.get_history()["loss"]
+    assert len(hist) == 2 and abs(hist[0] - a) < 1e-12 and abs(hist[1] - 2 * a) < 1e-6
+    tv.clear_history()
+    assert tv.get_history() == {"loss": []}
+    assert float(B.cost_functions["total_variation"](direction="maximize").calculate({"flow": flow, "omit_boundary": True})) == -a
+    h = HybridCost("minimize", {"total_variation": 3.0}, store_history=True)
+    assert abs(float(h.calculate({"flow": flow, "omit_boundary": True})) - 3.0 * a) < 1e-6
+    h.update_weight({"total_variation": "inv"})
+    assert abs(float(h.calculate({"flow": flow, "omit_boundary": True})) - 1.0 / a) < 1e-5
+    assert [len(v) for v in h.get_history().values()] == [2, 2]
+    with pytest.raises(AssertionError):
+        h.update_weight({"image_variance": 1.0})
+    h.disable_history_register()
+    assert h.cost_func["total_variation"]["func"].store_history is False
