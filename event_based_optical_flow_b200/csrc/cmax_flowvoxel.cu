@@ -13,6 +13,8 @@
 //
 // Arithmetic: fp32, every operation rounded separately in the reference's order (the library is built -fmad=false), so
 // the voxel is bit-identical to the reference's fp32 torch result.
+#include <vector>
+
 #include "cmax_common.cuh"
 
 namespace cmax {
@@ -277,6 +279,10 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArg
   }
 }
 
+// The propagation itself has no structural limit on the number of levels (the reference's own tests use 60 and 100,
+// tests/utils/test_flow_utils.py:52-106); the voxel WARP is limited to CMAX_MAX_BINS by its edge table.
+constexpr int kFvMaxLevels = 4096;
+
 struct FvGeom {
   int H, W, T, scheme, t0;
   float dt;
@@ -288,7 +294,7 @@ struct FvGeom {
 
 static int fv_geom(const char* fn, int H, int W, int T, int scheme, int t0_middle, FvGeom* g) {
   CMAX_REQUIRE(H >= 1 && W >= 1, "%s: bad image size %dx%d", fn, H, W);
-  CMAX_REQUIRE(T >= 1 && T <= CMAX_MAX_BINS, "%s: time_bin must be in [1,%d], got %d", fn, CMAX_MAX_BINS, T);
+  CMAX_REQUIRE(T >= 1 && T <= kFvMaxLevels, "%s: time_bin must be in [1,%d], got %d", fn, kFvMaxLevels, T);
   CMAX_REQUIRE(scheme == CMAX_SCHEME_UPWIND || scheme == CMAX_SCHEME_BURGERS, "%s: unknown scheme %d", fn, scheme);
   g->H = H; g->W = W; g->T = T; g->scheme = scheme;
   g->t0 = t0_middle ? T / 2 : 0;
@@ -299,15 +305,15 @@ static int fv_geom(const char* fn, int H, int W, int T, int scheme, int t0_middl
 
 // The levels each side of t0 produces, in the order they are stepped: forward side t0+1 .. T-1; backward side
 // t0-1 .. 0 (followed by T-1 when the backward loop wraps).
-static int fv_side(const FvGeom& g, bool forward, int* levels) {
-  int n = 0;
+static std::vector<int> fv_side(const FvGeom& g, bool forward) {
+  std::vector<int> levels;
   if (forward) {
-    for (int l = g.t0 + 1; l <= g.T - 1; ++l) levels[n++] = l;
+    for (int l = g.t0 + 1; l <= g.T - 1; ++l) levels.push_back(l);
   } else {
-    for (int l = g.t0 - 1; l >= 0; --l) levels[n++] = l;
-    if (g.wrap) levels[n++] = g.T - 1;
+    for (int l = g.t0 - 1; l >= 0; --l) levels.push_back(l);
+    if (g.wrap) levels.push_back(g.T - 1);
   }
-  return n;
+  return levels;
 }
 
 static dim3 fv_grid(const FvGeom& g, int z) { return dim3((g.W + kFvTW - 1) / kFvTW, (g.H + kFvTH - 1) / kFvTH, z); }
@@ -336,8 +342,8 @@ int cmax_flow_voxel(const float* dense, int H, int W, int time_bin, int scheme, 
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const int64_t L = 2 * (int64_t)H * W;  // floats per level
-  int lv[2][CMAX_MAX_BINS + 1];
-  const int n[2] = {fv_side(g, true, lv[0]), fv_side(g, false, lv[1])};
+  const std::vector<int> lv[2] = {fv_side(g, true), fv_side(g, false)};
+  const int n[2] = {(int)lv[0].size(), (int)lv[1].size()};
   if (n[0] == 0 && n[1] == 0) {  // T == 1, upwind
     CMAX_CUDA_CHECK(cudaMemcpyAsync(voxel, dense, (size_t)L * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return CMAX_OK;
@@ -376,8 +382,8 @@ int cmax_flow_voxel_backward(const float* dense, const float* voxel, const float
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const int64_t L = 2 * (int64_t)H * W;
-  int lv[2][CMAX_MAX_BINS + 1];
-  const int n[2] = {fv_side(g, true, lv[0]), fv_side(g, false, lv[1])};
+  const std::vector<int> lv[2] = {fv_side(g, true), fv_side(g, false)};
+  const int n[2] = {(int)lv[0].size(), (int)lv[1].size()};
   if (n[0] == 0 && n[1] == 0) {
     CMAX_CUDA_CHECK(cudaMemcpyAsync(grad_dense, grad_voxel, (size_t)L * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return CMAX_OK;

@@ -162,7 +162,8 @@ typedef enum {
 } cmax_voxel_scheme;
 /* construct_dense_flow_voxel_torch (src/utils/flow_utils.py:99-161): dense [2,H,W] (the flow at t0) -> voxel
  * [time_bin,2,H,W] by explicit upwind / inviscid-Burgers steps of dt = 1/time_bin, forward in time from level t0 up and
- * backward (sign-flipped flow) from t0 down; t0 = time_bin/2 when t0_middle, else 0.  fp32, bit-identical to the
+ * backward (sign-flipped flow) from t0 down; t0 = time_bin/2 when t0_middle, else 0; 1 <= time_bin <= 4096 (the reference's
+ * own tests use 60 and 100 levels; only the voxel WARP is limited to CMAX_MAX_BINS).  fp32, bit-identical to the
  * reference's torch fp32 result.  One launch per 8 levels (both sides of t0 in the same launch).  The backward is the
  * exact adjoint (torch's even split of d max(x,0)/dx at x == 0 included), gather form, no atomics: grad_voxel
  * [time_bin,2,H,W] -> grad_dense [2,H,W].  `dense` and `voxel` are the forward's input and output.  workspace:

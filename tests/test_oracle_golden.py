@@ -200,3 +200,17 @@ def test_flow_voxel_rejects_unknown_arguments():
         O.flow_voxel(x, 3, "upwind", "last")
     with pytest.raises(NotImplementedError):
         O.flow_voxel(x, 3, "nearest", "middle")
+
+
+@pytest.mark.parametrize("scheme", ["upwind", "burgers"])
+def test_flow_voxel_reference_test_cases(scheme):
+    """The reference's own checks of the voxel construction (tests/utils/test_flow_utils.py:52-88), on the oracle: level t0
+    holds the input flow for both t0 locations, a single level is the input (upwind), 60 levels on a 100x200 random flow."""
+    rng = np.random.default_rng(0)
+    flow = torch.from_numpy(rng.uniform(-20, 20, (2, 100, 200)))
+    n_bin = 60
+    assert torch.equal(O.flow_voxel(flow, 1, "upwind", "middle")[0], flow)
+    assert torch.equal(O.flow_voxel(flow, n_bin, scheme, "middle")[n_bin // 2], flow)
+    assert torch.equal(O.flow_voxel(flow, n_bin, scheme, "first")[0], flow)
+    vox = O.flow_voxel(torch.from_numpy(rng.uniform(-1, 1, (2, 20, 30))), 100, scheme, "first")
+    assert vox.shape == (100, 2, 20, 30) and bool(torch.isfinite(vox).all())
