@@ -328,9 +328,11 @@ def run_b200(args) -> None:
             from event_based_optical_flow_b200 import _lib as L
             import ctypes as C
             obj.value_and_grad(flows[0])  # leave a consistent workspace behind
-            obj.plan.set_stage_mask(2)
             stream = torch.cuda.current_stream().cuda_stream
             m = flows[1].contiguous()
+            spec_p = C.byref(obj.spec)
+            ng = grad_buf.numel()
+            # the staged entry points enqueue exactly the kernels of the fused call: vote = K1 alone, grad(pre_zeroed) = K3 alone
 
             def time_kernel(fn, reps=20):
                 out = []
@@ -344,22 +346,24 @@ def run_b200(args) -> None:
                     out.append(a.elapsed_time(b))
                 return float(np.mean(out[3:]))
 
-            k1 = time_kernel(lambda: L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, None, None, None, stream))
-            k3 = time_kernel(lambda: L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), stream))
-            obj.plan.set_stage_mask(7)
-            # in-situ stage times of one eager iteration (L2 flushed before the iteration only): K1+fold | cost | K3
-            spec_p = C.byref(obj.spec)
+            def fold_and_cost():
+                L.call("cmax_objective_fold", obj.plan.handle, obj._ws_ptr, None, stream)
+                L.call("cmax_objective_cost", obj.plan.handle, spec_p, None, obj._ws_ptr, 1, cost_buf.data_ptr(), grad_buf.data_ptr(), ng, stream)
+
+            k1 = time_kernel(lambda: L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, stream))
+            fold_and_cost()
+            k3 = time_kernel(lambda: L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), 1, stream))
+            # in-situ stage times of one eager iteration (L2 flushed before the iteration only): K1 | fold + cost | K3
             stage_ms = np.zeros(3)
             for rep in range(13):
                 flush_l2()
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                fused = C.c_int32(0)
                 e[0].record()
-                L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, None, spec_p, C.byref(fused), stream)
+                L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, stream)
                 e[1].record()
-                L.call("cmax_objective_cost", obj.plan.handle, spec_p, None, obj._ws_ptr, fused.value, 1, cost_buf.data_ptr(), stream)
+                fold_and_cost()
                 e[2].record()
-                L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), stream)
+                L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), 1, stream)
                 e[3].record()
                 torch.cuda.synchronize()
                 if rep >= 3:
@@ -377,8 +381,8 @@ def run_b200(args) -> None:
             dom = max(kernels, key=lambda k: kernels[k]["ms"])
             roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
                     "frac": kernels[dom]["GBps"] / peak, "traffic": traffic_of(dom), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
-                    "kernels": kernels, "stages_in_situ_ms": {"vote(K1+fold)": stage_ms[0], "cost(combine+gq)": stage_ms[1],
-                                                              "grad(memset+K3)": stage_ms[2]}, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
+                    "kernels": kernels, "stages_in_situ_ms": {"vote(K1)": stage_ms[0], "fold+cost(2 image-kernel launches, staged API)": stage_ms[1],
+                                                              "grad(K3)": stage_ms[2]}, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
         else:
             roof = {"bound": "hbm", "kernel": "whole CM iteration (per GPU)", "achieved": step_gbps, "peak": peak, "unit": "GB/s",
                     "frac": step_gbps / peak, "traffic": None, "peak_source": peak_src}
@@ -391,8 +395,9 @@ def run_b200(args) -> None:
                    "sample": f"5 timed + 1 warm-up CM iterations over the full {n}-event config-2 batch, fp32 torch CPU ops"}
 
         clocks = sampler.finish() if sampler else None
-        # K1 vote, fold(+variance+cost), gradient pictures, K3 grad; the eager 3-stage path adds the combine kernel
-        per_step_kernels = 4 if world == 1 else {'peer': 6, 'push': 8, 'nccl': 5}[args.exchange]
+        # K1 vote, image kernel (fold + variance + cost + gradient quads), K3 grad; sharded "peer": + the gradient-exchange
+        # kernel (the IWE exchange lives inside the image kernel); "nccl": K1, fold, cost, K3 (+ 2 NCCL all-reduces)
+        per_step_kernels = 3 if world == 1 else {'peer': 4, 'nccl': 4}[args.exchange]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -402,8 +407,8 @@ def run_b200(args) -> None:
                        "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16), "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
                        "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
-                                       {"nccl": "NCCL all-reduce", "peer": "NVLink peer-memory reads + in-stream barriers",
-                                        "push": "NVLink pushes into per-rank mailboxes + flags (no barrier kernels)"}[args.exchange])
+                                       {"nccl": "NCCL all-reduce",
+                                        "peer": "NVLink peer-memory reads behind in-kernel flags (no collective, no barrier kernel)"}[args.exchange])
                        if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host pinned flow -> device, ContrastObjective.step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
@@ -436,8 +441,8 @@ def main():
     ap.add_argument("--grad-variant", type=int, default=-1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
-    ap.add_argument("--exchange", choices=("nccl", "peer", "push"), default="peer",
-                    help="multi-GPU: NCCL all-reduce, NVLink peer reads behind barriers, or NVLink pushes into mailboxes with flags")
+    ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer",
+                    help="multi-GPU: NCCL all-reduces between the stages, or NVLink peer reads behind flags inside the kernels")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:

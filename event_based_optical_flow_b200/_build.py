@@ -14,8 +14,8 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200.so")
-SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu")
-HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", "cmax_runs.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
+SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_mid.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu")
+HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", "cmax_runs.cuh", "cmax_objective.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared")
 

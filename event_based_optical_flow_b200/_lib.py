@@ -10,6 +10,7 @@ import threading
 
 from . import _build
 
+ABI_VERSION = 2
 MAX_REFS = 4
 MAX_BINS = 64
 MAX_PEERS = 8
@@ -25,6 +26,12 @@ SCHEME = {"upwind": 0, "burgers": 1}
 
 class Ref(C.Structure):
     _fields_ = [("mode", C.c_int32), ("fraction", C.c_float)]
+
+
+class Peers(C.Structure):
+    """cmax_peers: symmetric-memory addresses of every rank's partial IWE stack, partial gradient and flag block."""
+    _fields_ = [("n_peers", C.c_int32), ("rank", C.c_int32), ("iwe", C.c_void_p * MAX_PEERS), ("grad", C.c_void_p * MAX_PEERS),
+                ("flags", C.c_void_p * MAX_PEERS)]
 
 
 class CostSpec(C.Structure):
@@ -67,16 +74,14 @@ _SIGNATURES = {
     "cmax_plan_set_compact": (_i, [_p, _i, C.POINTER(C.c_int32), _p]),
     "cmax_objective_workspace_bytes": (_sz, [_p, C.POINTER(CostSpec)]),
     "cmax_objective_workspace_init": (_i, [_p, _p, _p]),
-    "cmax_objective_vote": (_i, [_p, _i, _p, _p, C.POINTER(_p), C.POINTER(CostSpec), C.POINTER(C.c_int32), _p]),
-    "cmax_objective_cost": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _i, _p, _p]),
-    "cmax_objective_grad": (_i, [_p, _i, _p, _p, _p, _p]),
+    "cmax_objective_vote": (_i, [_p, _i, _p, _p, _p]),
+    "cmax_objective_fold": (_i, [_p, _p, C.POINTER(_p), _p]),
+    "cmax_objective_cost": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _p, _p, _i64, _p]),
+    "cmax_objective_grad": (_i, [_p, _i, _p, _p, _p, _i, _p]),
     "cmax_objective": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, _p, _p, _p]),
     "cmax_objective_iwe_offset": (_sz, [_p]),
     "cmax_objective_full_iwe_offset": (_sz, [_p]),
-    "cmax_objective_reduce_iwe": (_i, [_p, C.POINTER(CostSpec), C.POINTER(_p), _i, _p, _p, _p, C.POINTER(C.c_int32), _p, _p, _p]),
-    "cmax_push": (_i, [_p, _i64, C.POINTER(_p), C.POINTER(_p), _i, _p, _p, _p]),
-    "cmax_objective_cost_after_reduce": (_i, [_p, C.POINTER(CostSpec), _p, _p, _i, _i, _p, _p]),
-    "cmax_reduce_peers": (_i, [C.POINTER(_p), _i, _i64, _p, _p, _p, _p]),
+    "cmax_objective_sharded": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, C.POINTER(Peers), _p, _p, _p]),
     "cmax_combine_cost": (_i, [_p, _i, _i, _i, _p, C.POINTER(_f), _i, _i, _p, _p, _p]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -113,8 +118,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError here = header and library out of sync
             fn.restype = res
             fn.argtypes = args
-        if lib.cmax_abi_version() != 1:
-            raise RuntimeError(f"{path}: ABI version {lib.cmax_abi_version()} != 1")
+        if lib.cmax_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"{path}: ABI version {lib.cmax_abi_version()} != {ABI_VERSION} (stale build: run `python -m event_based_optical_flow_b200._build --force`)")
         _lib = lib
         return lib
 

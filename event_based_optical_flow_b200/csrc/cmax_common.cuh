@@ -38,7 +38,9 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                  \
   } while (0)
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on a B200: 2 dies x 74 SMs).
+// Grids are sized in multiples of it.
+int num_sms();
 
 static inline cudaStream_t as_stream(cmax_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

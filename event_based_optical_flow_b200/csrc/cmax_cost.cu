@@ -118,7 +118,7 @@ __global__ void combine_cost_kernel(const double* __restrict__ stats, CombineDev
 void launch_combine(const double* stats, const CombineDev& cd, cudaStream_t s) { combine_cost_kernel<<<1, 32, 0, s>>>(stats, cd); }
 
 static inline int stat_grid(int64_t n) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((n + kStatBlock - 1) / kStatBlock, kNumSMs * 2));
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + kStatBlock - 1) / kStatBlock, num_sms() * 2));
 }
 
 }  // namespace cmax

@@ -109,35 +109,44 @@ __device__ __forceinline__ bool source_pixel(float x, float y, int H, int W, int
   return (*r >= 0) && (*r < H) && (*c >= 0) && (*c < W) && (x == x) && (y == y);
 }
 
-__global__ void __launch_bounds__(256) validate_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
-                                                       int32_t* __restrict__ status) {
+// One pass over the caller's events: validates the source pixel (status bit 0: outside the image or NaN), notices fractional
+// coordinates (status bit 1: no compact / strip packing), and writes the sort key -- tile id (TILE order: events of a tile
+// keep their time order) or tile id * 1024 + pixel inside the tile (PIXEL order) -- with the identity permutation.  No
+// atomics per event: the per-key counts come from the SORTED keys afterwards (key_first_kernel).  An invalid event gets
+// key 0, so everything enqueued behind this kernel stays in bounds until the host has looked at the status word.
+__global__ void __launch_bounds__(256) keys_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W, int tiles_x,
+                                                   int by_pixel, uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                                                   int32_t* __restrict__ status) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   bool bad = false, frac = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     int r, c;
     const float x = __ldg(ev + i * stride), y = __ldg(ev + i * stride + 1);
-    bad |= !source_pixel(x, y, H, W, &r, &c);
-    frac |= (x != truncf(x)) || (y != truncf(y));  // bit 1: fractional coordinates -> no compact packing
+    const bool ok = source_pixel(x, y, H, W, &r, &c);
+    bad |= !ok;
+    frac |= (x != truncf(x)) || (y != truncf(y));
+    if (keys != nullptr) {
+      uint32_t key = 0u;
+      if (ok) {
+        const uint32_t tile = (uint32_t)((r / kTile) * tiles_x + (c / kTile));
+        key = by_pixel ? (tile * (uint32_t)(kTile * kTile) + (uint32_t)((r % kTile) * kTile + (c % kTile))) : tile;
+      }
+      keys[i] = key;
+      idx[i] = (uint32_t)i;
+    }
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
   if (__any_sync(0xffffffffu, frac) && (threadIdx.x & 31) == 0) atomicOr(status, 2);
 }
 
-// Sort key: tile id (TILE order: events of a tile keep their time order) or tile id * 1024 + pixel inside the tile
-// (PIXEL order).  Also counts events per tile for the chunk list of the privatised kernels.
-__global__ void __launch_bounds__(256) sort_keys_kernel(const float* __restrict__ ev, int64_t n, int stride, int H, int W,
-                                                        int tiles_x, int by_pixel, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ idx, uint32_t* __restrict__ tile_counts,
-                                                        uint32_t* __restrict__ key_counts) {
-  const int64_t step = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-    int r, c;
-    source_pixel(__ldg(ev + i * stride), __ldg(ev + i * stride + 1), H, W, &r, &c);  // validated before
-    const uint32_t tile = (uint32_t)((r / kTile) * tiles_x + (c / kTile));
-    keys[i] = by_pixel ? (tile * (uint32_t)(kTile * kTile) + (uint32_t)((r % kTile) * kTile + (c % kTile))) : tile;
-    idx[i] = (uint32_t)i;
-    atomicAdd(&tile_counts[tile], 1u);
-    if (key_counts != nullptr) atomicAdd(&key_counts[keys[i]], 1u);
+// key_first[k] = index of the first event whose key is >= k (k in [0, n_keys]); events of key k are
+// key_first[k] .. key_first[k+1].  One thread per boundary of the sorted key array fills the (possibly empty) keys in between.
+__global__ void __launch_bounds__(256) key_first_kernel(const uint32_t* __restrict__ sorted_keys, int64_t n, int64_t n_keys,
+                                                        uint32_t* __restrict__ key_first) {
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = j < n ? (int64_t)sorted_keys[j] : n_keys;
+    const int64_t kprev = j > 0 ? (int64_t)sorted_keys[j - 1] : -1;
+    for (int64_t q = kprev + 1; q <= k; ++q) key_first[q] = (uint32_t)j;
   }
 }
 
@@ -186,14 +195,14 @@ __global__ void __launch_bounds__(256) repack_kernel(const float4* __restrict__ 
 //   [32 headers: row << 17 | col << 4 | count][32 x float4: times 0..3 of lane's strip][32 x float4: times 4..7]
 // = 1152 bytes, one TMA bulk copy; both float4 blocks are read with conflict-free LDS.128.  4.5 bytes per event instead
 // of 8, plus the padding (half a strip per occupied pixel on average: ~6 % at 55 events per pixel).
-__global__ void __launch_bounds__(256) strip_counts_kernel(const uint32_t* __restrict__ key_counts, int64_t n_keys,
+__global__ void __launch_bounds__(256) strip_counts_kernel(const uint32_t* __restrict__ key_first, int64_t n_keys,
                                                            uint32_t* __restrict__ key_strips) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_keys; k += (int64_t)gridDim.x * blockDim.x)
-    key_strips[k] = k < n_keys ? (key_counts[k] + kRunE - 1) / kRunE : 0u;
+    key_strips[k] = k < n_keys ? (key_first[k + 1] - key_first[k] + kRunE - 1) / kRunE : 0u;
 }
 
 __global__ void __launch_bounds__(256) pack_strips_kernel(const float4* __restrict__ ev, const uint32_t* __restrict__ sorted_keys, int64_t n,
-                                                          const uint32_t* __restrict__ key_counts, const uint32_t* __restrict__ key_first,
+                                                          const uint32_t* __restrict__ key_first,
                                                           const uint32_t* __restrict__ key_strip0, int H, int W,
                                                           const cmax_time_params_t* __restrict__ tp, int with_dt, int tile_bytes,
                                                           unsigned char* __restrict__ out) {
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(256) pack_strips_kernel(const float4* __restri
     if (slot == 0) {
       int r, c;
       source_pixel(e.x, e.y, H, W, &r, &c);
-      const uint32_t left = key_counts[key] - rank;
+      const uint32_t left = key_first[key + 1] - (uint32_t)j;
       reinterpret_cast<uint32_t*>(tile)[lane] = ((uint32_t)r << 17) | ((uint32_t)c << 4) | (left < (uint32_t)kRunE ? left : (uint32_t)kRunE);
     }
   }
@@ -240,10 +249,10 @@ static int bits_for(uint64_t v) {
 
 struct PlanLayout {
   size_t off_packed;
-  size_t off_params, off_minmax, off_status, off_events, off_keys[2], off_idx[2], off_counts, off_chunks, off_temp, temp_bytes, total;
-  size_t off_kcnt, off_kstr, off_kfirst, off_kstrip0, off_strips, off_scan_temp, scan_temp_bytes;
+  size_t off_params, off_minmax, off_status, off_events, off_keys[2], off_idx[2], off_temp, temp_bytes, total;
+  size_t off_kstr, off_kfirst, off_kstrip0, off_strips, off_scan_temp, scan_temp_bytes;
   int64_t n_keys, strip_capacity;  // strips the region holds (whole warp-tiles)
-  int tiles_x, tiles_y, n_tiles, max_chunks, key_bits;
+  int tiles_x, tiles_y, n_tiles, key_bits;
 };
 
 // Returns false (message set) when the CUB temp-storage query fails, e.g. without a device.
@@ -256,14 +265,11 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
   size_t off = 0;
   L.off_params = off; off = align_up(off + sizeof(cmax_time_params_t), 256);
   L.off_minmax = off; off = align_up(off + 2 * sizeof(float), 256);
-  L.off_status = off; off = align_up(off + sizeof(int32_t), 256);
+  L.off_status = off; off = align_up(off + 2 * sizeof(int32_t), 256);  // [status bits, number of strips]
   L.off_packed = off; off = align_up(off + (size_t)packed_slots(n) * sizeof(float4), 256);
   if (order != CMAX_ORDER_ASIS) {
     L.key_bits = bits_for((uint64_t)L.n_tiles * (order == CMAX_ORDER_PIXEL ? kTile * kTile : 1));
-    L.max_chunks = (int)(n / kChunk) + L.n_tiles + 1;
     L.off_events = off; off = align_up(off + (size_t)n * sizeof(float4), 256);
-    L.off_counts = off; off = align_up(off + (size_t)L.n_tiles * sizeof(uint32_t), 256);
-    L.off_chunks = off; off = align_up(off + (size_t)L.max_chunks * sizeof(Chunk), 256);
     for (int k = 0; k < 2; ++k) {
       L.off_keys[k] = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
       L.off_idx[k] = off; off = align_up(off + (size_t)n * sizeof(uint32_t), 256);
@@ -280,7 +286,7 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
     if (order == CMAX_ORDER_PIXEL) {  // strips (see pack_strips_kernel): allowed to be up to 1.5x the events
       L.n_keys = (int64_t)L.n_tiles * kTile * kTile;
       L.strip_capacity = ((n + n / 2) / kRunE + 31) / 32 * 32 + 32;
-      for (size_t* o : {&L.off_kcnt, &L.off_kstr, &L.off_kfirst, &L.off_kstrip0}) {
+      for (size_t* o : {&L.off_kstr, &L.off_kfirst, &L.off_kstrip0}) {
         *o = off; off = align_up(off + (size_t)(L.n_keys + 1) * sizeof(uint32_t), 256);
       }
       size_t st = 0;
@@ -297,6 +303,34 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
   L.total = off;
   *out = L;
   return true;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = 148;  // B200
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+// (Re)build the packed copy the RUN kernels read (the strip kernels never touch it, so a plan with strips only pays for it
+// when a run variant is selected).
+int ensure_packed(const cmax_plan* plan, cudaStream_t s) {
+  cmax_plan* p = const_cast<cmax_plan*>(plan);
+  if (p->packed_valid || p->n == 0) return CMAX_OK;
+  const int64_t slots = packed_slots(p->n);
+  const int grid = (int)std::min<int64_t>(num_sms() * 8, (slots + 255) / 256);
+  if (p->compact)
+    repack_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p->events), p->n, slots, p->H, p->W, p->d_params, p->packed_has_dt, p->packed);
+  else
+    repack_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(p->events), p->n, slots, p->H, p->W, p->d_params, p->packed_has_dt, p->packed);
+  CMAX_CUDA_CHECK(cudaGetLastError());
+  p->packed_valid = 1;
+  return CMAX_OK;
 }
 
 }  // namespace cmax
@@ -316,7 +350,7 @@ int cmax_time_range(const float* events, int64_t n, int ev_stride, float* d_minm
   cudaStream_t s = as_stream(stream);
   init_minmax_kernel<<<1, 1, 0, s>>>(d_minmax);
   if (n > 0) {
-    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
+    const int grid = (int)std::min<int64_t>(num_sms() * 8, (n + 255) / 256);
     time_range_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, d_minmax);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
@@ -388,109 +422,77 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   p->vote_variant = 2;
   p->grad_variant = 2;
 
+  // Everything below is ENQUEUED first and looked at once: one stream synchronisation per plan.  The kernels behind the
+  // validation are safe on invalid input (an invalid event sorts under key 0), so the host can afford to learn about it last.
   int rc = CMAX_OK;
-  std::vector<uint32_t> h_counts;
-  std::vector<Chunk> h_chunks;
   float h_mm[2] = {t_min, t_max};
-  int32_t h_status = 0;
+  int32_t h_status[2] = {0, 0};  // [status bits, number of strips]
+  const bool try_strips = sort && n > 0 && order == CMAX_ORDER_PIXEL && H < (1 << 13) && W < (1 << 13);
+  uint32_t *kfirst = nullptr, *kstrip0 = nullptr;
+  const uint32_t* sorted_keys = nullptr;
 #define PLAN_CHECK(call)                                      \
   do {                                                        \
     cudaError_t e__ = (call);                                 \
     if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call); goto fail; } \
   } while (0)
 
-  PLAN_CHECK(cudaMemsetAsync(p->d_status, 0, sizeof(int32_t), s));
-  if (n > 0) {
-    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
-    validate_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, p->d_status);
+  PLAN_CHECK(cudaMemsetAsync(p->d_status, 0, 2 * sizeof(int32_t), s));
+  {
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms() * 8, (n + 255) / 256));
+    cub::DoubleBuffer<uint32_t> dk(reinterpret_cast<uint32_t*>(ws + L.off_keys[0]), reinterpret_cast<uint32_t*>(ws + L.off_keys[1]));
+    cub::DoubleBuffer<uint32_t> dv(reinterpret_cast<uint32_t*>(ws + L.off_idx[0]), reinterpret_cast<uint32_t*>(ws + L.off_idx[1]));
+    if (n > 0)
+      keys_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, L.tiles_x, order == CMAX_ORDER_PIXEL, sort ? dk.Current() : nullptr,
+                                       sort ? dv.Current() : nullptr, p->d_status);
+    if (t_min != t_min || t_max != t_max) {  // NaN -> compute from this batch
+      rc = cmax_time_range(events, n, ev_stride, p->d_minmax, stream);
+      if (rc != CMAX_OK) goto fail;
+      PLAN_CHECK(cudaMemcpyAsync(h_mm, p->d_minmax, sizeof(h_mm), cudaMemcpyDeviceToHost, s));
+    } else {
+      PLAN_CHECK(cudaMemcpyAsync(p->d_minmax, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, s));
+    }
+    if (sort && n > 0) {
+      float4* sorted = reinterpret_cast<float4*>(ws + L.off_events);
+      size_t temp = L.temp_bytes + 256;
+      PLAN_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.off_temp, temp, dk, dv, (int)n, 0, L.key_bits, s));  // stable
+      gather_events_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, dv.Current(), sorted);
+      PLAN_CHECK(cudaGetLastError());
+      p->events = reinterpret_cast<const float*>(sorted);
+      p->order = order;
+      sorted_keys = dk.Current();
+      if (try_strips) {
+        uint32_t* kstr = reinterpret_cast<uint32_t*>(ws + L.off_kstr);
+        kfirst = reinterpret_cast<uint32_t*>(ws + L.off_kfirst);
+        kstrip0 = reinterpret_cast<uint32_t*>(ws + L.off_kstrip0);
+        key_first_kernel<<<grid, 256, 0, s>>>(sorted_keys, n, L.n_keys, kfirst);
+        strip_counts_kernel<<<(int)std::min<int64_t>(num_sms() * 4, (L.n_keys + 256) / 256), 256, 0, s>>>(kfirst, L.n_keys, kstr);
+        size_t st = L.scan_temp_bytes + 256;
+        PLAN_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.off_scan_temp, st, kstr, kstrip0, (int)(L.n_keys + 1), s));
+        PLAN_CHECK(cudaMemcpyAsync(p->d_status + 1, kstrip0 + L.n_keys, sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+      }
+    }
   }
-  if (t_min != t_min || t_max != t_max) {  // NaN -> compute from this batch
-    rc = cmax_time_range(events, n, ev_stride, p->d_minmax, stream);
-    if (rc != CMAX_OK) goto fail;
-    PLAN_CHECK(cudaMemcpyAsync(h_mm, p->d_minmax, sizeof(h_mm), cudaMemcpyDeviceToHost, s));
-  } else {
-    PLAN_CHECK(cudaMemcpyAsync(p->d_minmax, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, s));
-  }
-  PLAN_CHECK(cudaMemcpyAsync(&h_status, p->d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  PLAN_CHECK(cudaMemcpyAsync(h_status, p->d_status, sizeof(h_status), cudaMemcpyDeviceToHost, s));
   PLAN_CHECK(cudaStreamSynchronize(s));
-  if (h_status & 1) {
+  if (h_status[0] & 1) {
     set_error("cmax_plan_create: an event's pixel (x=row, y=col) lies outside the %dx%d image (or is NaN); "
               "the reference's torch.gather raises here (src/warp.py:305-307)", H, W);
     rc = CMAX_ERR_SOURCE_OOB;
     goto fail;
   }
-  p->compact_ok = (!(h_status & 2) && H <= 65535 && W <= 65535) ? 1 : 0;
+  p->compact_ok = (!(h_status[0] & 2) && H <= 65535 && W <= 65535) ? 1 : 0;
   p->compact = p->compact_ok;
   p->t_min = h_mm[0];
   p->t_max = h_mm[1];
-
-  if (sort && n > 0) {
-    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + L.off_counts);
-    float4* sorted = reinterpret_cast<float4*>(ws + L.off_events);
-    cub::DoubleBuffer<uint32_t> dk(reinterpret_cast<uint32_t*>(ws + L.off_keys[0]), reinterpret_cast<uint32_t*>(ws + L.off_keys[1]));
-    cub::DoubleBuffer<uint32_t> dv(reinterpret_cast<uint32_t*>(ws + L.off_idx[0]), reinterpret_cast<uint32_t*>(ws + L.off_idx[1]));
-    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (n + 255) / 256);
-    PLAN_CHECK(cudaMemsetAsync(counts, 0, (size_t)L.n_tiles * sizeof(uint32_t), s));
-    const bool try_strips = order == CMAX_ORDER_PIXEL && p->compact_ok && H < (1 << 13) && W < (1 << 13);
-    uint32_t* kcnt = try_strips ? reinterpret_cast<uint32_t*>(ws + L.off_kcnt) : nullptr;
-    if (try_strips) PLAN_CHECK(cudaMemsetAsync(kcnt, 0, (size_t)(L.n_keys + 1) * sizeof(uint32_t), s));
-    sort_keys_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, H, W, L.tiles_x, order == CMAX_ORDER_PIXEL, dk.Current(),
-                                          dv.Current(), counts, kcnt);
-    size_t temp = L.temp_bytes + 256;
-    PLAN_CHECK(cub::DeviceRadixSort::SortPairs(ws + L.off_temp, temp, dk, dv, (int)n, 0, L.key_bits, s));  // stable
-    gather_events_kernel<<<grid, 256, 0, s>>>(events, n, ev_stride, dv.Current(), sorted);
-    PLAN_CHECK(cudaGetLastError());
-    h_counts.resize(L.n_tiles);
-    PLAN_CHECK(cudaMemcpyAsync(h_counts.data(), counts, (size_t)L.n_tiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    PLAN_CHECK(cudaStreamSynchronize(s));
-    uint32_t begin = 0;
-    for (int t = 0; t < L.n_tiles; ++t) {
-      for (uint32_t b = 0; b < h_counts[t]; b += kChunk) {
-        Chunk c;
-        c.tile = t;
-        c.begin = (int32_t)(begin + b);
-        c.count = (int32_t)std::min<uint32_t>(kChunk, h_counts[t] - b);
-        c.pad_ = 0;
-        h_chunks.push_back(c);
-      }
-      begin += h_counts[t];
-    }
-    if ((int)h_chunks.size() > L.max_chunks || begin != (uint32_t)n) {
-      set_error("cmax_plan_create: internal error, %zu chunks (max %d), %u of %lld events binned", h_chunks.size(),
-                L.max_chunks, begin, (long long)n);
-      rc = CMAX_ERR_WORKSPACE;
-      goto fail;
-    }
-    Chunk* d_chunks = reinterpret_cast<Chunk*>(ws + L.off_chunks);
-    PLAN_CHECK(cudaMemcpyAsync(d_chunks, h_chunks.data(), h_chunks.size() * sizeof(Chunk), cudaMemcpyHostToDevice, s));
-    PLAN_CHECK(cudaStreamSynchronize(s));
-    p->events = reinterpret_cast<const float*>(sorted);
-    p->chunks = d_chunks;
-    p->n_chunks = (int)h_chunks.size();
-    p->order = order;
-    if (try_strips) {
-      uint32_t* kstr = reinterpret_cast<uint32_t*>(ws + L.off_kstr);
-      uint32_t* kfirst = reinterpret_cast<uint32_t*>(ws + L.off_kfirst);
-      uint32_t* kstrip0 = reinterpret_cast<uint32_t*>(ws + L.off_kstrip0);
-      strip_counts_kernel<<<(int)std::min<int64_t>(kNumSMs * 4, (L.n_keys + 256) / 256), 256, 0, s>>>(kcnt, L.n_keys, kstr);
-      size_t st = L.scan_temp_bytes + 256;
-      PLAN_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.off_scan_temp, st, kcnt, kfirst, (int)(L.n_keys + 1), s));
-      st = L.scan_temp_bytes + 256;
-      PLAN_CHECK(cub::DeviceScan::ExclusiveSum(ws + L.off_scan_temp, st, kstr, kstrip0, (int)(L.n_keys + 1), s));
-      uint32_t h_strips = 0;
-      PLAN_CHECK(cudaMemcpyAsync(&h_strips, kstrip0 + L.n_keys, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-      PLAN_CHECK(cudaStreamSynchronize(s));
-      if ((int64_t)h_strips <= L.strip_capacity - 32) {  // dense enough: the padding stays below 50 %
-        p->strips = ws + L.off_strips;
-        p->n_strips = (int64_t)h_strips;
-        p->sorted_keys = dk.Current();
-        p->key_counts = kcnt;
-        p->key_first = kfirst;
-        p->key_strip0 = kstrip0;
-        p->vote_variant = 5;
-        p->grad_variant = 5;
-      }
-    }
+  // strips: integer coordinates, and dense enough that padding every pixel's run to whole strips stays below 50 %
+  if (try_strips && p->compact_ok && (int64_t)(uint32_t)h_status[1] <= L.strip_capacity - 32) {
+    p->strips = ws + L.off_strips;
+    p->n_strips = (int64_t)(uint32_t)h_status[1];
+    p->sorted_keys = sorted_keys;
+    p->key_first = kfirst;
+    p->key_strip0 = kstrip0;
+    p->vote_variant = 5;
+    p->grad_variant = 5;
   }
 #undef PLAN_CHECK
   {
@@ -533,21 +535,11 @@ int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant)
 
 int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cmax_stream_t stream) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_compact: plan is NULL");
+  (void)stream;
   const int want = (enable && plan->compact_ok) ? 1 : 0;
   if (want != plan->compact) {
     plan->compact = want;
-    // re-pack with the reference times already on the device
-    if (plan->n > 0) {
-      const int64_t slots = packed_slots(plan->n);
-      const int grid = (int)std::min<int64_t>(kNumSMs * 8, (slots + 255) / 256);
-      if (want)
-        repack_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
-                                                                  plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
-      else
-        repack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
-                                                                   plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
-      CMAX_CUDA_CHECK(cudaGetLastError());
-    }
+    plan->packed_valid = 0;  // re-packed on demand (ensure_packed)
   }
   if (h_compact) *h_compact = plan->compact;
   return CMAX_OK;
@@ -556,6 +548,10 @@ int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cma
 int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask) {
   CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_stage_mask: plan is NULL");
   CMAX_REQUIRE(mask >= 1 && mask <= 7, "cmax_plan_set_stage_mask: mask must be in [1,7]");
+#ifndef CMAX_MEASURE
+  CMAX_REQUIRE(mask == 7, "cmax_plan_set_stage_mask: this is a release build; partial stage masks (timing-only results) need a library "
+                          "built with -DCMAX_MEASURE");
+#endif
   plan->stage_mask = mask;
   return CMAX_OK;
 }
@@ -567,24 +563,16 @@ int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int
   plan->n_ref = n_ref;
   plan->n_bins = n_bins;
   plan->packed_has_dt = (n_ref == 1) ? 1 : 0;
-  if (plan->n > 0) {
-    const int64_t slots = packed_slots(plan->n);
-    const int grid = (int)std::min<int64_t>(kNumSMs * 8, (slots + 255) / 256);
-    if (plan->compact)
-      repack_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
-                                                                plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
-    else
-      repack_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->n, slots, plan->H,
-                                                                 plan->W, plan->d_params, plan->packed_has_dt, plan->packed);
-    if (plan->strips != nullptr) {
-      const int64_t tiles = (plan->n_strips + 31) / 32;
-      plan->strip_tile_bytes = kStripTileBytes + (n_bins > 0 ? n_ref * kStripBinBytes : 0);
-      CMAX_CUDA_CHECK(cudaMemsetAsync(plan->strips, 0, (size_t)tiles * plan->strip_tile_bytes, as_stream(stream)));
-      pack_strips_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->sorted_keys, plan->n,
-                                                               plan->key_counts, plan->key_first, plan->key_strip0, plan->H, plan->W,
-                                                               plan->d_params, plan->packed_has_dt, plan->strip_tile_bytes,
-                                                               static_cast<unsigned char*>(plan->strips));
-    }
+  plan->packed_valid = 0;
+  if (plan->n > 0 && plan->strips != nullptr) {
+    const int grid = (int)std::min<int64_t>(num_sms() * 8, (plan->n + 255) / 256);
+    const int64_t tiles = (plan->n_strips + 31) / 32;
+    plan->strip_tile_bytes = kStripTileBytes + (n_bins > 0 ? n_ref * kStripBinBytes : 0);
+    CMAX_CUDA_CHECK(cudaMemsetAsync(plan->strips, 0, (size_t)tiles * plan->strip_tile_bytes, as_stream(stream)));
+    pack_strips_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(plan->events), plan->sorted_keys, plan->n,
+                                                             plan->key_first, plan->key_strip0, plan->H, plan->W, plan->d_params,
+                                                             plan->packed_has_dt, plan->strip_tile_bytes,
+                                                             static_cast<unsigned char*>(plan->strips));
     CMAX_CUDA_CHECK(cudaGetLastError());
   }
   return CMAX_OK;

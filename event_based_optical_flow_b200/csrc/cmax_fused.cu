@@ -14,41 +14,9 @@
 //                                            corners, so K3 gathers ONE float4 per event per reference time
 #include <stdlib.h>
 
-#include "cmax_runs.cuh"
-#include "cmax_stats.cuh"
+#include "cmax_objective.cuh"
 
 namespace cmax {
-
-// ------------------------------------------------------------------------------------------------ workspace
-struct ObjLayout {
-  size_t off_acc, off_iwe, off_iwe_full, off_blur, off_statacc, off_stats, off_affine, off_misc, off_gxy, off_g, off_g2, off_gq, total;
-  int64_t cells, HW;
-};
-
-static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-
-static ObjLayout obj_layout(int Hp, int Wp) {
-  ObjLayout L;
-  const int R = CMAX_MAX_REFS;
-  L.cells = (int64_t)(Hp + 1) * (Wp + 1) + 1;  // + one cell no pixel reads: its gradient quad is all zero (the strip K3's 'outside' cell)
-  L.HW = (int64_t)Hp * Wp;
-  size_t off = 0;
-  L.off_acc = off;     off = align256(off + (size_t)R * L.cells * sizeof(float4));
-  L.off_iwe = off;     off = align256(off + (size_t)R * L.HW * sizeof(float));
-  L.off_iwe_full = off; off = align256(off + (size_t)R * L.HW * sizeof(float));  // peer exchange: the summed IWE (off_iwe stays the partial peers read)
-  L.off_blur = off;    off = align256(off + (size_t)R * L.HW * sizeof(float));
-  L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
-  L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
-  L.off_misc = off;    off = align256(off + 2 * sizeof(double));  // 2-dof fp64 staging
-  // [StatAcc block][Sobel pair] is exactly the workspace layout cmax_image_stats expects (cmax_cost.cu)
-  L.off_statacc = off; off = align256(off + (size_t)R * sizeof(StatAcc));
-  L.off_gxy = off;     off = align256(off + (size_t)R * 2 * L.HW * sizeof(float));
-  L.off_g = off;       off = align256(off + (size_t)R * L.HW * sizeof(float));
-  L.off_g2 = off;      off = align256(off + (size_t)R * L.HW * sizeof(float));
-  L.off_gq = off;      off = align256(off + (size_t)R * L.cells * sizeof(float4));
-  L.total = off;
-  return L;
-}
 
 // One event, one reference time: (x', y', dt, bin).        src/warp.py:254-258, 306-307, 346-357, 507-514
 template <int MODEL>
@@ -120,91 +88,6 @@ __global__ void __launch_bounds__(256) vote_fused_kernel(FusedArgs a, float4* __
       }
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------ fold
-// acc -> IWE.  Every scalar component of every accumulator cell has exactly ONE reader (pixel (r,c) reads .x of cell
-// (r,c), .y of (r-1,c), .z of (r,c-1), .w of (r-1,c-1)), so the reader also zeroes it: the accumulators are clean again
-// for the next CM iteration and no memset is ever enqueued (components no pixel reads only ever collect votes of
-// out-of-image corners and are never looked at).  Optionally the variance sums of the crop in the same pass (fp64
-// accumulators), and optionally (single-GPU fused path) the last CTA to finish also evaluates the scalar cost, so that
-// fold + statistics + combine are ONE launch.
-__global__ void __launch_bounds__(kStatBlock) fold_kernel(float4* __restrict__ acc, float* __restrict__ iwe, int Hp, int Wp,
-                                                          int64_t cells, int want_var, int omit, StatAcc* __restrict__ sacc,
-                                                          double* __restrict__ stats, int want_combine, CombineDev cd,
-                                                          unsigned int* __restrict__ ctas_done) {
-  __shared__ double red[kStatBlock / 32];
-  __shared__ bool all_done;
-  pdl_trigger();
-  pdl_wait();  // K1's reductions are complete and visible
-  const int img = blockIdx.y;
-  const int64_t HW = (int64_t)Hp * Wp;
-  float* A = reinterpret_cast<float*>(acc + img * cells);
-  const int Wc = Wp + 1;
-  double s = 0.0, q = 0.0;
-  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(p / Wp), c = (int)(p % Wp);
-    const int64_t k = (int64_t)(r + 1) * Wc + (c + 1);
-    float* a00 = A + 4 * k;                  // .x of cell (r, c)
-    float* a10 = A + 4 * (k - Wc) + 1;       // .y of cell (r-1, c)
-    float* a01 = A + 4 * (k - 1) + 2;        // .z of cell (r, c-1)
-    float* a11 = A + 4 * (k - Wc - 1) + 3;   // .w of cell (r-1, c-1)
-    const float v = ((*a00 + *a10) + *a01) + *a11;
-    *a00 = 0.f;
-    *a10 = 0.f;
-    *a01 = 0.f;
-    *a11 = 0.f;
-    iwe[img * HW + p] = v;
-    if (want_var && (!omit || (r >= 1 && r <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
-      s += (double)v;
-      q += (double)v * (double)v;
-    }
-  }
-  if (want_var) {
-    const int64_t M = omit ? (int64_t)(Hp - 2) * (Wp - 2) : HW;
-    variance_commit(s, q, M, gridDim.x, &sacc[img], stats + 4 * img, red);
-    if (want_combine) {
-      if (threadIdx.x == 0) {
-        __threadfence();
-        all_done = (atomicAdd(ctas_done, 1u) == gridDim.x * gridDim.y - 1);
-      }
-      __syncthreads();
-      if (all_done && threadIdx.x == 0) {
-        __threadfence();
-        combine_eval(stats, cd);
-      }
-    }
-  } else if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 64) {
-    // statistics not fused here: leave the 256-byte statistics block clean for whoever accumulates next
-    // (the peer IWE reduction of the multi-GPU path), instead of a memset node
-    reinterpret_cast<unsigned int*>(sacc)[threadIdx.x] = 0u;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ gq
-// Per-corner gradient pictures.  G[p] = a * (src[p] - m) (inside the crop when `crop`, else everywhere), gathered at
-// the four corners of every accumulator cell with the per-corner in-bounds masks.  Also zeroes `zero` (the motion
-// gradient K3 is about to accumulate into) so that no memset is enqueued for it.
-__global__ void __launch_bounds__(256) gq_build_kernel(const float* __restrict__ src, const float* __restrict__ affine, int Hp, int Wp,
-                                                       int64_t cells, int crop, float4* __restrict__ gq, float* __restrict__ zero,
-                                                       int64_t n_zero) {
-  pdl_trigger();  // K3 may start prefetching its event tiles now
-  pdl_wait();     // the IWE / statistics / affine pair of the predecessor are complete
-  const int img = blockIdx.y;
-  const int64_t HW = (int64_t)Hp * Wp;
-  const float* I = src + img * HW;
-  const float a = affine[2 * img], m = affine[2 * img + 1];
-  const int Wc = Wp + 1;
-  const int lo = crop ? 1 : 0, hi_r = crop ? Hp - 2 : Hp - 1, hi_c = crop ? Wp - 2 : Wp - 1;
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < cells; k += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(k / Wc) - 1, c = (int)(k % Wc) - 1;
-    auto g = [&](int rr, int cc) -> float {
-      return (rr >= lo && rr <= hi_r && cc >= lo && cc <= hi_c) ? a * (__ldg(I + (int64_t)rr * Wp + cc) - m) : 0.f;
-    };
-    gq[img * cells + k] = make_float4(g(r, c), g(r + 1, c), g(r, c + 1), g(r + 1, c + 1));
-  }
-  if (zero != nullptr && img == 0)
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_zero; k += (int64_t)gridDim.x * blockDim.x) zero[k] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -357,13 +240,8 @@ __device__ __forceinline__ void vote_step(float x, float y, float tz, int key, V
       st.key = key;
       st.src = PackedEv<COMPACT>::src(key, a.W);
       if (MODEL == CMAX_MOTION_DENSE) {
-        if (a.dbg & 2) {
-          st.f0 = 3.0f + (float)(st.src & 7);
-          st.f1 = -2.0f;
-        } else {
-          st.f0 = __ldg(a.motion + st.src);
-          st.f1 = __ldg(a.motion + HW + st.src);
-        }
+        st.f0 = __ldg(a.motion + st.src);
+        st.f1 = __ldg(a.motion + HW + st.src);
       }
     }
   }
@@ -377,7 +255,7 @@ __device__ __forceinline__ void vote_step(float x, float y, float tz, int key, V
     vote_weights(v, w);
     const int c = vote_cell(v, a.Hp, a.Wp);
     const bool same = c == st.cell[r];
-    red_add_v4_if(!same && st.cell[r] >= 0 && !(a.dbg & 1), acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
+    red_add_v4_if(!same && st.cell[r] >= 0, acc + r * a.cells + max(st.cell[r], 0), st.w0[r], st.w1[r], st.w2[r], st.w3[r]);
     st.cell[r] = c;
     const float keep = same ? 1.0f : 0.0f;  // acc * 1 + w and acc * 0 + w are exact: one select instead of four
     const f32x2 keep2 = pk2(keep, keep);
@@ -798,176 +676,6 @@ __global__ void __launch_bounds__(kRunThreads) grad_runs_kernel(FusedArgs a, con
   }
 }
 
-// 2-dof gradient: the CTAs accumulate in two doubles (off_misc), narrowed here.
-__global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __restrict__ out) {
-  if (threadIdx.x < 2) out[threadIdx.x] = (float)acc2[threadIdx.x];
-}
-
-// ------------------------------------------------------------------------------------------------ peer reductions
-// Multi-GPU exchange over NVLink peer memory (the workspaces live in symmetric memory, one process per GPU): instead
-// of an NCCL all-reduce followed by the statistics kernels, ONE kernel on every rank reads all ranks' partial IWEs
-// (P2P loads, summed in rank order so every rank gets the bit-identical image), writes the full IWE and -- exactly like
-// the single-GPU fold -- accumulates the variance sums and lets its last CTA evaluate the scalar cost.
-struct PeerPtrs {
-  const float* p[CMAX_MAX_PEERS];
-  int n;
-};
-
-// ---- push exchange: flags instead of barrier kernels.  Every rank owns a MAILBOX in symmetric memory: one slot per
-// source rank and one 32-bit flag per source rank.  A producer (push_kernel) stores its partial result into its slot of
-// EVERY rank's mailbox (posted NVLink stores, no round trip), fences at system scope, and its last CTA then stores the new
-// epoch into its flag on every rank.  A consumer kernel starts by waiting until all flags of its own mailbox carry the
-// current epoch and then reads only LOCAL memory.  Two mailboxes alternate (IWE, gradient), which is what makes reuse
-// safe without a barrier: a rank can only start overwriting its IWE slots for evaluation e+1 after it has seen every
-// peer's gradient flag of evaluation e, and a peer raises that flag (stream order) after its IWE reduction of e.
-struct PushPtrs {
-  float* slot[CMAX_MAX_PEERS];
-  uint32_t* flag[CMAX_MAX_PEERS];
-  int n;
-};
-
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Block until flags[0..n) have all reached *epoch (called by every CTA of a consumer kernel).  A peer that never
-// arrives (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which surfaces as a CUDA error.
-__device__ __forceinline__ void wait_flags(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch, int n) {
-  if (flags == nullptr) return;
-  if ((int)threadIdx.x < n) {
-    const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(epoch);
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - e) < 0) {
-      if (clock64() - t0 > 8000000000ll) __trap();
-    }
-  }
-  __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) push_kernel(const float* __restrict__ src, int64_t n, PushPtrs dst, uint32_t* __restrict__ epoch,
-                                                   uint32_t* __restrict__ counter) {
-  __shared__ bool last;
-  if ((n & 3) == 0) {  // (slots and sources are 256-byte aligned)
-    const int64_t n4 = n >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-      const float4 v = reinterpret_cast<const float4*>(src)[i];
-      for (int q = 0; q < dst.n; ++q) reinterpret_cast<float4*>(dst.slot[q])[i] = v;
-    }
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      const float v = src[i];
-      for (int q = 0; q < dst.n; ++q) dst.slot[q][i] = v;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // one system-scope fence per CTA (fences are cumulative: the stores of the whole CTA, ordered before this thread by
-    // the barrier, are visible system-wide before the CTA is counted); a fence per thread costs ~20 us per launch
-    __threadfence_system();
-    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence_system();
-    const uint32_t e = *epoch + 1u;
-    *epoch = e;
-    *counter = 0u;
-    for (int q = 0; q < dst.n; ++q) st_release_sys(dst.flag[q], e);
-  }
-}
-
-__global__ void wait_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch, int n) { wait_flags(flags, epoch, n); }
-
-__global__ void __launch_bounds__(kStatBlock) peer_iwe_kernel(PeerPtrs peers, float* __restrict__ iwe, int Hp, int Wp, int want_var, int omit,
-                                                              StatAcc* __restrict__ sacc, double* __restrict__ stats, int want_combine,
-                                                              CombineDev cd, unsigned int* __restrict__ ctas_done,
-                                                              const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch) {
-  __shared__ double red[kStatBlock / 32];
-  __shared__ bool all_done;
-  wait_flags(flags, epoch, peers.n);  // push exchange: every rank's partial image has landed in this rank's mailbox
-  const int img = blockIdx.y;
-  const int64_t HW = (int64_t)Hp * Wp;
-  double s = 0.0, q = 0.0;
-  auto account = [&](int64_t p, float v) {
-    const int rr = (int)(p / Wp), c = (int)(p % Wp);
-    if (want_var && (!omit || (rr >= 1 && rr <= Hp - 2 && c >= 1 && c <= Wp - 2))) {
-      s += (double)v;
-      q += (double)v * (double)v;
-    }
-  };
-  if ((HW & 3) == 0) {
-    // 16-byte loads, all ranks' loads of a thread in flight together: one NVLink round trip per thread instead of 4 n
-    for (int64_t p4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p4 < (HW >> 2); p4 += (int64_t)gridDim.x * blockDim.x) {
-      float4 part[CMAX_MAX_PEERS];
-#pragma unroll
-      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-        if (r < peers.n) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.p[r] + img * HW) + p4);  // L2-coherent: written by another GPU
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-        if (r < peers.n) {  // rank order: every rank computes the bit-identical sum
-          v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
-        }
-      reinterpret_cast<float4*>(iwe + img * HW)[p4] = v;
-      account(4 * p4, v.x); account(4 * p4 + 1, v.y); account(4 * p4 + 2, v.z); account(4 * p4 + 3, v.w);
-    }
-  } else {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
-      float v = 0.f;
-      for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + img * HW + p);
-      iwe[img * HW + p] = v;
-      account(p, v);
-    }
-  }
-  if (want_var) {
-    const int64_t M = omit ? (int64_t)(Hp - 2) * (Wp - 2) : HW;
-    variance_commit(s, q, M, gridDim.x, &sacc[img], stats + 4 * img, red);
-    if (want_combine) {
-      if (threadIdx.x == 0) {
-        __threadfence();
-        all_done = (atomicAdd(ctas_done, 1u) == gridDim.x * gridDim.y - 1);
-      }
-      __syncthreads();
-      if (all_done && threadIdx.x == 0) {
-        __threadfence();
-        combine_eval(stats, cd);
-      }
-    }
-  }
-}
-
-// out[i] = sum over ranks of peers[r][i], rank order (the motion-gradient exchange)
-__global__ void __launch_bounds__(256) peer_sum_kernel(PeerPtrs peers, int64_t n, float* __restrict__ out, const uint32_t* __restrict__ flags,
-                                                       const uint32_t* __restrict__ epoch) {
-  wait_flags(flags, epoch, peers.n);
-  if ((n & 3) == 0) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
-      float4 part[CMAX_MAX_PEERS];
-#pragma unroll
-      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-        if (r < peers.n) part[r] = __ldcg(reinterpret_cast<const float4*>(peers.p[r]) + i);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-        if (r < peers.n) {
-          v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
-        }
-      reinterpret_cast<float4*>(out)[i] = v;
-    }
-  } else {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-      float v = 0.f;
-      for (int r = 0; r < peers.n; ++r) v += __ldcg(peers.p[r] + i);
-      out[i] = v;
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ dispatch
 template <int MODEL, int NREF, bool COMPACT>
 static void launch_vote_runs(int variant, cudaStream_t s, const FusedArgs& a, float4* acc) {
@@ -1042,13 +750,10 @@ static void launch_grad_m(int n_ref, int gvar, int grid, cudaStream_t s, const F
 
 static inline int event_grid(int64_t n, int per_sm) {
   const int64_t want = (n + 255) / 256;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * per_sm));
-}
-static inline int image_grid(int64_t n) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 4));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * per_sm));
 }
 
-static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
+FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   FusedArgs a;
   a.ev = reinterpret_cast<const float4*>(p->events);
   a.packed = p->packed;
@@ -1062,361 +767,23 @@ static FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.n_strips = p->n_strips;
   a.strip_tile_bytes = p->strip_tile_bytes;
   a.zero256 = nullptr;
-  {
-    static int dbg = -1;
-    if (dbg < 0) {
-      const char* e = getenv("CMAX_DEBUG");
-      dbg = e ? atoi(e) : 0;
-    }
-    a.dbg = dbg;
-  }
   return a;
 }
 
-static int check_model(const char* fn, const cmax_plan* p, int model) {
-  CMAX_REQUIRE(p != nullptr, "%s: plan is NULL", fn);
-  CMAX_REQUIRE(model == CMAX_MOTION_DENSE || model == CMAX_MOTION_VOXEL || model == CMAX_MOTION_2DOF,
-               "%s: motion model %d not supported", fn, model);
-  CMAX_REQUIRE(model != CMAX_MOTION_VOXEL || p->n_bins >= 1, "%s: dense-flow-voxel needs cmax_plan_set_refs(..., n_bins >= 1)", fn);
-  return CMAX_OK;
+void launch_vote_any(const cmax_plan* p, int motion_model, cudaStream_t s, const FusedArgs& a, float4* acc, float* iwe) {
+  const int grid = event_grid(p->n, 8);
+  if (motion_model == CMAX_MOTION_DENSE) launch_vote_m<CMAX_MOTION_DENSE>(p->n_ref, p->vote_variant, grid, s, a, acc, iwe);
+  else if (motion_model == CMAX_MOTION_VOXEL) launch_vote_m<CMAX_MOTION_VOXEL>(p->n_ref, p->vote_variant, grid, s, a, acc, iwe);
+  else launch_vote_m<CMAX_MOTION_2DOF>(p->n_ref, p->vote_variant, grid, s, a, acc, iwe);
 }
 
-static bool can_fuse_stats(const cmax_cost_spec* spec) {
-  return spec != nullptr && spec->stat == CMAX_STAT_VARIANCE && !(spec->sigma > 0.f);
-}
-
-static int check_spec(const char* fn, const cmax_cost_spec* spec, int n_ref) {
-  CMAX_REQUIRE(spec != nullptr, "%s: spec is NULL", fn);
-  CMAX_REQUIRE(spec->stat == CMAX_STAT_VARIANCE || spec->stat == CMAX_STAT_GRADMAG, "%s: unknown statistic %d", fn, spec->stat);
-  CMAX_REQUIRE(spec->form >= CMAX_COST_PLAIN && spec->form <= CMAX_COST_MULTIFOCAL, "%s: unknown cost form %d", fn, spec->form);
-  CMAX_REQUIRE(spec->direction_sign == 1 || spec->direction_sign == -1, "%s: direction_sign must be +1 or -1", fn);
-  CMAX_REQUIRE(spec->form != CMAX_COST_PLAIN || n_ref == 1, "%s: a plain cost takes exactly one reference time (plan has %d)", fn, n_ref);
-  CMAX_REQUIRE(spec->form != CMAX_COST_NORMALIZED || n_ref == 1, "%s: a normalised cost takes exactly one reference time (plan has %d)", fn, n_ref);
-  CMAX_REQUIRE(!(spec->sigma < 0.f), "%s: sigma must be >= 0", fn);
-  return CMAX_OK;
-}
-
-// ------------------------------------------------------------------------------------------------ stages
-struct Ws {
-  float4* acc; float* iwe; float* iwe_full; float* blur; StatAcc* sacc; double* stats; float* affine; unsigned int* ctas_done;
-  float* G; float* G2; float4* gq; char* stats_ws; double* acc2;
-};
-
-static Ws carve(void* workspace, const ObjLayout& L) {
-  char* ws = static_cast<char*>(workspace);
-  Ws w;
-  w.acc = reinterpret_cast<float4*>(ws + L.off_acc);
-  w.iwe = reinterpret_cast<float*>(ws + L.off_iwe);
-  w.iwe_full = reinterpret_cast<float*>(ws + L.off_iwe_full);
-  w.blur = reinterpret_cast<float*>(ws + L.off_blur);
-  w.sacc = reinterpret_cast<StatAcc*>(ws + L.off_statacc);
-  w.stats = reinterpret_cast<double*>(ws + L.off_stats);
-  w.affine = reinterpret_cast<float*>(ws + L.off_affine);
-  w.ctas_done = reinterpret_cast<unsigned int*>(ws + L.off_statacc + 192);  // inside the 256-byte StatAcc block
-  w.G = reinterpret_cast<float*>(ws + L.off_g);
-  w.G2 = reinterpret_cast<float*>(ws + L.off_g2);
-  w.gq = reinterpret_cast<float4*>(ws + L.off_gq);
-  w.stats_ws = ws + L.off_statacc;  // [StatAcc block][Sobel pair], the layout cmax_image_stats expects
-  w.acc2 = reinterpret_cast<double*>(ws + L.off_misc);  // 2-dof fp64 staging
-  return w;
-}
-
-static inline size_t motion_floats(const cmax_plan* p, int motion_model) {
-  const size_t HW = (size_t)p->H * p->W;
-  if (motion_model == CMAX_MOTION_DENSE) return 2 * HW;
-  if (motion_model == CMAX_MOTION_VOXEL) return 2 * (size_t)p->n_bins * HW;
-  return 2;
-}
-
-// Stage 1.  `fused_combine` (may be NULL): when the statistics can be fused into the fold, also evaluate the scalar
-// cost in the fold's last CTA (single-GPU convenience path).
-static int vote_stage(const cmax_plan* p, int motion_model, const float* motion, void* workspace, const cmax_cost_spec* fuse_spec,
-                      const CombineDev* fused_combine, int32_t* stats_fused, cudaStream_t s) {
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  const int n_ref = p->n_ref;
-  FusedArgs a = fused_args(p, motion);
-  const int variant = p->vote_variant;
-  const bool fuse = can_fuse_stats(fuse_spec) && variant != 1;
-  const int mask = p->stage_mask;
-  static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 192, "StatAcc block and the CTA counter share 256 bytes");
-  // the 256-byte statistics block is cleared by K1's first CTA when there is one (variant 2), else by a memset
-  const bool k1_clears = fuse && variant >= 2 && p->n > 0 && (mask & 2);
-  if (k1_clears) a.zero256 = reinterpret_cast<unsigned int*>(w.sacc);
-  if (mask & 1) {
-    // the per-corner accumulators are left clean by the fold (see fold_kernel) and by cmax_objective_workspace_init
-    if (variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(w.iwe, 0, (size_t)n_ref * L.HW * sizeof(float), s));
-    if (fuse && !k1_clears) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
-  }
-  if (p->n > 0 && (mask & 2)) {
-    const int grid = event_grid(p->n, 8);
-    if (motion_model == CMAX_MOTION_DENSE) launch_vote_m<CMAX_MOTION_DENSE>(n_ref, variant, grid, s, a, w.acc, w.iwe);
-    else if (motion_model == CMAX_MOTION_VOXEL) launch_vote_m<CMAX_MOTION_VOXEL>(n_ref, variant, grid, s, a, w.acc, w.iwe);
-    else launch_vote_m<CMAX_MOTION_2DOF>(n_ref, variant, grid, s, a, w.acc, w.iwe);
-  }
-  if (variant != 1 && (mask & 4)) {
-    dim3 grid((unsigned)std::min<int64_t>((L.HW + kStatBlock - 1) / kStatBlock, kNumSMs * 4), n_ref);
-    CombineDev cd;
-    memset(&cd, 0, sizeof(cd));
-    if (fuse && fused_combine) cd = *fused_combine;
-    launch_k(pdl_enabled(), fold_kernel, grid, dim3(kStatBlock), s, w.acc, w.iwe, p->Hp, p->Wp, L.cells, fuse ? 1 : 0,
-             fuse ? fuse_spec->omit_boundary : 0, w.sacc, w.stats, (fuse && fused_combine) ? 1 : 0, cd, w.ctas_done);
-  }
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  if (stats_fused) *stats_fused = fuse ? 1 : 0;
-  return CMAX_OK;
-}
-
-static CombineDev combine_for(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, double* d_cost, const Ws& w) {
-  const bool explicit_grad = spec->sigma > 0.f || spec->stat == CMAX_STAT_GRADMAG;
-  return make_combine(p->n_ref, spec->stat, spec->form, spec->direction_sign, explicit_grad ? 1 : 0, spec->weights, d_orig_stat, d_cost,
-                      w.affine);
-}
-
-// Stage 2.  combined != 0: the scalar combination already ran inside the fold (cmax_objective's fast path).
-// zero_grad (may be NULL): motion-gradient buffer to clear inside the gradient-picture kernel.
-static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int stats_fused,
-                      int combined, int want_grad, double* d_cost, float* zero_grad, size_t n_zero, cmax_stream_t stream,
-                      bool use_full = false) {
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  cudaStream_t s = as_stream(stream);
-  const int n_ref = p->n_ref;
-  const bool blurred = spec->sigma > 0.f;
-  const float* img = use_full ? w.iwe_full : w.iwe;
-  int rc;
-  if (!(p->stage_mask & 4)) return CMAX_OK;
-  if (blurred) {
-    rc = cmax_blur3(img, w.blur, n_ref, p->Hp, p->Wp, spec->sigma, 0, stream);
-    if (rc) return rc;
-    img = w.blur;
-  }
-  // variance without blur needs no explicit gradient image: dL/dIWE is affine in the IWE
-  const bool explicit_grad = blurred || spec->stat == CMAX_STAT_GRADMAG;
-  if (!stats_fused) {
-    static_assert(sizeof(StatAcc) * CMAX_MAX_REFS <= 256, "StatAcc block must fit the 256 bytes before the Sobel pair");
-    rc = cmax_image_stats(img, n_ref, p->Hp, p->Wp, spec->stat, spec->omit_boundary, w.stats, (want_grad && explicit_grad) ? w.G : nullptr,
-                          w.stats_ws, stream);
-    if (rc) return rc;
-  }
-  if (!combined) launch_combine(w.stats, combine_for(p, spec, d_orig_stat, d_cost, w), s);
-  if (want_grad) {
-    const float* gsrc = img;
-    int crop = spec->omit_boundary ? 1 : 0;
-    if (explicit_grad) {
-      gsrc = w.G;
-      crop = 0;
-      if (blurred) {
-        rc = cmax_blur3(w.G, w.G2, n_ref, p->Hp, p->Wp, spec->sigma, 1, stream);
-        if (rc) return rc;
-        gsrc = w.G2;
-      }
-    }
-    dim3 grid((unsigned)image_grid(L.cells), n_ref);
-    launch_k(pdl_enabled(), gq_build_kernel, grid, dim3(256), s, gsrc, (const float*)w.affine, p->Hp, p->Wp, L.cells, crop, w.gq, zero_grad,
-             (int64_t)n_zero);
-  }
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  return CMAX_OK;
-}
-
-// Stage 3.  pre_zeroed: grad_motion was cleared by stage 2.
-static int grad_stage(const cmax_plan* p, int motion_model, const float* motion, void* workspace, float* grad_motion, int pre_zeroed,
-                      cudaStream_t s) {
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  const FusedArgs a = fused_args(p, motion);
-  if (p->stage_mask & 1) {
-    if (!pre_zeroed) CMAX_CUDA_CHECK(cudaMemsetAsync(grad_motion, 0, motion_floats(p, motion_model) * sizeof(float), s));
-    if (motion_model == CMAX_MOTION_2DOF) CMAX_CUDA_CHECK(cudaMemsetAsync(w.acc2, 0, 2 * sizeof(double), s));
-  }
-  if (p->n > 0 && (p->stage_mask & 2)) {
-    const int grid = event_grid(p->n, 8);
-    int gvar = p->grad_variant;
-    if (gvar == 1 && p->order != CMAX_ORDER_PIXEL) gvar = 0;  // the segmented reduction needs source-pixel order
-    float* target = (motion_model == CMAX_MOTION_2DOF) ? reinterpret_cast<float*>(w.acc2) : grad_motion;
-    if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, w.gq, target);
-    else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, w.gq, target);
-    else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, w.gq, target);
-    if (motion_model == CMAX_MOTION_2DOF) finish_2dof_kernel<<<1, 32, 0, s>>>(w.acc2, grad_motion);
-  }
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  return CMAX_OK;
+void launch_grad_any(const cmax_plan* p, int motion_model, cudaStream_t s, const FusedArgs& a, const float4* gq, float* target) {
+  const int grid = event_grid(p->n, 8);
+  int gvar = p->grad_variant;
+  if (gvar == 1 && p->order != CMAX_ORDER_PIXEL) gvar = 0;  // the segmented reduction needs source-pixel order
+  if (motion_model == CMAX_MOTION_DENSE) launch_grad_m<CMAX_MOTION_DENSE>(p->n_ref, gvar, grid, s, a, gq, target);
+  else if (motion_model == CMAX_MOTION_VOXEL) launch_grad_m<CMAX_MOTION_VOXEL>(p->n_ref, gvar, grid, s, a, gq, target);
+  else launch_grad_m<CMAX_MOTION_2DOF>(p->n_ref, gvar, grid, s, a, gq, target);
 }
 
 }  // namespace cmax
-
-using namespace cmax;
-
-extern "C" {
-
-size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_spec* spec) {
-  (void)spec;
-  if (plan == nullptr) {
-    set_error("cmax_objective_workspace_bytes: plan is NULL");
-    return 0;
-  }
-  return obj_layout(plan->Hp, plan->Wp).total;
-}
-
-int cmax_objective_workspace_init(const cmax_plan_t* plan, void* workspace, cmax_stream_t stream) {
-  CMAX_REQUIRE(plan != nullptr && workspace != nullptr, "cmax_objective_workspace_init: NULL argument");
-  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective_workspace_init: workspace must be 256-byte aligned");
-  CMAX_CUDA_CHECK(cudaMemsetAsync(workspace, 0, obj_layout(plan->Hp, plan->Wp).total, as_stream(stream)));
-  return CMAX_OK;
-}
-
-int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float** iwe_out,
-                        const cmax_cost_spec* fuse_spec, int32_t* stats_fused, cmax_stream_t stream) {
-  int rc = check_model("cmax_objective_vote", plan, motion_model);
-  if (rc) return rc;
-  CMAX_REQUIRE(motion != nullptr && workspace != nullptr, "cmax_objective_vote: NULL motion/workspace");
-  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective_vote: workspace must be 256-byte aligned");
-  rc = vote_stage(plan, motion_model, motion, workspace, fuse_spec, nullptr, stats_fused, as_stream(stream));
-  if (rc) return rc;
-  if (iwe_out) *iwe_out = carve(workspace, obj_layout(plan->Hp, plan->Wp)).iwe;
-  return CMAX_OK;
-}
-
-int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
-                        int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream) {
-  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost: NULL argument");
-  int rc = check_spec("cmax_objective_cost", spec, plan->n_ref);
-  if (rc) return rc;
-  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_cost: normalised costs need d_orig_stat");
-  CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective_cost: images must be at least 3x3");
-  CMAX_REQUIRE(!stats_fused || can_fuse_stats(spec), "cmax_objective_cost: stats_fused set for a spec that cannot fuse");
-  return cost_stage(plan, spec, d_orig_stat, workspace, stats_fused, 0, want_grad, d_cost, nullptr, 0, stream);
-}
-
-int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float* grad_motion,
-                        cmax_stream_t stream) {
-  int rc = check_model("cmax_objective_grad", plan, motion_model);
-  if (rc) return rc;
-  CMAX_REQUIRE(motion != nullptr && workspace != nullptr && grad_motion != nullptr, "cmax_objective_grad: NULL argument");
-  return grad_stage(plan, motion_model, motion, workspace, grad_motion, 0, as_stream(stream));
-}
-
-int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
-                   const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion, cmax_stream_t stream) {
-  int rc = check_model("cmax_objective", plan, motion_model);
-  if (rc) return rc;
-  CMAX_REQUIRE(motion != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective: NULL argument");
-  CMAX_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "cmax_objective: workspace must be 256-byte aligned");
-  rc = check_spec("cmax_objective", spec, plan->n_ref);
-  if (rc) return rc;
-  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective: normalised costs need d_orig_stat");
-  CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective: images must be at least 3x3");
-  const Ws w = carve(workspace, obj_layout(plan->Hp, plan->Wp));
-  const CombineDev cd = combine_for(plan, spec, d_orig_stat, d_cost, w);
-  int32_t fused = 0;
-  rc = vote_stage(plan, motion_model, motion, workspace, spec, &cd, &fused, as_stream(stream));
-  if (rc) return rc;
-  // with everything enabled the gradient buffer is cleared inside the gradient-picture kernel instead of by a memset
-  const bool zero_in_gq = grad_motion != nullptr && plan->stage_mask == 7;
-  rc = cost_stage(plan, spec, d_orig_stat, workspace, fused, fused, grad_motion != nullptr, d_cost, zero_in_gq ? grad_motion : nullptr,
-                  zero_in_gq ? motion_floats(plan, motion_model) : 0, stream);
-  if (rc) return rc;
-  if (grad_motion != nullptr) rc = grad_stage(plan, motion_model, motion, workspace, grad_motion, zero_in_gq ? 1 : 0, as_stream(stream));
-  return rc;
-}
-
-int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
-                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, const uint32_t* d_flags,
-                              const uint32_t* d_epoch, cmax_stream_t stream) {
-  CMAX_REQUIRE((d_flags == nullptr) == (d_epoch == nullptr), "cmax_objective_reduce_iwe: d_flags and d_epoch go together");
-  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && h_peer_iwe != nullptr && d_cost != nullptr, "cmax_objective_reduce_iwe: NULL argument");
-  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_objective_reduce_iwe: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
-  int rc = check_spec("cmax_objective_reduce_iwe", spec, plan->n_ref);
-  if (rc) return rc;
-  CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_reduce_iwe: normalised costs need d_orig_stat");
-  const cmax_plan* p = plan;
-  const ObjLayout L = obj_layout(p->Hp, p->Wp);
-  const Ws w = carve(workspace, L);
-  cudaStream_t s = as_stream(stream);
-  PeerPtrs peers;
-  peers.n = n_peers;
-  for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_iwe[r] : nullptr;
-  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_objective_reduce_iwe: peer %d IWE pointer is NULL", r);
-  const bool fuse = can_fuse_stats(spec);
-  // the statistics block was left clean by this rank's fold (fold_kernel); variant 1 has no fold
-  if (fuse && p->vote_variant == 1) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
-  CombineDev cd;
-  memset(&cd, 0, sizeof(cd));
-  if (fuse) cd = combine_for(p, spec, d_orig_stat, d_cost, w);
-  const int64_t work = (L.HW & 3) == 0 ? L.HW / 4 : L.HW;  // threads with work (16-byte loads when the image allows)
-  dim3 grid((unsigned)std::min<int64_t>((work + kStatBlock - 1) / kStatBlock, kNumSMs * 4), p->n_ref);
-  peer_iwe_kernel<<<grid, kStatBlock, 0, s>>>(peers, w.iwe_full, p->Hp, p->Wp, fuse ? 1 : 0, fuse ? spec->omit_boundary : 0, w.sacc, w.stats,
-                                              fuse ? 1 : 0, cd, w.ctas_done, d_flags, d_epoch);
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  if (combined) *combined = fuse ? 1 : 0;
-  return CMAX_OK;
-}
-
-int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
-                                     int combined, int want_grad, double* d_cost, cmax_stream_t stream) {
-  CMAX_REQUIRE(plan != nullptr && workspace != nullptr && d_cost != nullptr, "cmax_objective_cost_after_reduce: NULL argument");
-  int rc = check_spec("cmax_objective_cost_after_reduce", spec, plan->n_ref);
-  if (rc) return rc;
-  CMAX_REQUIRE(!combined || can_fuse_stats(spec), "cmax_objective_cost_after_reduce: combined set for a spec that cannot fuse");
-  return cost_stage(plan, spec, d_orig_stat, workspace, combined, combined, want_grad, d_cost, nullptr, 0, stream, true);
-}
-
-int cmax_push(const float* src, int64_t n, float* const* h_peer_slots, uint32_t* const* h_peer_flags, int n_peers, uint32_t* d_epoch,
-              uint32_t* d_counter, cmax_stream_t stream) {
-  CMAX_REQUIRE(h_peer_slots != nullptr && h_peer_flags != nullptr && d_epoch != nullptr && d_counter != nullptr, "cmax_push: NULL argument");
-  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_push: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
-  CMAX_REQUIRE(n >= 0 && (n == 0 || src != nullptr), "cmax_push: bad source");
-  PushPtrs dst;
-  dst.n = n_peers;
-  for (int r = 0; r < CMAX_MAX_PEERS; ++r) {
-    dst.slot[r] = r < n_peers ? h_peer_slots[r] : nullptr;
-    dst.flag[r] = r < n_peers ? h_peer_flags[r] : nullptr;
-  }
-  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(dst.flag[r] != nullptr && (n == 0 || dst.slot[r] != nullptr), "cmax_push: peer %d pointer is NULL", r);
-  const int grid = n == 0 ? 1 : (int)std::max<int64_t>(1, std::min<int64_t>(((n + 3) / 4 + 255) / 256, (int64_t)kNumSMs * 2));
-  push_kernel<<<grid, 256, 0, as_stream(stream)>>>(src, n, dst, d_epoch, d_counter);
-  CMAX_CUDA_CHECK(cudaGetLastError());
-  return CMAX_OK;
-}
-
-int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, const uint32_t* d_flags, const uint32_t* d_epoch,
-                      cmax_stream_t stream) {
-  CMAX_REQUIRE((d_flags == nullptr) == (d_epoch == nullptr), "cmax_reduce_peers: d_flags and d_epoch go together");
-  if (n == 0 && d_flags != nullptr) {  // nothing to sum: just consume the flags (closes a value-only evaluation)
-    CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_reduce_peers: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
-    wait_kernel<<<1, 32, 0, as_stream(stream)>>>(d_flags, d_epoch, n_peers);
-    CMAX_CUDA_CHECK(cudaGetLastError());
-    return CMAX_OK;
-  }
-  CMAX_REQUIRE(h_peer_bufs != nullptr && out != nullptr, "cmax_reduce_peers: NULL argument");
-  CMAX_REQUIRE(n_peers >= 1 && n_peers <= CMAX_MAX_PEERS, "cmax_reduce_peers: n_peers must be in [1,%d], got %d", CMAX_MAX_PEERS, n_peers);
-  CMAX_REQUIRE(n >= 0, "cmax_reduce_peers: n must be >= 0");
-  PeerPtrs peers;
-  peers.n = n_peers;
-  for (int r = 0; r < CMAX_MAX_PEERS; ++r) peers.p[r] = r < n_peers ? h_peer_bufs[r] : nullptr;
-  for (int r = 0; r < n_peers; ++r) CMAX_REQUIRE(peers.p[r] != nullptr, "cmax_reduce_peers: peer %d pointer is NULL", r);
-  if (n > 0) {
-    peer_sum_kernel<<<image_grid((n & 3) == 0 ? n / 4 : n), 256, 0, as_stream(stream)>>>(peers, n, out, d_flags, d_epoch);
-    CMAX_CUDA_CHECK(cudaGetLastError());
-  }
-  return CMAX_OK;
-}
-
-size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan) {
-  if (plan == nullptr) {
-    set_error("cmax_objective_full_iwe_offset: plan is NULL");
-    return 0;
-  }
-  return obj_layout(plan->Hp, plan->Wp).off_iwe_full;
-}
-
-size_t cmax_objective_iwe_offset(const cmax_plan_t* plan) {
-  if (plan == nullptr) {
-    set_error("cmax_objective_iwe_offset: plan is NULL");
-    return 0;
-  }
-  return obj_layout(plan->Hp, plan->Wp).off_iwe;
-}
-
-}  // extern "C"

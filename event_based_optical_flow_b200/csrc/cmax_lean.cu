@@ -360,14 +360,9 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
 
 // ------------------------------------------------------------------------------------------------ dispatch
 static int strips_grid_size(int per_sm, int64_t n_strips) {
+  // persistent: exactly the CTAs that are resident at once (2 x that / one tile per warp measured no better: profiles/README.md)
   const int64_t tiles = (n_strips + 31) / 32, ctas = (tiles + kRunWarps - 1) / kRunWarps;
-  static int waves = -1;  // CMAX_STRIPS_WAVES=k: k x the resident CTAs instead of 1 x (0 = one tile per warp); measurement
-  if (waves < 0) {
-    const char* e = getenv("CMAX_STRIPS_WAVES");
-    waves = e ? atoi(e) : 1;
-  }
-  if (waves == 0) return (int)std::max<int64_t>(1, ctas);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm * waves));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)num_sms() * per_sm));
 }
 template <typename K>
 static int strips_grid(K kernel, int64_t n_strips) {

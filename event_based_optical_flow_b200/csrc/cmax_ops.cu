@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) blur3_transpose_kernel(const float* __res
 
 static inline int grid_for(int64_t n, int block, int per_sm) {
   const int64_t want = (n + block - 1) / block;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)kNumSMs * per_sm));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms() * per_sm));
 }
 
 }  // namespace cmax

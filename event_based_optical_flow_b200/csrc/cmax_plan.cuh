@@ -4,23 +4,13 @@
 
 namespace cmax {
 
-// Source tiles: events are grouped by the 32x32 tile their UN-warped pixel falls in.  A CTA privatises a
-// 64x64 window of the IWE (the tile plus a 16-pixel halo on every side) in shared memory as int32 fixed point.
+// Source tiles: the plan's sort key is tile-major (32x32 tiles of UN-warped pixels, row-major inside a tile), so that events
+// which are neighbours in the stream read neighbouring flow vectors and vote into neighbouring IWE cells.
 constexpr int kTile = 32;
-constexpr int kHalo = 16;
-constexpr int kWin = kTile + 2 * kHalo;  // 64
 constexpr int kRunE = 8;                  // consecutive events one thread of a run kernel walks
 constexpr int kWarpTile = 32 * kRunE;    // events per warp-tile of the packed copy
 constexpr int kStripTileBytes = 128 + 32 * kRunE * 4;  // 32 strip headers + 32 strips of kRunE times (cmax_events.cu)
 constexpr int kStripBinBytes = 32 * kRunE;              // time-aware plans: + one byte per event and reference time (its time bin)
-constexpr int kChunk = 8192;             // events per CTA work item (bounds the fixed-point range, see cmax_fused.cu)
-
-struct Chunk {
-  int32_t tile;   // tile id (ty * tiles_x + tx)
-  int32_t begin;  // first event (index into the tile-sorted array)
-  int32_t count;  // <= kChunk
-  int32_t pad_;
-};
 
 }  // namespace cmax
 
@@ -42,19 +32,17 @@ struct cmax_plan {
   int64_t n_strips;
   int strip_tile_bytes;  // kStripTileBytes, + n_ref * kStripBinBytes when the plan was packed for a flow voxel (n_bins > 0)
   const uint32_t* sorted_keys;
-  const uint32_t* key_counts;
-  const uint32_t* key_first;
-  const uint32_t* key_strip0;
+  const uint32_t* key_first;   // [n_keys + 1]: first event of every sort key (events of key k = key_first[k] .. key_first[k+1])
+  const uint32_t* key_strip0;  // [n_keys + 1]: first strip of every sort key
+  int packed_valid;            // the packed copy matches the current reference times / format (built on demand: the strip kernels never read it)
   int64_t n;
   int H, W, pad_h, pad_w, Hp, Wp;
   float t_min, t_max;
   int order;         // cmax_order
   int vote_variant;  // see cmax_plan_set_variant
   int grad_variant;
-  int stage_mask;       // see cmax_plan_set_stage_mask (7 = everything)
+  int stage_mask;       // see cmax_plan_set_stage_mask (7 = everything; other values only in CMAX_MEASURE builds)
   int tiles_x, tiles_y, n_tiles;
-  const cmax::Chunk* chunks;  // device
-  int n_chunks;
   cmax_time_params_t* d_params;  // device
   float* d_minmax;               // device [2]
   int32_t* d_status;             // device [1]

@@ -21,8 +21,7 @@ struct FusedArgs {
   const float* motion;
   const cmax_time_params_t* tp;
   int64_t cells;  // (Hp+1)*(Wp+1)
-  unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block), or NULL
-  int dbg;                // measurement only (CMAX_DEBUG): bit 0 = skip the reductions, bit 1 = skip the flow loads
+  unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block + grid-barrier counters), or NULL
 };
 
 // Time parameters one CTA needs, staged in shared memory once per CTA.
@@ -187,13 +186,17 @@ __device__ __forceinline__ int vote_cell(const Vote& v, int Hp, int Wp) {
 }
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait); `pdl == false` is an ordinary launch.
-static inline bool pdl_enabled() {  // CMAX_PDL=0 turns programmatic dependent launch off (measurement)
+static inline bool pdl_enabled() {
+#ifdef CMAX_MEASURE  // measurement builds only: CMAX_PDL=0 turns programmatic dependent launch off
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CMAX_PDL");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+#else
+  return true;
+#endif
 }
 
 template <typename... KArgs, typename... Args>
@@ -225,9 +228,12 @@ static inline int run_grid(K kernel, int64_t n) {
     per_sm = v;
   }
   const int64_t ctas = ((n + kWarpTile - 1) / kWarpTile + kRunWarps - 1) / kRunWarps;
-  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)kNumSMs * per_sm));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(ctas, (int64_t)num_sms() * per_sm));
 }
 
+
+// (re)build the packed copy the run kernels read, if it is stale (cmax_events.cu)
+int ensure_packed(const cmax_plan* plan, cudaStream_t s);
 
 // strip kernels (cmax_lean.cu)
 int strips_tile_bytes_for(int motion_model, int n_ref);

@@ -132,7 +132,7 @@ int cmax_tile_flow_upsample(const float* motion, int hp, int wp, int pad_h, int 
   const int rc = make_geom("cmax_tile_flow_upsample", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
   if (rc) return rc;
   const int64_t HW = (int64_t)H * W;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((HW + 255) / 256, (int64_t)kNumSMs * 4));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((HW + 255) / 256, (int64_t)num_sms() * 4));
   tile_flow_upsample_kernel<<<grid, 256, 0, as_stream(stream)>>>(motion, g, dense);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;

@@ -2,15 +2,14 @@
 
 This is the fast path behind the reference's per-iteration seam
 `PatchContrastMaximization.calculate_cost` / `get_arg_for_cost` (src/solver/patch_contrast_base.py:273-352):
-events are made resident once per `optimize()` (`EventPlan`), and every objective evaluation is three C-ABI calls
-(`cmax_objective_vote` -> [all-reduce IWE] -> `cmax_objective_cost` -> `cmax_objective_grad` -> [all-reduce grad])
-with no host synchronisation.  The gradient w.r.t. the motion is analytic; events never
+events are made resident once per `optimize()` (`EventPlan`), and every objective evaluation is ONE C-ABI call
+(`cmax_objective`: K1 -> image kernel -> K3; sharded over several GPUs `cmax_objective_sharded`, which does its two sums
+over NVLink peer memory inside those kernels) with no host synchronisation.  The gradient w.r.t. the motion is analytic; events never
 receive a gradient (the reference only ever asks for d cost / d motion, scipy_autograd/torch_wrapper.py:38-40).
 """
 from __future__ import annotations
 
 import ctypes as C
-import os
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -131,7 +130,7 @@ class EventPlan:
         return bool(out.value)
 
     def set_stage_mask(self, mask: int = 7) -> None:
-        """Measurement aid, see cmax_plan_set_stage_mask in include/cmax_b200.h."""
+        """Measurement builds only (-DCMAX_MEASURE): the release library accepts no mask but 7."""
         _lib.call("cmax_plan_set_stage_mask", self.handle, int(mask))
 
     def close(self) -> None:
@@ -163,8 +162,9 @@ class ContrastObjective:
     `direction` = the cost direction (src/costs/base.py:20-25), `outer_padding` as in `EventImageConverter`.
     `process_group`: events are sharded over its ranks; the partial IWE and the partial gradient are summed once each per
     evaluation, either with an NCCL all-reduce (`exchange="nccl"`) or over NVLink peer memory
-    (`exchange="peer"`: the workspaces live in torch symmetric memory, an in-stream barrier replaces the collective
-    launch, and one kernel per exchange reads all ranks' partial buffers -- the IWE one also computes the cost).
+    (`exchange="peer"`: the workspaces live in torch symmetric memory and the sums happen INSIDE the image kernel and a
+    gradient-exchange kernel, behind flags raised on the peers -- no collective launch, no barrier kernel; see
+    cmax_objective_sharded in include/cmax_b200.h).
     """
 
     def __init__(self, events: Union[torch.Tensor, EventPlan], image_size: Tuple[int, int], *, cost: str = "image_variance",
@@ -185,13 +185,14 @@ class ContrastObjective:
         self.stat, self.form = stat, form
         self.ref_keys = tuple(k for k, _ in refs)
         self.group = process_group
-        if exchange not in ("nccl", "peer", "push"):
-            raise ValueError(f"exchange must be 'nccl', 'peer' or 'push', got {exchange}")
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"exchange must be 'nccl' or 'peer', got {exchange}")
         self.exchange = exchange if process_group is not None else "nccl"
         if orig_events is None and isinstance(events, torch.Tensor):
             orig_events = events
         # second order (Hessian-vector products) runs on the modular operators, which take the caller's event array
-        self._events_ref = events.detach() if isinstance(events, torch.Tensor) else None
+        # (an objective built from an EventPlan keeps the caller's tensor through `orig_events`)
+        self._events_ref = events.detach() if isinstance(events, torch.Tensor) else (orig_events.detach() if orig_events is not None else None)
         self._modular_tp = None
         self.plan = events if isinstance(events, EventPlan) else EventPlan(events, image_size, outer_padding, order, t_range)
         self.device = self.plan.device
@@ -217,7 +218,7 @@ class ContrastObjective:
         self._symm = None
         with torch.cuda.device(self.device):
             nbytes = self.lib.cmax_objective_workspace_bytes(self.plan.handle, C.byref(self.spec))
-            if self.exchange in ("peer", "push"):
+            if self.exchange == "peer":
                 self._setup_peer_exchange(nbytes)
             else:
                 self._ws = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
@@ -230,16 +231,14 @@ class ContrastObjective:
             self._orig_stat = self._orig_statistic(orig_events)
         self._iwe_view = None
 
-    # -- NVLink peer-memory exchange: the workspace and the partial-gradient buffer are symmetric allocations
+    # -- NVLink peer-memory exchange: workspace, partial gradient and flag block are ONE symmetric allocation per rank
     def _setup_peer_exchange(self, nbytes: int) -> None:
-        """One symmetric allocation per rank: [objective workspace][partial gradient][IWE mailbox: one slot per source rank]
-        [gradient mailbox][IWE flags][gradient flags].  "peer" reads the peers' partial buffers after an in-stream barrier;
-        "push" writes into the peers' mailboxes and raises flags (see cmax_push in include/cmax_b200.h)."""
+        """[objective workspace][partial gradient][flag block]; `cmax_peers` holds every rank's addresses of the three."""
         import torch.distributed._symmetric_memory as symm_mem
         world = torch.distributed.get_world_size(self.group)
         rank = torch.distributed.get_rank(self.group)
         if world > _lib.MAX_PEERS:
-            raise ValueError(f"exchange={self.exchange!r} supports up to {_lib.MAX_PEERS} ranks (one NVLink domain), got {world}")
+            raise ValueError(f"exchange='peer' supports up to {_lib.MAX_PEERS} ranks (one NVLink domain), got {world}")
         import warnings
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -248,19 +247,10 @@ class ContrastObjective:
             except Exception:
                 pass  # newer torch enables it implicitly
         n_motion = int(np.prod(self.motion_shape))
-        Hp, Wp = self.padded_size
-        n_iwe = len(self.directions) * Hp * Wp
         al = lambda v: (v + 255) // 256 * 256  # noqa: E731
         grad_off = al(nbytes)
-        box_iwe = al(grad_off + 4 * n_motion)
-        iwe_slot = al(4 * n_iwe)
-        box_grad = box_iwe + world * iwe_slot
-        grad_slot = al(4 * n_motion)
-        flags_iwe = box_grad + world * grad_slot
-        flags_grad = flags_iwe + 256
-        total = flags_grad + 256
-        if self.exchange == "peer":
-            total = box_iwe  # no mailboxes
+        flags_off = al(grad_off + 4 * n_motion)
+        total = flags_off + 256
         self._ws = symm_mem.empty(total, dtype=torch.uint8, device=self.device)
         if self._ws.data_ptr() % 256 != 0:
             raise RuntimeError("symmetric allocation is not 256-byte aligned")
@@ -268,28 +258,14 @@ class ContrastObjective:
         self._symm = symm_mem.rendezvous(self._ws, self.group)
         bases = [int(p) for p in self._symm.buffer_ptrs]
         iwe_off = int(self.lib.cmax_objective_iwe_offset(self.plan.handle))
-        self._n_peers = world
-        self._n_iwe, self._n_motion = n_iwe, n_motion
         self._grad_part = self._ws[grad_off:grad_off + 4 * n_motion].view(torch.float32).view(self.motion_shape)
-        arr = lambda vals: (C.c_void_p * world)(*vals)  # noqa: E731
-        if self.exchange == "peer":
-            self._peer_iwe = arr([b + iwe_off for b in bases])
-            self._peer_grad = arr([b + grad_off for b in bases])
-        else:
-            me = bases[rank]
-            self._iwe_local_ptr = me + iwe_off
-            # where THIS rank writes on every rank q, and what it reads locally
-            self._push_iwe_slots = arr([b + box_iwe + rank * iwe_slot for b in bases])
-            self._push_iwe_flags = arr([b + flags_iwe + 4 * rank for b in bases])
-            self._push_grad_slots = arr([b + box_grad + rank * grad_slot for b in bases])
-            self._push_grad_flags = arr([b + flags_grad + 4 * rank for b in bases])
-            self._peer_iwe = arr([me + box_iwe + r * iwe_slot for r in range(world)])
-            self._peer_grad = arr([me + box_grad + r * grad_slot for r in range(world)])
-            self._flags_iwe_ptr, self._flags_grad_ptr = me + flags_iwe, me + flags_grad
-            # local bookkeeping words: [epoch IWE, epoch gradient, CTA counter IWE, CTA counter gradient]
-            self._push_words = torch.zeros(64, dtype=torch.int32, device=self.device)
+        peers = _lib.Peers()
+        peers.n_peers, peers.rank = world, rank
+        for r, b in enumerate(bases):
+            peers.iwe[r], peers.grad[r], peers.flags[r] = b + iwe_off, b + grad_off, b + flags_off
+        self._peers = peers
         torch.cuda.synchronize(self.device)
-        torch.distributed.barrier(group=self.group)
+        torch.distributed.barrier(group=self.group)  # every rank's flags are zero before anyone raises one
 
     # -- the statistic of the un-warped IWE (normalised costs); constant per optimize(), so computed once
     #    (the reference recomputes it on every call, src/solver/patch_contrast_base.py:295-301)
@@ -315,75 +291,35 @@ class ContrastObjective:
             raise ValueError(f"motion for {self.motion_model} must have shape {self.motion_shape}, got {tuple(motion.shape)}")
         return motion.detach().to(torch.float32).contiguous()
 
-    def _vote(self, m: torch.Tensor, stream: int) -> int:
+    def _vote_and_fold(self, m: torch.Tensor, stream: int) -> None:
+        """K1 + fold: this rank's (partial) IWE stack is in `self._iwe_view` afterwards."""
         iwe_ptr = C.c_void_p()
-        fused = C.c_int32(0)
-        spec = C.byref(self.spec) if self.group is None else None
-        _lib.call("cmax_objective_vote", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr,
-                  C.byref(iwe_ptr), spec, C.byref(fused), stream)
+        _lib.call("cmax_objective_vote", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr, stream)
+        _lib.call("cmax_objective_fold", self.plan.handle, self._ws_ptr, C.byref(iwe_ptr), stream)
         if self._iwe_view is None:
             off = iwe_ptr.value - self._ws.data_ptr()
             Hp, Wp = self.padded_size
             k = len(self.directions)
             self._iwe_view = self._ws[off:off + 4 * k * Hp * Wp].view(torch.float32).view(k, Hp, Wp)
-        if self.group is not None and self.exchange == "nccl":
-            torch.distributed.all_reduce(self._iwe_view, group=self.group)
-        return fused.value
 
     def _evaluate(self, m: torch.Tensor, cost: torch.Tensor, grad: Optional[torch.Tensor], stream: int) -> None:
-        """Stages 1-3 with the exchange of this objective in between; writes cost[0] and (if given) grad.  No host sync."""
+        """One evaluation: writes cost[0] and (if given) grad.  No host sync, CUDA-graph capturable."""
         model = _lib.MOTION[self.motion_model]
         orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
-        want = 1 if grad is not None else 0
+        gptr = grad.data_ptr() if grad is not None else None
         self.plan.set_refs(self.directions, self.n_bins)  # no-op unless another objective re-packed the shared plan
-        if self.group is None:  # single GPU: the three stages in one C-ABI call (4 kernels for the metric configuration)
-            _lib.call("cmax_objective", self.plan.handle, model, m.data_ptr(), C.byref(self.spec), orig, self._ws_ptr, cost.data_ptr(),
-                      grad.data_ptr() if grad is not None else None, stream)
-            return
-        fused = self._vote(m, stream)
-        if self.exchange == "push":
-            w = self._push_words.data_ptr()
-            ep_iwe, ep_grad, cnt_iwe, cnt_grad = w, w + 4, w + 8, w + 12
-            _lib.call("cmax_push", self._iwe_local_ptr, self._n_iwe, self._push_iwe_slots, self._push_iwe_flags, self._n_peers, ep_iwe, cnt_iwe, stream)
-            combined = C.c_int32(0)
-            _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
-                      self._ws_ptr, cost.data_ptr(), C.byref(combined), self._flags_iwe_ptr, ep_iwe, stream)
-            _lib.call("cmax_objective_cost_after_reduce", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, combined.value,
-                      want, cost.data_ptr(), stream)
+        if self.group is None:  # single GPU: K1 -> image kernel -> K3
+            _lib.call("cmax_objective", self.plan.handle, model, m.data_ptr(), C.byref(self.spec), orig, self._ws_ptr, cost.data_ptr(), gptr, stream)
+        elif self.exchange == "peer":  # sharded, both sums inside the kernels over NVLink peer memory
+            _lib.call("cmax_objective_sharded", self.plan.handle, model, m.data_ptr(), C.byref(self.spec), orig, self._ws_ptr,
+                      C.byref(self._peers), cost.data_ptr(), gptr, stream)
+        else:  # sharded, NCCL all-reduces between the stages (the baseline exchange)
+            self._vote_and_fold(m, stream)
+            torch.distributed.all_reduce(self._iwe_view, group=self.group)
+            _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, 1 if grad is not None else 0,
+                      cost.data_ptr(), gptr, grad.numel() if grad is not None else 0, stream)
             if grad is not None:
-                _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
-                _lib.call("cmax_push", self._grad_part.data_ptr(), self._n_motion, self._push_grad_slots, self._push_grad_flags, self._n_peers,
-                          ep_grad, cnt_grad, stream)
-                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), self._flags_grad_ptr, ep_grad, stream)
-            else:
-                # value only: the gradient phase still runs empty (flags only), so that no rank overwrites its IWE slots
-                # (next evaluation) while a slower peer is still reading them
-                _lib.call("cmax_push", None, 0, self._push_grad_slots, self._push_grad_flags, self._n_peers, ep_grad, cnt_grad, stream)
-                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, 0, None, self._flags_grad_ptr, ep_grad, stream)
-            return
-        if self.exchange == "peer":
-            skip = os.environ.get("CMAX_TIMING_SKIP_BARRIER") == "1"  # measurement only: results are then undefined
-            if not skip:
-                self._symm.barrier(channel=0)  # every rank's partial IWE is complete and visible
-            combined = C.c_int32(0)
-            _lib.call("cmax_objective_reduce_iwe", self.plan.handle, C.byref(self.spec), self._peer_iwe, self._n_peers, orig,
-                      self._ws_ptr, cost.data_ptr(), C.byref(combined), None, None, stream)
-            _lib.call("cmax_objective_cost_after_reduce", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, combined.value,
-                      want, cost.data_ptr(), stream)
-            if grad is not None:
-                _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, self._grad_part.data_ptr(), stream)
-                if not skip:
-                    self._symm.barrier(channel=1)
-                _lib.call("cmax_reduce_peers", self._peer_grad, self._n_peers, grad.numel(), grad.data_ptr(), None, None, stream)
-            else:
-                # value only: still close the evaluation with a barrier, so that no rank overwrites its partial IWE (next
-                # evaluation's fold) while a slower peer is reading it
-                self._symm.barrier(channel=1)
-            return
-        _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, fused, want, cost.data_ptr(), stream)
-        if grad is not None:
-            _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, grad.data_ptr(), stream)
-            if self.group is not None:
+                _lib.call("cmax_objective_grad", self.plan.handle, model, m.data_ptr(), self._ws_ptr, gptr, 1, stream)
                 torch.distributed.all_reduce(grad, group=self.group)
 
     def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
@@ -405,26 +341,19 @@ class ContrastObjective:
         """The (un-blurred) IWE stack [n_ref, Hp, Wp] for `motion` (a copy; summed over all ranks when sharded)."""
         m = self._check_motion(motion)
         with torch.cuda.device(self.device):
-            self._vote(m, _stream_ptr())
+            self.plan.set_refs(self.directions, self.n_bins)
+            self._vote_and_fold(m, _stream_ptr())
             out = self._iwe_view.clone()
-            if self.group is not None and self.exchange in ("peer", "push"):
+            if self.group is not None:
                 torch.distributed.all_reduce(out, group=self.group)  # off the hot path: plain NCCL
         return out
 
     def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
         """Allocation-free evaluation into caller buffers (fp32 motion, float64[1] cost, fp32 gradient), CUDA-graph
-        capturable.  Single GPU: one `cmax_objective` call.  Sharded: the three stages with the two NCCL all-reduces in
-        between (NCCL collectives are capturable, every rank captures the same sequence)."""
+        capturable (also sharded: the flag exchange lives inside the kernels, and NCCL collectives are capturable)."""
         if self._post_sign < 0:
             raise RuntimeError("step_into supports the minimize / maximize directions")
-        orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
-        model = _lib.MOTION[self.motion_model]
-        stream = _stream_ptr()
-        if self.group is None:
-            _lib.call("cmax_objective", self.plan.handle, model, motion_f32.data_ptr(), C.byref(self.spec), orig, self._ws_ptr,
-                      cost_out.data_ptr(), grad_out.data_ptr(), stream)
-            return
-        self._evaluate(motion_f32, cost_out, grad_out, stream)
+        self._evaluate(motion_f32, cost_out, grad_out, _stream_ptr())
 
     # -- second order: the same cost composed from the modular operators (warp -> vote -> blur -> statistic, one C-ABI
     #    call each, every backward differentiable once more), so that torch can differentiate the gradient itself
@@ -435,7 +364,7 @@ class ContrastObjective:
         if self.group is not None:
             raise NotImplementedError("Hessian-vector products are not implemented for sharded objectives")
         if self._events_ref is None:
-            raise NotImplementedError("Hessian-vector products need the objective to be built from the event tensor (not from an EventPlan)")
+            raise NotImplementedError("Hessian-vector products need the event tensor: pass `orig_events=` when the objective is built from an EventPlan")
         ev = self._events_ref
         if ev.shape[1] == 3:
             ev = torch.cat([ev, ev.new_zeros(len(ev), 1)], dim=1)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CMAX_ABI_VERSION 1
+#define CMAX_ABI_VERSION 2
 #define CMAX_MAX_REFS 4   /* reference times fused into one event pass (first / middle / last / one more) */
 #define CMAX_MAX_BINS 64  /* time bins of a flow voxel */
 #define CMAX_MAX_PEERS 8  /* GPUs of one NVLink domain whose partial images one kernel sums */
@@ -184,7 +184,8 @@ typedef enum {
 
 /* Resident, pre-processed event batch (events are constant over one solver.optimize()).  Validates source pixels,
  * takes (t_min,t_max) (pass NaN to compute from this batch; multi-GPU callers pass the GLOBAL range), and -- for
- * order != ASIS -- stably re-orders the events into the workspace as float4.  Synchronises `stream` once.
+ * order != ASIS -- stably re-orders the events into the workspace as float4 (radix sort by source pixel; the per-pixel
+ * counts come from the sorted keys, no atomics).  Everything is enqueued first and `stream` is synchronised ONCE.
  * `events` must stay alive and unchanged while the plan is used when order == CMAX_ORDER_ASIS. */
 size_t cmax_plan_workspace_bytes(int64_t n, int H, int W, int order);
 int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_stride, int H, int W, int pad_h,
@@ -219,10 +220,9 @@ int cmax_plan_set_variant(cmax_plan_t* plan, int vote_variant, int grad_variant)
  * identical.  enable = 0 forces the 16-byte format (measurement / tests); *h_compact (may be NULL) returns the format in
  * use afterwards. */
 int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cmax_stream_t stream);
-/* Measurement aid (bench.py roofline): which launches the three stages enqueue.  Bit 0 = the memsets, bit 1 = the
- * event kernels (K1 in cmax_objective_vote, K3 in cmax_objective_grad), bit 2 = the image-sized kernels (fold, blur,
- * statistics, gradient pictures).  Default 7 = everything; any other value produces timing-only (not meaningful)
- * results, e.g. 2 lets a CUDA-event pair bracket exactly one K1 or K3 launch. */
+/* Measurement aid, MEASUREMENT BUILDS ONLY (-DCMAX_MEASURE; the release library rejects every mask but 7 with
+ * CMAX_ERR_ARG, so that no switch can silently change the results of a release build): which launches the stages enqueue.
+ * Bit 0 = the memsets, bit 1 = the event kernels, bit 2 = the image-sized kernels. */
 int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask);
 
 /* What one CM evaluation computes: cost = form(stat(blur(iwe_r)))   src/costs/*.py, src/solver/patch_contrast_base.py:289-352 */
@@ -241,56 +241,57 @@ size_t cmax_objective_workspace_bytes(const cmax_plan_t* plan, const cmax_cost_s
  * are kept clean BETWEEN evaluations by the kernels themselves (the fold zeroes what it reads), so no evaluation ever
  * enqueues a memset for them. */
 int cmax_objective_workspace_init(const cmax_plan_t* plan, void* workspace, cmax_stream_t stream);
-/* Stage 1 (K1 + fold): warp by `motion` and bilinear-vote into n_ref images; returns in *iwe_out a pointer INTO the
- * workspace to [n_ref,Hp,Wp] fp32 (multi-GPU callers all-reduce it in place before stage 2).
- * (src/warp.py:301-313|339-365|506-520 -> src/event_image_converter.py:316-374, composed as in
- * src/solver/patch_contrast_base.py:308-347).  fuse_spec != NULL lets the fold also accumulate the variance sums
- * when the spec allows it (VARIANCE, sigma == 0; single-GPU only); *stats_fused (may be NULL) reports whether it did. */
-int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace,
-                        float** iwe_out, const cmax_cost_spec* fuse_spec, int32_t* stats_fused, cmax_stream_t stream);
-/* Stage 2 (K2): blur, statistics, scalar cost into d_cost[0] (float64, device) and -- when want_grad -- the
- * per-corner dL/dIWE pictures stage 3 gathers from.  d_orig_stat: device float64 statistic of the un-warped IWE
- * (normalised / multi-focal forms), else NULL.  stats_fused must repeat what stage 1 reported. */
-int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
-                        int stats_fused, int want_grad, double* d_cost, cmax_stream_t stream);
-/* Stage 3 (K3): re-warp, gather dL/dIWE at the 4 corners, chain to dL/dmotion (same shape as motion, ZEROED BY THE
- * CALLEE; multi-GPU callers all-reduce it afterwards).  (autograd of stage 1) */
-int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace,
-                        float* grad_motion, cmax_stream_t stream);
-/* Single-GPU convenience: stages 1-3 back to back (one CM iteration = warp + IWE + cost + gradient). */
+
+/* One CM iteration on one GPU = THREE launches: K1 (event pass: warp + vote), the image kernel (fold + statistics + scalar
+ * cost + per-corner gradient quads, grid-wide barriers between its phases), K3 (event pass: re-warp, gather, chain to
+ * dL/dmotion).  cost -> d_cost[0] (float64, device); grad_motion (same shape as motion; NULL = value only) is written in
+ * full.  d_orig_stat: device float64 statistic of the un-warped IWE (normalised / multi-focal forms), else NULL.
+ * Gradient-magnitude and blurred costs run the operator kernels (blur, Sobel statistics, combine) between a fold-only and
+ * a quads-only launch of the image kernel.
+ * (src/warp.py:301-313|339-365|506-520 -> src/event_image_converter.py:316-374 -> src/costs/<cost>.py, composed as in
+ * src/solver/patch_contrast_base.py:289-352; backward = autograd of all of it) */
 int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
                    const double* d_orig_stat, void* workspace, double* d_cost, float* grad_motion /* NULL = value only */,
                    cmax_stream_t stream);
-/* ---- multi-GPU exchange over NVLink peer memory (workspaces in symmetric memory) ----
- * After cmax_objective_vote on every rank and a cross-GPU barrier, every rank calls cmax_objective_reduce_iwe with the
- * device pointers of ALL ranks' partial IWE stacks (h_peer_iwe[r] = peer r's workspace base + cmax_objective_iwe_offset,
- * a host array of device pointers, rank order): one kernel sums them (P2P loads, rank order -> bit-identical on all
- * ranks) into this rank's FULL-IWE buffer (workspace + cmax_objective_full_iwe_offset; the partial stays intact because
- * peers are reading it) and, when the spec allows (VARIANCE, sigma == 0), also accumulates the
- * statistics and evaluates the scalar cost -- the collective and the cost are ONE kernel.  *combined reports whether
- * it did; pass it to cmax_objective_cost_after_reduce, which runs what is left of stage 2 (blur / statistics / cost when
- * not combined, then the gradient pictures).  The partial gradient is exchanged the same way: cmax_objective_grad into
- * a symmetric buffer, barrier, cmax_reduce_peers. */
+/* The same evaluation stage by stage (what cmax_objective enqueues for a variance cost without blur is exactly
+ * vote + cost(zero_grad = grad_motion) + grad(pre_zeroed = 1)); callers that all-reduce with NCCL put their collectives
+ * between the stages: vote, fold, [all-reduce *iwe_out in place], cost, grad, [all-reduce the gradient].
+ *   vote  K1: warp by `motion` and bilinear-vote into the per-corner accumulators of the n_ref images.
+ *   fold  accumulators -> IWE stack [n_ref,Hp,Wp] fp32 inside the workspace (*iwe_out, may be NULL, receives its address).
+ *   cost  statistics + scalar cost of the folded IWEs and -- when want_grad -- the gradient quads; zero_grad (may be NULL)
+ *         = n_zero floats cleared on the way (the buffer `grad` accumulates into).
+ *   grad  K3 into grad_motion; pre_zeroed != 0 promises the buffer was cleared by `cost`. */
+int cmax_objective_vote(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, cmax_stream_t stream);
+int cmax_objective_fold(const cmax_plan_t* plan, void* workspace, float** iwe_out, cmax_stream_t stream);
+int cmax_objective_cost(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace, int want_grad,
+                        double* d_cost, float* zero_grad, int64_t n_zero, cmax_stream_t stream);
+int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* motion, void* workspace, float* grad_motion,
+                        int pre_zeroed, cmax_stream_t stream);
+
+/* ---- multi-GPU: events sharded over the ranks of one NVLink domain, one process per GPU ----
+ * The objective workspace, the partial-gradient buffer and a flag block of every rank live in SYMMETRIC (peer-mapped)
+ * memory.  cmax_objective_sharded is cmax_objective with the two sums of the sharded path fused into its kernels, no
+ * collective launch and no barrier kernel:
+ *   K1 -> image kernel: fold this rank's partial IWE; its last CTA raises this rank's flag on every peer (one fence + one
+ *         posted store per peer); every CTA then waits for all ranks' flags and sums the partial IWEs of ALL ranks
+ *         through NVLink peer loads, in rank order (bit-identical on every rank), accumulating the variance sums on the
+ *         way; cost; gradient quads  -- the all-reduce of the IWE and the cost are ONE launch;
+ *   K3 into this rank's partial gradient -> gradient exchange kernel: raise the gradient flag, wait, sum all ranks'
+ *         partial gradients into grad_motion (value only: flags only, which keeps the ranks in step).
+ * Flags are evaluation counters (monotonic), the two flag arrays alternate per evaluation, and that alternation is what
+ * makes re-use of the partial buffers safe without any further synchronisation.  Every rank must call with the same
+ * arguments in the same order; a rank that never arrives makes the waiting kernels trap after ~4 s. */
+typedef struct {
+  int32_t n_peers, rank;
+  const float* iwe[CMAX_MAX_PEERS];  /* rank r's partial IWE stack = its workspace + cmax_objective_iwe_offset */
+  const float* grad[CMAX_MAX_PEERS]; /* rank r's partial motion gradient (as many floats as the motion) */
+  uint32_t* flags[CMAX_MAX_PEERS];   /* rank r's flag block: 2 * CMAX_MAX_PEERS uint32, zeroed once by the caller */
+} cmax_peers;
 size_t cmax_objective_iwe_offset(const cmax_plan_t* plan);
-size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan);
-int cmax_objective_reduce_iwe(const cmax_plan_t* plan, const cmax_cost_spec* spec, const float* const* h_peer_iwe, int n_peers,
-                              const double* d_orig_stat, void* workspace, double* d_cost, int32_t* combined, const uint32_t* d_flags,
-                              const uint32_t* d_epoch, cmax_stream_t stream);
-int cmax_objective_cost_after_reduce(const cmax_plan_t* plan, const cmax_cost_spec* spec, const double* d_orig_stat, void* workspace,
-                                     int combined, int want_grad, double* d_cost, cmax_stream_t stream);
-/* out[i] = sum_r h_peer_bufs[r][i], rank order (n floats). */
-int cmax_reduce_peers(const float* const* h_peer_bufs, int n_peers, int64_t n, float* out, const uint32_t* d_flags, const uint32_t* d_epoch,
-                      cmax_stream_t stream);
-/* ---- push exchange (flags instead of barrier kernels).  Every rank owns a mailbox in symmetric memory: one slot and one
- * 32-bit flag per source rank.  cmax_push copies n floats from `src` into this rank's slot of EVERY rank's mailbox
- * (h_peer_slots[q] = address of that slot on rank q, own rank included; posted NVLink stores), fences, and its last CTA
- * stores the new epoch (*d_epoch + 1, written back to d_epoch) into this rank's flag on every rank (h_peer_flags[q]).
- * n == 0 sends the flag only.  d_counter: a zeroed uint32 the kernel uses and resets.  The consumers above take
- * (d_flags = this rank's own flag array, d_epoch): every CTA first waits until all n_peers flags have reached *d_epoch,
- * then reads LOCAL slots only (pass the local slot addresses as h_peer_iwe / h_peer_bufs).  cmax_reduce_peers with n == 0
- * just waits.  Alternating two mailboxes (IWE, gradient) per evaluation makes slot reuse safe without any barrier. */
-int cmax_push(const float* src, int64_t n, float* const* h_peer_slots, uint32_t* const* h_peer_flags, int n_peers, uint32_t* d_epoch,
-              uint32_t* d_counter, cmax_stream_t stream);
+size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan); /* where the summed IWE stack of the last evaluation sits */
+int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
+                           const double* d_orig_stat, void* workspace, const cmax_peers* peers, double* d_cost,
+                           float* grad_motion /* NULL = value only */, cmax_stream_t stream);
 
 /* Scalar combination of per-image statistics (exposed for the modular cost plugins).
  * d_stats: n_ref x 4 doubles from cmax_image_stats; h_weights: n_ref multi-focal weights (NULL = 1).

@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_header_symbols():
     for name in declared:
         assert hasattr(raw, name), f"{name} declared in include/cmax_b200.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
-    assert lib.cmax_abi_version() == 1
+    assert lib.cmax_abi_version() == _lib.ABI_VERSION == 2
     assert lib.cmax_build_arch() == b"sm_100a"
 
 

@@ -1,7 +1,6 @@
 """2-GPU parity of the sharded objective (needs >= 2 CUDA devices; skipped otherwise): contiguous event shards + the
-global time range + the two per-iteration exchanges (NCCL all-reduce, NVLink peer-memory reads behind in-stream barriers, and
-NVLink pushes into per-rank mailboxes with flags) must reproduce the
-single-GPU cost and gradient."""
+global time range + the two per-iteration exchanges (NCCL all-reduces between the stages; NVLink peer-memory reads behind
+flags inside the image / gradient-exchange kernels) must reproduce the single-GPU cost and gradient."""
 import os
 import socket
 
@@ -37,7 +36,7 @@ def _worker(rank, world, port, out):
         for cost, sigma in (("image_variance", 0.0), ("multi_focal_normalized_gradient_magnitude", 1.0)):
             full = B.ContrastObjective(ev, (H, W), cost=cost, motion_model="dense-flow", sigma=sigma)
             v_ref, g_ref = full.value_and_grad(flow)
-            for exchange in ("nccl", "peer", "push"):
+            for exchange in ("nccl", "peer"):
                 obj = make_sharded_objective(shard_events(ev, world, rank), (H, W), cost=cost, motion_model="dense-flow", sigma=sigma,
                                              exchange=exchange, orig_events=shard_events(ev, world, rank))
                 for _ in range(3):  # repeated evaluations exercise the buffer-reuse hazards of the peer exchange
