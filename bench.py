@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the contrast-maximization inner loop (BASELINE.json metric): events/s per CM iteration
-(warp + IWE + variance cost + gradient w.r.t. the dense flow) at 346x260.
+(warp + IWE + cost + gradient w.r.t. the motion).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            the B200 path (one rank per GPU under torchrun)
-  python bench.py --impl reference [--steps K] [--warmup W]       the reference algorithm on the host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2]      the B200 path (one rank per GPU under torchrun)
+  python bench.py --impl reference [--steps K] [--warmup W]               the reference algorithm on the host cores
 
-A step = one CM iteration over the resident event batch with a fresh flow field.  Workload = BASELINE config 2
-(5 M synthetic events per GPU, 260x346 dense flow, variance cost + gradient); for N > 1 every rank holds its own
-5 M-event contiguous shard (weak scaling) and the partial IWE / gradient are summed across the ranks each step
-(--exchange: NVLink peer-memory kernels behind in-stream barriers by default, NCCL all-reduce or the push exchange on request).
+A step = one CM iteration over the resident event batch with a fresh motion.  Workloads (BASELINE.json `configs`):
+  c2 (default, the configuration the metric is quoted on): 5 M synthetic events per GPU, 260x346 dense flow, variance cost
+     + gradient; for N > 1 every rank holds its own 5 M-event contiguous shard (weak scaling) and the partial IWE / gradient
+     are summed across the ranks each step (--exchange: inside the kernels over NVLink peer memory behind flags [default],
+     or NCCL all-reduces between the stages);
+  c1: 30 k events, 260x346, 2-dof translation, variance (the shipped YAML's batch size; launch-bound regime);
+  c3: 10 M events, 480x640, 16x16 tile flow -> Burgers flow voxel (T=10) -> time-aware warp, gradient-magnitude cost;
+  c4: 10 M events per GPU, 260x346, 16x16 tile flow -> Burgers voxel (T=10), the shipped multi-focal normalised
+      gradient-magnitude cost with blur (configs/mvsec_indoor_burgers.yaml), sharded like c2.
 `value` is timed on the device (CUDA events, L2 flushed before every step, the step replayed from a CUDA graph); `e2e` is the
-same step through the public API with the flow coming from pinned host memory and gradient + cost going back every step;
-`roofline` times each event kernel alone against MEASURED_PEAKS.json; `cpu_baseline` is the oracle port on the host cores.
+same step through the public API with the motion coming from pinned host memory and gradient + cost going back every step;
+`roofline` times each event kernel alone, live, against MEASURED_PEAKS.json; `parity` compares the benched evaluation with the
+CPU oracle; `plan_ms` is the one-time cost of making the batch resident (sort + packing), `value_amortised_50_iters` charges
+it to 50 CM iterations (config 2's "50 CM iters"); `sharded_vs_single` (N > 1) re-evaluates the gathered batch on one GPU.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -29,45 +36,65 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-H, W = 260, 346
+H, W = 260, 346          # config 2 (kept as module constants: scripts/ import them)
 EVENTS_PER_GPU = 5_000_000
 MAX_FLOW = 10.0          # px of displacement over the normalised window
-N_FLOWS = 8              # distinct pre-generated flow fields cycled through the steps
+N_FLOWS = 8              # distinct pre-generated motions cycled through the steps
 L2_FLUSH_BYTES = 512 << 20
-METRIC = "events/sec per CM iteration (warp+IWE+cost+grad) @346x260"
 UNIT = "events/s"
 
+CONFIGS = {
+    "c1": dict(H=260, W=346, events=30_000, model="2d-translation", cost="image_variance", sigma=0.0,
+               workload="config1: 30k events, 260x346, 2-dof translation, variance cost+grad"),
+    "c2": dict(H=260, W=346, events=5_000_000, model="dense-flow", cost="image_variance", sigma=0.0,
+               workload="config2: 5M events per GPU, 260x346 dense flow, variance cost+grad"),
+    "c3": dict(H=480, W=640, events=10_000_000, model="time-aware", cost="gradient_magnitude", sigma=0.0, T=10, window=(30, 40),
+               workload="config3: 10M events, 480x640, 16x16 tile flow -> Burgers voxel T=10 -> time-aware warp, gradient-magnitude cost+grad"),
+    "c4": dict(H=260, W=346, events=10_000_000, model="time-aware", cost="multi_focal_normalized_gradient_magnitude", sigma=1.0, T=10,
+               window=(16, 21),
+               workload="config4: 10M events per GPU, 260x346, 16x16 tile flow -> Burgers voxel T=10, multi-focal normalised "
+                        "gradient magnitude (3 reference times, blur sigma 1: configs/mvsec_indoor_burgers.yaml), sharded"),
+}
 
-def synth_events(n: int, seed: int) -> np.ndarray:
+
+def metric_name(cfg) -> str:
+    return f"events/sec per CM iteration (warp+IWE+cost+grad) @{cfg['W']}x{cfg['H']}"
+
+
+def synth_events(n: int, seed: int, h: int = H, w: int = W) -> np.ndarray:
     """The reference's own fixture (src/utils/event_utils.py:18-47), seeded: integer pixel coordinates, sorted
     uniform timestamps in [0, 0.05), random polarity; fp32 [n,4] = (x=row, y=col, t, p)."""
     rng = np.random.default_rng(seed)
     ev = np.empty((n, 4), dtype=np.float32)
-    ev[:, 0] = rng.integers(0, H, n)
-    ev[:, 1] = rng.integers(0, W, n)
+    ev[:, 0] = rng.integers(0, h, n)
+    ev[:, 1] = rng.integers(0, w, n)
     ev[:, 2] = np.sort(rng.uniform(0.0, 0.05, n))
     ev[:, 3] = rng.integers(0, 2, n)
     return ev
 
 
-def synth_flows(k: int, seed: int) -> np.ndarray:
+def synth_flows(k: int, seed: int, h: int = H, w: int = W) -> np.ndarray:
     """Smooth flows as the pyramid produces at its finest scale: a 16x16 patch grid, bilinearly up-sampled
     (SURVEY.md section 8d), |flow| <= MAX_FLOW."""
     import torch
     rng = np.random.default_rng(seed)
     grid = torch.from_numpy(rng.uniform(-MAX_FLOW, MAX_FLOW, (k, 2, 16, 16)).astype(np.float32))
-    return torch.nn.functional.interpolate(grid, size=(H, W), mode="bilinear", align_corners=False).numpy()
+    return torch.nn.functional.interpolate(grid, size=(h, w), mode="bilinear", align_corners=False).numpy()
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two event kernels at this workload, from the
-# committed `ncu --set full` capture profiles/r01_ncu_r1o.txt (strip kernels) / r01_ncu_r1k.txt (run kernels)
-TRAFFIC_SOURCE = "profiles/r01_ncu_r1o.txt (strips) / r01_ncu_r1k.txt (runs): dram__bytes_read.sum + dram__bytes_write.sum per launch"
-_TRAFFIC = {"K1 vote (vote_strips_kernel)": 26.09e6, "K3 grad (grad_strips_kernel)": 26.81e6,
-            "K1 vote (vote_runs_kernel)": 42.18e6, "K3 grad (grad_runs_kernel)": 42.91e6}
+def synth_motions(cfg, k: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    if cfg["model"] == "dense-flow":
+        return synth_flows(k, seed, cfg["H"], cfg["W"])
+    if cfg["model"] == "2d-translation":
+        return rng.uniform(-20, 20, (k, 2)).astype(np.float32)
+    return rng.uniform(-MAX_FLOW, MAX_FLOW, (k, 2, 16, 16)).astype(np.float32)  # tile motion of the time-aware configurations
 
 
-def traffic_of(kernel: str):
-    return _TRAFFIC.get(kernel)
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the event kernels, from the committed `ncu --set full`
+# captures under profiles/ (config 2 only; other configurations report traffic null)
+TRAFFIC_SOURCE = "profiles/r02_ncu_r2a.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch"
+_TRAFFIC = {"K1 vote (vote_strips_kernel)": 26.09e6, "K3 grad (grad_strips_kernel)": 26.81e6}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -118,21 +145,36 @@ class ClockSampler(threading.Thread):
         return out
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_steps(ev_np: np.ndarray, flows_np: np.ndarray, steps: int, warmup: int):
-    """The reference's algorithm for this path (torch CPU branch: warp -> bilinear vote -> variance -> autograd
-    gradient), restated in oracle/cm_oracle.py and pinned to the reference's outputs by tests/test_oracle_golden.py.
-    fp32, all host threads.  Returns (seconds per step list, threads)."""
+# ------------------------------------------------------------------------------------------------ the CPU oracle leg
+def oracle_value_and_grad(cfg, ev, motion, dtype):
+    """One CM evaluation of configuration `cfg` with the CPU oracle (oracle/cm_oracle.py = the reference's torch branch,
+    pinned to the reference's own outputs by tests/test_oracle_golden.py).  -> (cost, gradient w.r.t. `motion`)."""
     import torch
     from oracle import cm_oracle as O
+    ev = ev.to(dtype)
+    m = motion.to(dtype)
+    size = (cfg["H"], cfg["W"])
+    if cfg["model"] != "time-aware":
+        return O.objective_value_and_grad(ev, m, size, motion_model=cfg["model"], cost=cfg["cost"], sigma=cfg["sigma"])
+    m = m.detach().clone().requires_grad_(True)
+    dense = O.upsample_tile_flow(m, size, cfg["window"], cfg["window"], (0, 0))
+    voxel = O.flow_voxel(dense, cfg["T"], "burgers", "middle")
+    value = O.objective(ev, voxel, size, motion_model="dense-flow-voxel", cost=cfg["cost"], sigma=cfg["sigma"])
+    (grad,) = torch.autograd.grad(value, m)
+    return value.detach(), grad
+
+
+def cpu_reference_steps(cfg, ev_np: np.ndarray, motions_np: np.ndarray, steps: int, warmup: int):
+    """fp32, all host threads.  Returns (seconds per step list, threads)."""
+    import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     ev = torch.from_numpy(ev_np)
     times = []
     for i in range(warmup + steps):
-        flow = torch.from_numpy(flows_np[i % len(flows_np)])
+        m = torch.from_numpy(motions_np[i % len(motions_np)])
         t0 = time.perf_counter()
-        val, grad = O.objective_value_and_grad(ev, flow, (H, W), motion_model="dense-flow", cost="image_variance")
+        val, _ = oracle_value_and_grad(cfg, ev, m, torch.float32)
         float(val)
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -140,22 +182,29 @@ def cpu_reference_steps(ev_np: np.ndarray, flows_np: np.ndarray, steps: int, war
     return times, threads
 
 
+def reference_sample(cfg) -> int:
+    """Events of one CPU step: the whole batch where the oracle finishes in seconds, else a bounded sample."""
+    return min(cfg["events"], 5_000_000 if cfg["model"] != "time-aware" else 1_000_000)
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = EVENTS_PER_GPU
-    ev = synth_events(n, seed=0)
-    flows = synth_flows(N_FLOWS, seed=100)
-    times, threads = cpu_reference_steps(ev, flows, args.steps, args.warmup)
+    cfg = CONFIGS[args.config]
+    n = reference_sample(cfg)
+    ev = synth_events(n, 0, cfg["H"], cfg["W"])
+    motions = synth_motions(cfg, N_FLOWS, seed=100)
+    times, threads = cpu_reference_steps(cfg, ev, motions, args.steps, args.warmup)
     sec = float(np.mean(times))
     value = n / sec
-    sample = f"{n} events (one full config-2 batch) per step, fp32, torch CPU ops, {threads} threads"
+    whole = "the full batch" if n == cfg["events"] else f"a bounded sample of the {cfg['events']}-event batch"
+    sample = f"{n} events per step ({whole}), fp32, torch CPU ops, {threads} threads"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "config2: 5M events, 260x346 dense flow, variance cost+grad", "events": n, "image": [H, W]},
+        "config": {"workload": cfg["workload"], "events": n, "image": [cfg["H"], cfg["W"]]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -164,10 +213,37 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def build_objective(cfg, ev, group, t_range, args):
+    """-> (callable step_into(motion, cost, grad), the ContrastObjective, shape of the motion)."""
+    from event_based_optical_flow_b200 import ContrastObjective, TimeAwareObjective
+    size = (cfg["H"], cfg["W"])
+    if cfg["model"] != "time-aware":
+        obj = ContrastObjective(ev, size, cost=cfg["cost"], motion_model=cfg["model"], sigma=cfg["sigma"], order=args.order,
+                                process_group=group, t_range=t_range, exchange=args.exchange)
+        return obj.step_into, obj, obj.motion_shape
+    obj = ContrastObjective(ev, size, cost=cfg["cost"], motion_model="dense-flow-voxel", n_bins=cfg["T"], sigma=cfg["sigma"],
+                            order=args.order, process_group=group, t_range=t_range, exchange=args.exchange, orig_events=ev)
+    tobj = TimeAwareObjective(obj, scheme="burgers", t0_location="middle",
+                              tile=dict(patch_size=cfg["window"], sliding_window=cfg["window"], patch_shift=(0, 0)))
+    return tobj.step_into, obj, (2, 16, 16)
+
+
+def algorithmic_bytes(cfg, n, k_ref):
+    """per CM iteration, and per launch of K1 / K3."""
+    HW = cfg["H"] * cfg["W"]
+    if cfg["model"] == "time-aware":
+        T = cfg["T"]
+        return {"step": 32 * n + (16 * T + 16 * k_ref) * HW, "K1": 16 * n + (8 * T + 4 * k_ref) * HW, "K3": 16 * n + (16 * T + 4 * k_ref) * HW}
+    if cfg["model"] == "2d-translation":
+        return {"step": 32 * n + 16 * k_ref * HW, "K1": 16 * n + 4 * k_ref * HW, "K3": 16 * n + 4 * k_ref * HW}
+    return {"step": 32 * n + (16 + 16 * k_ref) * HW, "K1": 16 * n + (8 + 4 * k_ref) * HW, "K3": 16 * n + (16 + 4 * k_ref) * HW}
+
+
 def run_b200(args) -> None:
     import torch
     import torch.distributed as dist
 
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,24 +259,38 @@ def run_b200(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from event_based_optical_flow_b200 import ContrastObjective, _lib
+    from event_based_optical_flow_b200 import EventPlan, _lib
     from event_based_optical_flow_b200.distributed import global_time_range
     _lib.load()
 
-    n = EVENTS_PER_GPU
-    ev_np = synth_events(n, seed=rank)            # rank r's contiguous shard of the N*5M-event stream
-    ev_np[:, 2] = (ev_np[:, 2] + 0.05 * rank)     # shards are consecutive in time
-    flows_np = synth_flows(N_FLOWS, seed=100)     # identical on every rank (the flow is replicated)
+    Hc, Wc_ = cfg["H"], cfg["W"]
+    n = cfg["events"]
+    ev_np = synth_events(n, seed=rank, h=Hc, w=Wc_)   # rank r's contiguous shard of the N*n-event stream
+    ev_np[:, 2] = (ev_np[:, 2] + 0.05 * rank)        # shards are consecutive in time
+    motions_np = synth_motions(cfg, N_FLOWS, seed=100)  # identical on every rank (the motion is replicated)
     ev = torch.from_numpy(ev_np).to(dev)
-    flows = torch.from_numpy(flows_np).to(dev)
+    motions = torch.from_numpy(motions_np).to(dev)
     group = dist.group.WORLD if world > 1 else None
     t_range = global_time_range(ev, group)
-    obj = ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow", sigma=0.0, order=args.order,
-                            process_group=group, t_range=t_range, exchange=args.exchange)
+
+    # ---- one-time cost of making the batch resident (validation, sort, strips): host wall clock around plan creation,
+    # which ends with the plan's single stream synchronisation
+    plan_times = []
+    for _ in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        probe_plan = EventPlan(ev, (Hc, Wc_), 0, args.order, t_range)
+        torch.cuda.synchronize()
+        plan_times.append((time.perf_counter() - t0) * 1e3)
+        probe_plan.close()
+        del probe_plan
+    plan_ms = float(np.min(plan_times[1:]))
+
+    step_into, obj, motion_shape = build_objective(cfg, ev, group, t_range, args)
     if args.vote_variant >= 0 or args.grad_variant >= 0:  # default: what the plan chose (strip kernels when the batch qualifies)
         obj.plan.set_variant(args.vote_variant if args.vote_variant >= 0 else 5, args.grad_variant if args.grad_variant >= 0 else 5)
     compact = obj.plan.set_compact(not args.no_compact)
-    strips = args.vote_variant in (-1, 5) and args.grad_variant in (-1, 5) and args.order == "pixel"  # (dense synthetic batch: the plan builds strips)
+    strips = obj.plan.n_strips > 0 and args.vote_variant in (-1, 5) and args.grad_variant in (-1, 5)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     flush_rd = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.int32, device=dev)
 
@@ -210,44 +300,38 @@ def run_b200(args) -> None:
         step that follows."""
         flush.zero_()
         flush_rd.sum()
+    n_motion = int(np.prod(motion_shape))
     cost_buf = torch.zeros(1, dtype=torch.float64, device=dev)
-    grad_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
-    flow_buf = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
+    grad_buf = torch.zeros(motion_shape, dtype=torch.float32, device=dev)
+    motion_buf = torch.zeros(motion_shape, dtype=torch.float32, device=dev)
 
-    # one CM iteration, captured once in a CUDA graph: single GPU = 4 kernel nodes; sharded = 5 kernels + 2 NCCL
-    # all-reduces (NCCL is capturable; every rank captures the same sequence)
+    # one CM iteration, captured once in a CUDA graph (sharded: the flag exchange lives inside the kernels, NCCL is capturable)
     graph = None
     if not args.no_graph:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
-                obj.step_into(flow_buf, cost_buf, grad_buf)
+                step_into(motion_buf, cost_buf, grad_buf)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            obj.step_into(flow_buf, cost_buf, grad_buf)
-
-    def step(i: int):
-        if graph is not None:
-            flow_buf.copy_(flows[i % N_FLOWS])  # outside the timed bracket: the flow is "already resident"
-            return None
-        return flows[i % N_FLOWS]
+            step_into(motion_buf, cost_buf, grad_buf)
 
     def run_steps(count: int, first: int):
         """-> per-step device milliseconds (CUDA events on the launching stream), L2 flushed before every step."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
         for k in range(count):
-            f = step(first + k)
+            motion_buf.copy_(motions[(first + k) % N_FLOWS])  # outside the timed bracket: the motion is "already resident"
             flush_l2()
             evs[k][0].record()
             if graph is not None:
                 graph.replay()
             else:
-                c, g = obj.value_and_grad(f)
+                step_into(motion_buf, cost_buf, grad_buf)
             evs[k][1].record()
         torch.cuda.synchronize()
         return [a.elapsed_time(b) for a, b in evs]
@@ -274,16 +358,14 @@ def run_b200(args) -> None:
     # ---- end to end through the public API: per step the motion comes from pinned host memory (what scipy hands
     # over, scipy_autograd/torch_wrapper.py:33-36) and cost + gradient go back to the host (:46-49).  Events stay
     # resident, as in the reference (patch_contrast_pyramid.py:186 moves them once per optimize()).
-    host_flows = [torch.from_numpy(flows_np[i]).pin_memory() for i in range(N_FLOWS)]
-    host_grad = torch.empty(2, H, W, dtype=torch.float32).pin_memory()
-    host_cost = torch.empty(1, dtype=torch.float64).pin_memory()
-
+    host_motions = [torch.from_numpy(motions_np[i]).pin_memory() for i in range(N_FLOWS)]
     # one device block [gradient | cost] so that the result goes back to the host in ONE copy
-    out_dev = torch.zeros(2 * H * W + 2, dtype=torch.float32, device=dev)
-    out_host = torch.empty(2 * H * W + 2, dtype=torch.float32).pin_memory()
-    e2e_grad = out_dev[:2 * H * W].view(2, H, W)
-    e2e_cost = out_dev[2 * H * W:].view(torch.float64)
-    e2e_flow = torch.zeros(2, H, W, dtype=torch.float32, device=dev)
+    n_pad = (n_motion + 1) // 2 * 2
+    out_dev = torch.zeros(n_pad + 2, dtype=torch.float32, device=dev)
+    out_host = torch.empty(n_pad + 2, dtype=torch.float32).pin_memory()
+    e2e_grad = out_dev[:n_motion].view(motion_shape)
+    e2e_cost = out_dev[n_pad:].view(torch.float64)
+    e2e_motion = torch.zeros(motion_shape, dtype=torch.float32, device=dev)
 
     def e2e_steps(count: int):
         """Host wall-clock of `count` end-to-end steps.  The L2 flush (hygiene, not part of a step) is enqueued and waited
@@ -293,9 +375,9 @@ def run_b200(args) -> None:
             flush_l2()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            e2e_flow.copy_(host_flows[k % N_FLOWS], non_blocking=True)   # H2D from pinned host memory
-            obj.step_into(e2e_flow, e2e_cost, e2e_grad)                  # the allocation-free public entry point
-            out_host.copy_(out_dev, non_blocking=True)                   # D2H: gradient + cost
+            e2e_motion.copy_(host_motions[k % N_FLOWS], non_blocking=True)   # H2D from pinned host memory
+            step_into(e2e_motion, e2e_cost, e2e_grad)                        # the allocation-free public entry point
+            out_host.copy_(out_dev, non_blocking=True)                       # D2H: gradient + cost
             torch.cuda.synchronize()
             total += time.perf_counter() - t0
         return total
@@ -309,12 +391,42 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * n * args.steps / e2e_s
-    h2d = int(host_flows[0].numel() * 4)
+    h2d = int(host_motions[0].numel() * 4)
     d2h = int(out_host.numel() * 4)
+
+    # ---- sharded vs single GPU: rank 0 gathers every shard, evaluates the whole batch on its own GPU and compares
+    sharded_check = None
+    if world > 1:
+        motion_buf.copy_(motions[0])
+        step_into(motion_buf, cost_buf, grad_buf)
+        torch.cuda.synchronize()
+        grads = [torch.empty_like(grad_buf) for _ in range(world)]
+        costs = [torch.empty_like(cost_buf) for _ in range(world)]
+        dist.all_gather(grads, grad_buf)
+        dist.all_gather(costs, cost_buf)
+        shards = [torch.empty_like(ev) for _ in range(world)] if rank == 0 else None
+        dist.gather(ev, shards, dst=0)
+        if rank == 0:
+            args_single = argparse.Namespace(**{**vars(args), "exchange": "nccl"})
+            full_ev = torch.cat(shards)
+            del shards
+            single_step, single_obj, _ = build_objective(cfg, full_ev, None, None, args_single)
+            c1 = torch.zeros_like(cost_buf)
+            g1 = torch.zeros_like(grad_buf)
+            single_step(motion_buf, c1, g1)
+            torch.cuda.synchronize()
+            sharded_check = {
+                "cost_rel": abs(float(cost_buf) - float(c1)) / abs(float(c1)),
+                "grad_rel": float(torch.linalg.norm(grad_buf.double() - g1.double()) / torch.linalg.norm(g1.double())),
+                "all_ranks_bit_equal": bool(all(torch.equal(grads[0], g) for g in grads) and all(torch.equal(costs[0], c) for c in costs)),
+                "tolerance": 1e-5,
+                "what": f"rank 0 gathered the {world} shards ({world * n} events) and evaluated them on one GPU with the same motion",
+            }
+            del single_obj, full_ev
+        dist.barrier()
 
     line = None
     if rank == 0:
-        # ---- roofline of the dominant kernels, each timed alone with CUDA events (stage mask = event kernel only)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -322,17 +434,27 @@ def run_b200(args) -> None:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        HWp = H * W
+        k_ref = len(obj.directions)
+        ab = algorithmic_bytes(cfg, n, k_ref)
         kernels = {}
+        stage_ms = None
         if world == 1:
-            from event_based_optical_flow_b200 import _lib as L
+            # ---- roofline of the two event kernels, each timed alone, live, with CUDA events: the staged entry points enqueue
+            # exactly the kernels of the fused call (vote = K1 alone, grad(pre_zeroed) = K3 alone)
             import ctypes as C
-            obj.value_and_grad(flows[0])  # leave a consistent workspace behind
+            L = _lib
+            model = L.MOTION[obj.motion_model]
+            if cfg["model"] == "time-aware":
+                from event_based_optical_flow_b200 import ops
+                pad = ops.tile_flow_geometry((Hc, Wc_), cfg["window"], cfg["window"], (0, 0))
+                m = ops.flow_voxel(ops.tile_flow_upsample(motions[1], (Hc, Wc_), pad, cfg["window"]), cfg["T"], "burgers", "middle")
+            else:
+                m = motions[1].contiguous()
+            gk = torch.zeros(obj.motion_shape, dtype=torch.float32, device=dev)
+            obj.value_and_grad(m)  # leave a consistent workspace behind
             stream = torch.cuda.current_stream().cuda_stream
-            m = flows[1].contiguous()
             spec_p = C.byref(obj.spec)
-            ng = grad_buf.numel()
-            # the staged entry points enqueue exactly the kernels of the fused call: vote = K1 alone, grad(pre_zeroed) = K3 alone
+            orig = obj._orig_stat.data_ptr() if obj._orig_stat is not None else None
 
             def time_kernel(fn, reps=20):
                 out = []
@@ -348,72 +470,111 @@ def run_b200(args) -> None:
 
             def fold_and_cost():
                 L.call("cmax_objective_fold", obj.plan.handle, obj._ws_ptr, None, stream)
-                L.call("cmax_objective_cost", obj.plan.handle, spec_p, None, obj._ws_ptr, 1, cost_buf.data_ptr(), grad_buf.data_ptr(), ng, stream)
+                L.call("cmax_objective_cost", obj.plan.handle, spec_p, orig, obj._ws_ptr, 1, cost_buf.data_ptr(), gk.data_ptr(), gk.numel(), stream)
 
-            k1 = time_kernel(lambda: L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, stream))
+            def vote():
+                L.call("cmax_objective_vote", obj.plan.handle, model, m.data_ptr(), obj._ws_ptr, stream)
+
+            def grad():
+                L.call("cmax_objective_grad", obj.plan.handle, model, m.data_ptr(), obj._ws_ptr, gk.data_ptr(), 1, stream)
+
+            k1 = time_kernel(vote)
             fold_and_cost()
-            k3 = time_kernel(lambda: L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), 1, stream))
+            k3 = time_kernel(grad)
             # in-situ stage times of one eager iteration (L2 flushed before the iteration only): K1 | fold + cost | K3
-            stage_ms = np.zeros(3)
+            stage = np.zeros(3)
             for rep in range(13):
                 flush_l2()
                 e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
                 e[0].record()
-                L.call("cmax_objective_vote", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, stream)
+                vote()
                 e[1].record()
                 fold_and_cost()
                 e[2].record()
-                L.call("cmax_objective_grad", obj.plan.handle, 0, m.data_ptr(), obj._ws_ptr, grad_buf.data_ptr(), 1, stream)
+                grad()
                 e[3].record()
                 torch.cuda.synchronize()
                 if rep >= 3:
-                    stage_ms += [e[i].elapsed_time(e[i + 1]) for i in range(3)]
-            stage_ms /= 10
-            # algorithmic bytes per launch (DESIGN.md "Kernels"): K1 = 16 B/event + flow read 8 HW + IWE write 4 HW;
-            # K3 = 16 B/event + flow read 8 HW + dL/dIWE read 4 HW + gradient write 8 HW
-            kernels = {"K1 vote (vote_strips_kernel)" if strips else "K1 vote (vote_runs_kernel)": {"ms": k1, "bytes": 16 * n + 12 * HWp},
-                       "K3 grad (grad_strips_kernel)" if strips else "K3 grad (grad_runs_kernel)": {"ms": k3, "bytes": 16 * n + 20 * HWp}}
+                    stage += [e[i].elapsed_time(e[i + 1]) for i in range(3)]
+            stage /= 10
+            stage_ms = {"vote(K1)": stage[0], "fold+cost(image kernel launches, staged API)": stage[1], "grad(K3)": stage[2]}
+            kind = "strips" if strips else "runs"
+            kernels = {f"K1 vote (vote_{kind}_kernel)": {"ms": k1, "bytes": ab["K1"]}, f"K3 grad (grad_{kind}_kernel)": {"ms": k3, "bytes": ab["K3"]}}
             for v in kernels.values():
                 v["GBps"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
-        step_bytes = 32 * n + 32 * HWp  # per CM iteration, single reference time, dense flow
-        step_gbps = step_bytes / (ms_per_step * 1e-3) / 1e9
+        step_gbps = ab["step"] / (ms_per_step * 1e-3) / 1e9
         if kernels:
             dom = max(kernels, key=lambda k: kernels[k]["ms"])
             roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[dom]["GBps"] / peak, "traffic": traffic_of(dom), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
-                    "kernels": kernels, "stages_in_situ_ms": {"vote(K1)": stage_ms[0], "fold+cost(2 image-kernel launches, staged API)": stage_ms[1],
-                                                              "grad(K3)": stage_ms[2]}, "step": {"bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak}}
+                    "frac": kernels[dom]["GBps"] / peak, "traffic": _TRAFFIC.get(dom) if args.config == "c2" else None,
+                    "traffic_source": TRAFFIC_SOURCE if args.config == "c2" else None, "peak_source": peak_src,
+                    "kernels": kernels, "stages_in_situ_ms": stage_ms,
+                    "step": {"bytes": ab["step"], "achieved": step_gbps, "frac": step_gbps / peak}}
         else:
             roof = {"bound": "hbm", "kernel": "whole CM iteration (per GPU)", "achieved": step_gbps, "peak": peak, "unit": "GB/s",
                     "frac": step_gbps / peak, "traffic": None, "peak_source": peak_src}
 
-        # ---- CPU baseline: the oracle port of the reference algorithm on this box's host cores, bounded sample
-        cpu = None
+        # ---- parity with the CPU oracle on the benched batch (time-aware configurations: a bounded sample) and the CPU baseline
+        cpu = parity = None
         if world == 1 and not args.skip_cpu:
-            times, threads = cpu_reference_steps(synth_events(n, seed=0), flows_np, steps=5, warmup=1)
-            cpu = {"value": n / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"5 timed + 1 warm-up CM iterations over the full {n}-event config-2 batch, fp32 torch CPU ops"}
+            n_cpu = reference_sample(cfg)
+            ev_cpu = synth_events(n_cpu, 0, Hc, Wc_) if n_cpu != n else ev_np
+            m0 = torch.from_numpy(motions_np[0])
+            pobj = None
+            if n_cpu != n:
+                pstep, pobj, _ = build_objective(cfg, torch.from_numpy(ev_cpu).to(dev), None, None, args)
+            else:
+                pstep = step_into
+            c_gpu = torch.zeros(1, dtype=torch.float64, device=dev)
+            g_gpu = torch.zeros(motion_shape, dtype=torch.float32, device=dev)
+            pstep(m0.to(dev), c_gpu, g_gpu)
+            torch.cuda.synchronize()
+            del pobj
+            torch.set_num_threads(os.cpu_count() or 1)
+            v64, g64 = oracle_value_and_grad(cfg, torch.from_numpy(ev_cpu), m0, torch.float64)
+            v32, g32 = oracle_value_and_grad(cfg, torch.from_numpy(ev_cpu), m0, torch.float32)
+            parity = {
+                "cost_rel_vs_fp64_oracle": abs(float(c_gpu) - float(v64)) / abs(float(v64)),
+                "grad_rel_vs_fp32_oracle": float(torch.linalg.norm(g_gpu.cpu().double() - g32.double()) / torch.linalg.norm(g32.double())),
+                "grad_rel_vs_fp64_oracle": float(torch.linalg.norm(g_gpu.cpu().double() - g64) / torch.linalg.norm(g64)),
+                "fp32_oracle_grad_rel_vs_fp64_oracle": float(torch.linalg.norm(g32.double() - g64) / torch.linalg.norm(g64)),
+                "tolerance": 1e-5, "events": n_cpu,
+                "what": "cost vs the fp64 oracle, gradient norm-wise vs the same-dtype (fp32) oracle; the fp64 rows show how far "
+                        "fp32 itself is from fp64 (the gradient is discontinuous where a floor index flips)",
+            }
+            times, threads = cpu_reference_steps(cfg, ev_cpu, motions_np, steps=3 if cfg["model"] == "time-aware" else 5, warmup=1)
+            cpu = {"value": n_cpu / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"{len(times)} timed + 1 warm-up CM iterations over {n_cpu} events "
+                             f"({'the full batch' if n_cpu == n else 'a bounded sample of the batch'}), fp32 torch CPU ops"}
 
         clocks = sampler.finish() if sampler else None
-        # K1 vote, image kernel (fold + variance + cost + gradient quads), K3 grad; sharded "peer": + the gradient-exchange
-        # kernel (the IWE exchange lives inside the image kernel); "nccl": K1, fold, cost, K3 (+ 2 NCCL all-reduces)
-        per_step_kernels = 3 if world == 1 else {'peer': 4, 'nccl': 4}[args.exchange]
+        if cfg["model"] == "time-aware":
+            per_step_kernels = None  # tile upsample, voxel propagation, K1, image-side chain, K3, the two adjoints: see profiles/
+        else:
+            # K1 vote, image kernel (fold + variance + cost + gradient quads), K3 grad; sharded "peer": + the gradient-exchange
+            # kernel (the IWE exchange lives inside the image kernel); "nccl": K1, fold, cost, K3 (+ 2 NCCL all-reduces)
+            per_step_kernels = (3 if world == 1 else 4) + (1 if cfg["model"] == "2d-translation" else 0)
+        amortised_ms = ms_per_step + plan_ms / 50.0
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "config2: 5M events per GPU, 260x346 dense flow, variance cost+grad", "events_per_gpu": n,
-                       "image": [H, W], "flow": "smooth (16x16 grid upsampled), |f|<=10px, fresh per step",
-                       "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16), "vote_variant": args.vote_variant, "grad_variant": args.grad_variant,
-                       "cuda_graph": graph is not None, "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
+            "config": {"workload": cfg["workload"], "events_per_gpu": n, "image": [Hc, Wc_],
+                       "motion": {"dense-flow": "smooth dense flow (16x16 grid upsampled), |f|<=10px, fresh per step",
+                                  "2d-translation": "2-dof translation, |theta|<=20px, fresh per step",
+                                  "time-aware": "16x16 tile motion, |f|<=10px, fresh per step"}[cfg["model"]],
+                       "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16),
+                       "vote_variant": args.vote_variant, "grad_variant": args.grad_variant, "cuda_graph": graph is not None,
+                       "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
                                        {"nccl": "NCCL all-reduce",
                                         "peer": "NVLink peer-memory reads behind in-kernel flags (no collective, no barrier kernel)"}[args.exchange])
                        if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "what": "host pinned flow -> device, ContrastObjective.step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
-            "gpu_launches": per_step_kernels * args.steps,
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                    "what": "host pinned motion -> device, step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
+            "gpu_launches": per_step_kernels * args.steps if per_step_kernels else None,
+            "plan_ms": plan_ms, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
+            "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
         }
     if line is not None:
         print(json.dumps(line), flush=True)
@@ -436,6 +597,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c2", help="BASELINE.json configuration (default: c2, the one the metric is quoted on)")
     ap.add_argument("--order", choices=("asis", "tile", "pixel"), default="pixel")
     ap.add_argument("--vote-variant", type=int, default=-1, help="-1 = the plan's choice (5 = strip kernels when the batch qualifies, else 2)")
     ap.add_argument("--grad-variant", type=int, default=-1)
@@ -443,7 +605,7 @@ def main():
     ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
     ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer",
                     help="multi-GPU: NCCL all-reduces between the stages, or NVLink peer reads behind flags inside the kernels")
-    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (used under ncu)")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the parity / cpu_baseline legs (used under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -16,7 +16,9 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200.so")
 SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_mid.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu")
 HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", "cmax_runs.cuh", "cmax_objective.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
-NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+# CMAX_MEASURE=1 in the environment of the BUILD compiles the measurement aids in (partial stage masks, CMAX_PDL=0, phase
+# stamps of the image kernel); the release build has none of them, so nothing in a process's environment can change its results
+NVCC_FLAGS = (*(("-DCMAX_MEASURE",) if os.environ.get("CMAX_MEASURE") else ()), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared")
 
 

@@ -16,9 +16,22 @@ logger = logging.getLogger(__name__)
 
 
 def _stat(iwe: torch.Tensor, stat: str, omit_boundary: bool) -> torch.Tensor:
-    if iwe.dim() == 3:  # batch of images -> the reference reduces over everything only for 2-D; keep per-call scalars
-        return torch.stack([ops.ImageStatFunction.apply(i, stat, bool(omit_boundary)) for i in iwe]).mean()
-    return ops.ImageStatFunction.apply(iwe, stat, bool(omit_boundary))
+    """Statistic of one image [H,W] or of a batch [b,H,W].  The reference reduces over the WHOLE batch: `torch.var(iwe)` after
+    the crop (src/costs/image_variance.py:52-58) is the pooled unbiased variance, `torch.mean(gx^2 + gy^2)`
+    (src/costs/gradient_magnitude.py:67-76) the mean of the per-image means."""
+    omit = bool(omit_boundary)
+    if iwe.dim() == 2:
+        return ops.ImageStatFunction.apply(iwe, stat, omit)
+    per_image = torch.stack([ops.ImageStatFunction.apply(i, stat, omit) for i in iwe])
+    if stat != "variance" or iwe.shape[0] == 1:
+        return per_image.mean()
+    # pooled variance from the per-image (unbiased variance, mean, M): within-image + between-image sums of squares
+    crop = iwe[..., 1:-1, 1:-1] if omit else iwe
+    b, m = crop.shape[0], crop.shape[-2] * crop.shape[-1]
+    means = crop.mean(dim=(-2, -1))
+    within = (m - 1) * per_image.sum()
+    between = m * ((means - means.mean()) ** 2).sum()
+    return (within + between) / (b * m - 1)
 
 
 class ImageVariance(CostBase):

@@ -29,9 +29,9 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -62,8 +62,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_c
     __threadfence();
     atomicAdd(bar, 1u);
     if (wait) {
-      while (ld_acquire_gpu(bar) < n_ctas) {
+      while (ld_relaxed_gpu(bar) < n_ctas) {  // (an acquire load per poll would invalidate the L1 every time)
       }
+      __threadfence();
     }
   }
   __syncthreads();
@@ -89,6 +90,7 @@ struct ImageArgs {
   double* slots;        // [gridDim.x][n_ref][2] partial sums
   unsigned int* bar;    // [0] arrivals after the fold (sharded), [1] arrivals after the statistics
   double* stats_out;    // [n_ref][4]
+  double inv_M, inv_Mm1;  // 1 / M and 1 / (M - 1), M = pixels the statistic runs over
   CombineDev cd;
   PeerEx px;
 };
@@ -96,75 +98,124 @@ struct ImageArgs {
 // IWE[r,c] = acc[r,c].x + acc[r-1,c].y + acc[r,c-1].z + acc[r-1,c-1].w.  Every scalar component of every accumulator
 // cell has exactly ONE reader, which also zeroes it: the accumulators are clean again for the next CM iteration and no
 // memset is ever enqueued (components no pixel reads only collect votes of out-of-image corners and are never looked at).
-__device__ __forceinline__ float fold_pixel(float* __restrict__ A, int r, int c, int Wc) {
-  const int64_t k = (int64_t)(r + 1) * Wc + (c + 1);
-  float* a00 = A + 4 * k;                 // .x of cell (r, c)
-  float* a10 = A + 4 * (k - Wc) + 1;      // .y of cell (r-1, c)
-  float* a01 = A + 4 * (k - 1) + 2;       // .z of cell (r, c-1)
-  float* a11 = A + 4 * (k - Wc - 1) + 3;  // .w of cell (r-1, c-1)
-  const float v = ((*a00 + *a10) + *a01) + *a11;
-  *a00 = 0.f;
-  *a10 = 0.f;
-  *a01 = 0.f;
-  *a11 = 0.f;
-  return v;
+struct FoldAddr {
+  float *a00, *a10, *a01, *a11;
+};
+__device__ __forceinline__ FoldAddr fold_addr(float* __restrict__ A, unsigned r, unsigned c, unsigned Wc) {
+  const unsigned k = (r + 1u) * Wc + (c + 1u);
+  FoldAddr f;
+  f.a00 = A + 4u * k;                  // .x of cell (r, c)
+  f.a10 = A + 4u * (k - Wc) + 1u;      // .y of cell (r-1, c)
+  f.a01 = A + 4u * (k - 1u) + 2u;      // .z of cell (r, c-1)
+  f.a11 = A + 4u * (k - Wc - 1u) + 3u;  // .w of cell (r-1, c-1)
+  return f;
 }
 
+// The kernel is LATENCY bound (a 90 k-pixel image over 148 SMs is one or two pixels per thread), so what counts is the
+// length of the dependent chain per phase: 32-bit index arithmetic only (a 64-bit division is ~150 dependent instructions),
+// all loads of a thread issued before the first use, statistics reduced by one warp, one grid-wide barrier.
+template <bool SHARDED>
 __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
-  __shared__ double red[kMidThreads / 32];
+  constexpr int kWarps = kMidThreads / 32;
+  __shared__ double red[2][kWarps];
   __shared__ double sh_stats[4 * CMAX_MAX_REFS];
   __shared__ double sh_cost;
   __shared__ float sh_aff[2 * CMAX_MAX_REFS];
   __shared__ uint32_t sh_epoch;
+#ifdef CMAX_MEASURE  // measurement builds: per-CTA globaltimer stamps of the phases (scripts/image_probe.py)
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.slots) + 2048 + blockIdx.x * 8;
+#define STAMP(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[i] = t_; } } while (0)
+#else
+#define STAMP(i)
+#endif
+  STAMP(0);
   pdl_trigger();  // K3 may be scheduled (it prefetches its first event tile, then waits for this grid to complete)
   pdl_wait();     // K1's reductions are complete and visible
-  const int64_t HW = (int64_t)a.Hp * a.Wp;
-  const int Wc = a.Wp + 1;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-  const int64_t M = a.omit ? (int64_t)(a.Hp - 2) * (a.Wp - 2) : HW;
-  const bool sharded = a.px.n > 0;
+  STAMP(1);
+  const unsigned Hp = (unsigned)a.Hp, Wp = (unsigned)a.Wp, Wc = Wp + 1u;
+  const unsigned HW = Hp * Wp, cells = (unsigned)a.cells;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const double M = a.omit ? (double)(Hp - 2u) * (double)(Wp - 2u) : (double)HW;
   uint32_t epoch = 0;
-  if (sharded) {
+  if (SHARDED) {
     if (threadIdx.x == 0) sh_epoch = *reinterpret_cast<volatile uint32_t*>(a.px.epoch) + 1u;
     __syncthreads();
     epoch = sh_epoch;
   }
-  auto in_crop = [&](int r, int c) { return !a.omit || (r >= 1 && r <= a.Hp - 2 && c >= 1 && c <= a.Wp - 2); };
-  auto commit = [&](int img, double s, double q) {  // this CTA's partial sums of image `img` (all threads call)
-    s = block_sum(s, red);
-    q = block_sum(q, red);
-    if (threadIdx.x == 0) {
-      double* slot = a.slots + ((int64_t)blockIdx.x * a.n_ref + img) * 2;
-      slot[0] = s;
-      slot[1] = q;
+  const unsigned lo = a.omit ? 1u : 0u;
+  auto in_crop = [&](unsigned r, unsigned c) { return r >= lo && r + lo < Hp && c >= lo && c + lo < Wp; };
+  // this CTA's partial sums of image `img` -> its slot (all threads call; one __syncthreads)
+  auto commit = [&](int img, double s, double q) {
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      red[0][wid] = s;
+      red[1][wid] = q;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      double ts = lane < kWarps ? red[0][lane] : 0.0, tq = lane < kWarps ? red[1][lane] : 0.0;
+      ts = warp_sum(ts);
+      tq = warp_sum(tq);
+      if (lane == 0) {
+        double* slot = a.slots + ((size_t)img * gridDim.x + blockIdx.x) * 2;
+        slot[0] = ts;
+        slot[1] = tq;
+      }
     }
   };
 
-  // ---- phase 1: fold (and, on one GPU, the variance sums of the folded image)
-  if (a.fold || (a.stats && !sharded)) {
+  // ---- phase 1: fold (and, on one GPU, the variance sums of the folded image).  Two pixels per round, loads first.
+  if (a.fold || (a.stats && !SHARDED)) {
     for (int img = 0; img < a.n_ref; ++img) {
-      float* A = reinterpret_cast<float*>(a.acc + img * a.cells);
+      float* A = reinterpret_cast<float*>(a.acc + (size_t)img * cells);
+      float* I = a.iwe + (size_t)img * HW;
       double s = 0.0, q = 0.0;
-      for (int64_t p = tid; p < HW; p += nthr) {
-        const int r = (int)(p / a.Wp), c = (int)(p % a.Wp);
-        float v;
+      for (unsigned p0 = tid; p0 < HW; p0 += 2u * nthr) {
+        const unsigned p1 = p0 + nthr;
+        const bool two = p1 < HW;
+        const unsigned r0 = p0 / Wp, c0 = p0 - r0 * Wp;
+        const unsigned r1 = two ? p1 / Wp : 0u, c1 = two ? p1 - r1 * Wp : 0u;
+        float v0, v1 = 0.f;
         if (a.fold) {
-          v = fold_pixel(A, r, c, Wc);
-          a.iwe[img * HW + p] = v;
+          const FoldAddr f0 = fold_addr(A, r0, c0, Wc), f1 = fold_addr(A, r1, c1, Wc);
+          const float x0 = *f0.a00, y0 = *f0.a10, z0 = *f0.a01, w0 = *f0.a11;
+          float x1 = 0.f, y1 = 0.f, z1 = 0.f, w1 = 0.f;
+          if (two) {
+            x1 = *f1.a00; y1 = *f1.a10; z1 = *f1.a01; w1 = *f1.a11;
+          }
+          *f0.a00 = 0.f; *f0.a10 = 0.f; *f0.a01 = 0.f; *f0.a11 = 0.f;
+          v0 = ((x0 + y0) + z0) + w0;
+          I[p0] = v0;
+          if (two) {
+            *f1.a00 = 0.f; *f1.a10 = 0.f; *f1.a01 = 0.f; *f1.a11 = 0.f;
+            v1 = ((x1 + y1) + z1) + w1;
+            I[p1] = v1;
+          }
         } else {
-          v = a.iwe[img * HW + p];
+          v0 = I[p0];
+          if (two) v1 = I[p1];
         }
-        if (a.stats && !sharded && in_crop(r, c)) {
-          s += (double)v;
-          q += (double)v * (double)v;
+        if (a.stats && !SHARDED) {
+          if (in_crop(r0, c0)) {
+            s += (double)v0;
+            q += (double)v0 * (double)v0;
+          }
+          if (two && in_crop(r1, c1)) {
+            s += (double)v1;
+            q += (double)v1 * (double)v1;
+          }
         }
       }
-      if (a.stats && !sharded) commit(img, s, q);
+      STAMP(2);
+      if (a.stats && !SHARDED) commit(img, s, q);
     }
   }
+  STAMP(3);
 
   // ---- phase 2 (sharded): signal, wait, sum the partial images of all ranks in rank order (bit-identical on every rank)
-  if (sharded) {
+  if (SHARDED) {
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -179,34 +230,34 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     wait_flags(a.px.flags, epoch, a.px.n);
     for (int img = 0; img < a.n_ref; ++img) {
       double s = 0.0, q = 0.0;
-      auto account = [&](int64_t p, float v) {
-        const int r = (int)(p / a.Wp), c = (int)(p % a.Wp);
+      auto account = [&](unsigned p, float v) {
+        const unsigned r = p / Wp, c = p - r * Wp;
         if (a.stats && in_crop(r, c)) {
           s += (double)v;
           q += (double)v * (double)v;
         }
       };
-      if ((HW & 3) == 0) {
+      if ((HW & 3u) == 0) {
         // 16-byte peer loads, all ranks' loads of a thread in flight together: one NVLink round trip per thread
-        for (int64_t p4 = tid; p4 < (HW >> 2); p4 += nthr) {
+        for (unsigned p4 = tid; p4 < (HW >> 2); p4 += nthr) {
           float4 part[CMAX_MAX_PEERS];
 #pragma unroll
           for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-            if (r < a.px.n) part[r] = __ldcg(reinterpret_cast<const float4*>(a.px.part[r] + img * HW) + p4);  // L2-coherent: another GPU wrote it
+            if (r < a.px.n) part[r] = __ldcg(reinterpret_cast<const float4*>(a.px.part[r] + (size_t)img * HW) + p4);  // L2-coherent: another GPU wrote it
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < CMAX_MAX_PEERS; ++r)
             if (r < a.px.n) {
               v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
             }
-          reinterpret_cast<float4*>(a.iwe_full + img * HW)[p4] = v;
-          account(4 * p4, v.x); account(4 * p4 + 1, v.y); account(4 * p4 + 2, v.z); account(4 * p4 + 3, v.w);
+          reinterpret_cast<float4*>(a.iwe_full + (size_t)img * HW)[p4] = v;
+          account(4u * p4, v.x); account(4u * p4 + 1u, v.y); account(4u * p4 + 2u, v.z); account(4u * p4 + 3u, v.w);
         }
       } else {
-        for (int64_t p = tid; p < HW; p += nthr) {
+        for (unsigned p = tid; p < HW; p += nthr) {
           float v = 0.f;
-          for (int r = 0; r < a.px.n; ++r) v += __ldcg(a.px.part[r] + img * HW + p);
-          a.iwe_full[img * HW + p] = v;
+          for (int r = 0; r < a.px.n; ++r) v += __ldcg(a.px.part[r] + (size_t)img * HW + p);
+          a.iwe_full[(size_t)img * HW + p] = v;
           account(p, v);
         }
       }
@@ -214,39 +265,43 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     }
   }
 
-  // ---- phase 3: statistics -> scalar cost -> affine pair.  Every CTA sums the per-CTA slots in the same fixed order, so the
-  // fp64 totals (hence cost and gradient) are bit-identical in every CTA and on every rank.
-  const float* I = sharded ? a.iwe_full : a.iwe;
+  // ---- phase 3: statistics -> scalar cost -> affine pair.  Warp 0 of every CTA sums the per-CTA slots in the same fixed
+  // order, so the fp64 totals (hence cost and gradient) are bit-identical in every CTA and on every rank.
+  const float* I = SHARDED ? a.iwe_full : a.iwe;
   if (a.stats) {
     const bool need_all = a.gq_mode != 0;  // value only: CTA 0 alone finishes the cost
     grid_barrier(&a.bar[1], gridDim.x, need_all || blockIdx.x == 0);
+    STAMP(4);
     if (!need_all && blockIdx.x != 0) return;
-    for (int img = 0; img < a.n_ref; ++img) {
-      double s = 0.0, q = 0.0;
-      for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        const double* slot = a.slots + ((int64_t)c * a.n_ref + img) * 2;
-        s += __ldcg(slot);
-        q += __ldcg(slot + 1);
+    if (wid == 0) {
+      for (int img = 0; img < a.n_ref; ++img) {
+        double s = 0.0, q = 0.0;
+        for (unsigned c = lane; c < gridDim.x; c += 32u) {
+          const double2 sq = __ldcg(reinterpret_cast<const double2*>(a.slots + ((size_t)img * gridDim.x + c) * 2));
+          s += sq.x;
+          q += sq.y;
+        }
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if (lane == 0) {
+          // (reciprocals from the host: an fp64 division is a ~100-instruction dependent chain on this latency-bound path)
+          const double mean = s * a.inv_M;
+          sh_stats[4 * img + 0] = (q - s * mean) * a.inv_Mm1;  // unbiased (torch.var default)   src/costs/image_variance.py:47-58
+          sh_stats[4 * img + 1] = mean;
+          sh_stats[4 * img + 2] = M;
+          sh_stats[4 * img + 3] = 0.0;
+        }
       }
-      s = block_sum(s, red);
-      q = block_sum(q, red);
-      if (threadIdx.x == 0) {
-        const double mean = s / (double)M;
-        sh_stats[4 * img + 0] = (q - s * mean) / (double)(M - 1);  // unbiased (torch.var default)   src/costs/image_variance.py:47-58
-        sh_stats[4 * img + 1] = mean;
-        sh_stats[4 * img + 2] = (double)M;
-        sh_stats[4 * img + 3] = 0.0;
-      }
-    }
-    if (threadIdx.x == 0) {
-      CombineDev local = a.cd;
-      local.cost = &sh_cost;
-      local.affine = sh_aff;
-      combine_eval(sh_stats, local);
-      if (blockIdx.x == 0) {
-        for (int k = 0; k < 4 * a.n_ref; ++k) a.stats_out[k] = sh_stats[k];
-        for (int k = 0; k < 2 * a.n_ref; ++k) a.cd.affine[k] = sh_aff[k];
-        a.cd.cost[0] = sh_cost;
+      if (lane == 0) {
+        CombineDev local = a.cd;
+        local.cost = &sh_cost;
+        local.affine = sh_aff;
+        combine_eval(sh_stats, local);
+        if (blockIdx.x == 0) {
+          for (int k = 0; k < 4 * a.n_ref; ++k) a.stats_out[k] = sh_stats[k];
+          for (int k = 0; k < 2 * a.n_ref; ++k) a.cd.affine[k] = sh_aff[k];
+          a.cd.cost[0] = sh_cost;
+        }
       }
     }
     __syncthreads();
@@ -255,21 +310,35 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     __syncthreads();
     I = a.gsrc;
   }
+  STAMP(5);
   if (a.gq_mode == 0) return;
 
   // ---- phase 4: per-corner gradient quads.  G[p] = a * (I[p] - m) inside the crop (mode 1) / everywhere (mode 2), gathered at
   // the four corners of every accumulator cell with the per-corner in-bounds masks.
-  const int crop = (a.gq_mode == 1 && a.omit) ? 1 : 0;
-  const int lo = crop, hi_r = a.Hp - 1 - crop, hi_c = a.Wp - 1 - crop;
+  const unsigned glo = (a.gq_mode == 1) ? lo : 0u;
   for (int img = 0; img < a.n_ref; ++img) {
-    const float* Ii = I + img * HW;
+    const float* Ii = I + (size_t)img * HW;
     const float ga = sh_aff[2 * img], gm = sh_aff[2 * img + 1];
-    for (int64_t k = tid; k < a.cells; k += nthr) {
-      const int r = (int)(k / Wc) - 1, c = (int)(k % Wc) - 1;
-      auto g = [&](int rr, int cc) -> float {
-        return (rr >= lo && rr <= hi_r && cc >= lo && cc <= hi_c) ? ga * (__ldcg(Ii + (int64_t)rr * a.Wp + cc) - gm) : 0.f;
-      };
-      a.gq[img * a.cells + k] = make_float4(g(r, c), g(r + 1, c), g(r, c + 1), g(r + 1, c + 1));
+    // two cells per round, all eight loads issued before the first use
+    auto corners = [&](unsigned k, float (&v)[4]) {
+      const unsigned kr = k / Wc, kc = k - kr * Wc;
+      const int r0 = (int)kr - 1, c0 = (int)kc - 1;  // cell (r0, c0): corner pixels rows r0, r0+1 and columns c0, c0+1
+      const int gl = (int)glo, rhi = (int)Hp - 1 - gl, chi = (int)Wp - 1 - gl;  // a corner counts iff gl <= row <= rhi and gl <= col <= chi
+      const bool rin0 = r0 >= gl && r0 <= rhi, rin1 = r0 + 1 >= gl && r0 + 1 <= rhi;
+      const bool cin0 = c0 >= gl && c0 <= chi, cin1 = c0 + 1 >= gl && c0 + 1 <= chi;
+      const float* base = Ii + ((int64_t)r0 * (int64_t)Wp + c0);  // (only dereferenced where the masks allow)
+      v[0] = (rin0 && cin0) ? __ldcg(base) : gm;
+      v[1] = (rin1 && cin0) ? __ldcg(base + Wp) : gm;
+      v[2] = (rin0 && cin1) ? __ldcg(base + 1) : gm;
+      v[3] = (rin1 && cin1) ? __ldcg(base + Wp + 1) : gm;
+    };
+    for (unsigned k0 = tid; k0 < cells; k0 += 2u * nthr) {
+      const unsigned k1 = k0 + nthr;
+      float u[4], v[4];
+      corners(k0, u);
+      if (k1 < cells) corners(k1, v);
+      a.gq[(size_t)img * cells + k0] = make_float4(ga * (u[0] - gm), ga * (u[1] - gm), ga * (u[2] - gm), ga * (u[3] - gm));
+      if (k1 < cells) a.gq[(size_t)img * cells + k1] = make_float4(ga * (v[0] - gm), ga * (v[1] - gm), ga * (v[2] - gm), ga * (v[3] - gm));
     }
   }
   if (a.zero != nullptr) {
@@ -280,6 +349,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     }
   }
   if (a.zero2 != nullptr && tid < 2) a.zero2[tid] = 0.0;
+  STAMP(6);
 }
 
 // ------------------------------------------------------------------------------------------------ gradient exchange
@@ -375,6 +445,14 @@ static ImageArgs image_args(const cmax_plan* p, const ObjLayout& L, const Ws& w)
   return a;
 }
 
+static void set_stats(ImageArgs& a, const cmax_plan* p, const cmax_cost_spec* spec) {
+  a.stats = 1;
+  a.omit = spec->omit_boundary ? 1 : 0;
+  const double M = a.omit ? (double)(p->Hp - 2) * (double)(p->Wp - 2) : (double)p->Hp * (double)p->Wp;
+  a.inv_M = 1.0 / M;
+  a.inv_Mm1 = 1.0 / (M - 1.0);
+}
+
 static PeerEx peer_ex(const cmax_peers* peers, const float* const* part, int flag_block, const Ws& w) {
   PeerEx px;
   memset(&px, 0, sizeof(px));
@@ -421,7 +499,8 @@ static int launch_k1(const cmax_plan* p, int motion_model, const float* motion, 
 }
 
 static int launch_image(const ImageArgs& a, const ObjLayout& L, cudaStream_t s) {
-  launch_k(pdl_enabled(), image_kernel, dim3(image_grid(L, a.n_ref)), dim3(kMidThreads), s, a);
+  if (a.px.n > 0) launch_k(pdl_enabled(), image_kernel<true>, dim3(image_grid(L, a.n_ref)), dim3(kMidThreads), s, a);
+  else launch_k(pdl_enabled(), image_kernel<false>, dim3(image_grid(L, a.n_ref)), dim3(kMidThreads), s, a);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
 }
@@ -442,10 +521,10 @@ static int cost_stage(const cmax_plan* p, const cmax_cost_spec* spec, const doub
   a.zero2 = want_grad ? w.acc2 : nullptr;
   if (can_fuse_stats(spec)) {
     if (!bar_clean) CMAX_CUDA_CHECK(cudaMemsetAsync(w.sacc, 0, 256, s));
-    a.stats = 1;
+    set_stats(a, p, spec);
     a.gq_mode = want_grad ? 1 : 0;
-    a.omit = spec->omit_boundary ? 1 : 0;
     a.cd = combine_for(p, spec, d_orig_stat, d_cost, w);
+    a.cd.a.k2 = 2.0 * a.inv_Mm1;
     return launch_image(a, L, s);
   }
   const bool blurred = spec->sigma > 0.f;
@@ -587,10 +666,10 @@ int cmax_objective(const cmax_plan_t* plan, int motion_model, const float* motio
     // the metric path: K1 -> image_kernel (fold + variance + cost + gradient quads, gradient buffer cleared) -> K3
     ImageArgs a = image_args(p, L, w);
     a.fold = 1;
-    a.stats = 1;
+    set_stats(a, p, spec);
     a.gq_mode = want_grad ? 1 : 0;
-    a.omit = spec->omit_boundary ? 1 : 0;
     a.cd = combine_for(p, spec, d_orig_stat, d_cost, w);
+    a.cd.a.k2 = 2.0 * a.inv_Mm1;
     a.zero = grad_motion;
     a.n_zero = want_grad ? (int64_t)n_motion : 0;
     a.zero2 = want_grad ? w.acc2 : nullptr;
@@ -638,10 +717,10 @@ int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const floa
   a.fold = 1;
   a.px = peer_ex(peers, peers->iwe, 0, w);
   if (fuse) {
-    a.stats = 1;
+    set_stats(a, p, spec);
     a.gq_mode = want_grad ? 1 : 0;
-    a.omit = spec->omit_boundary ? 1 : 0;
     a.cd = combine_for(p, spec, d_orig_stat, d_cost, w);
+    a.cd.a.k2 = 2.0 * a.inv_Mm1;
     a.zero = want_grad ? grad_part : nullptr;
     a.n_zero = want_grad ? (int64_t)n_motion : 0;
     a.zero2 = want_grad ? w.acc2 : nullptr;

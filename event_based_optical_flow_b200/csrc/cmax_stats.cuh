@@ -56,6 +56,7 @@ __device__ __forceinline__ void variance_commit(double s, double q, int64_t M, u
 struct CombineArgs {
   int n_ref, stat, form, sign, explicit_grad, has_orig;
   float w[CMAX_MAX_REFS];
+  double k2;  // 2 / (M - 1) when the caller knows it on the host (0: divide on the device)
 };
 
 struct CombineDev {
@@ -70,6 +71,7 @@ static inline CombineDev make_combine(int n_ref, int stat, int form, int sign, i
   CombineDev cd;
   cd.a.n_ref = n_ref; cd.a.stat = stat; cd.a.form = form; cd.a.sign = sign; cd.a.explicit_grad = explicit_grad ? 1 : 0;
   cd.a.has_orig = orig != nullptr;
+  cd.a.k2 = 0.0;
   for (int r = 0; r < CMAX_MAX_REFS; ++r) cd.a.w[r] = (h_weights && r < n_ref) ? h_weights[r] : 1.0f;
   cd.orig = orig; cd.cost = cost; cd.affine = affine;
   return cd;
@@ -103,7 +105,7 @@ __device__ __forceinline__ void combine_eval(const double* __restrict__ stats, c
       }
     }
     if (a.stat == CMAX_STAT_VARIANCE && !a.explicit_grad) {
-      cd.affine[2 * r + 0] = (float)(alpha * 2.0 / (M - 1.0));
+      cd.affine[2 * r + 0] = (float)(alpha * (a.k2 != 0.0 ? a.k2 : 2.0 / (M - 1.0)));
       cd.affine[2 * r + 1] = (float)mean;
     } else {
       cd.affine[2 * r + 0] = (float)alpha;

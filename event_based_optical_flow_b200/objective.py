@@ -447,6 +447,12 @@ class TileFlowObjective:
     def value(self, motion: torch.Tensor) -> torch.Tensor:
         return self.value_and_grad(motion, want_grad=False)[0]
 
+    def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
+        """Evaluation into caller buffers (float64[1] cost, fp32 gradient shaped like the motion); CUDA-graph capturable."""
+        cost, gm = self.value_and_grad(motion_f32)
+        cost_out.copy_(cost.reshape(1))
+        grad_out.copy_(gm)
+
 
 class TimeAwareObjective:
     """cost(motion) for the time-aware configuration: motion -> [tile-flow upsample] -> dense flow at t0 -> flow voxel
@@ -497,6 +503,13 @@ class TimeAwareObjective:
 
     def value(self, motion: torch.Tensor) -> torch.Tensor:
         return self.value_and_grad(motion, want_grad=False)[0]
+
+    def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
+        """Evaluation into caller buffers (float64[1] cost, fp32 gradient shaped like the motion); CUDA-graph capturable
+        (the intermediate flow / voxel tensors come from the graph's private pool)."""
+        cost, gm = self.value_and_grad(motion_f32)
+        cost_out.copy_(cost.reshape(1))
+        grad_out.copy_(gm)
 
 
 class _ObjectiveFunction(torch.autograd.Function):

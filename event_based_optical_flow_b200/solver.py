@@ -15,13 +15,15 @@ tile-flow upsample, the scipy / optuna drivers -- is the reference's own, unchan
     solver.collections["b200_pyramidal_patch_contrast_maximization"] = B200Pyramidal   # selectable from the YAML
 
 Two levels of drop-in exist:
-  * `use_b200_operators(solver)` only swaps `solver.warper` / `solver.imager` / `solver.cost_func` for the CUDA
-    operator classes; the reference's own `get_arg_for_cost` keeps composing them (one kernel per operator call).
-  * the mixin replaces the composition itself by the fused path (3 kernels + 1 per CM iteration).
+  * `use_b200_operators(solver)` only swaps `solver.warper` / `solver.imager` / `solver.cost_func` for dual operators (the
+    CUDA classes for CUDA tensors, the reference's own objects for numpy input); the reference's own `get_arg_for_cost`
+    keeps composing them (one kernel per operator call).
+  * the mixin replaces the composition itself by the fused path (3 kernels per CM iteration).
 """
 from __future__ import annotations
 
 import logging
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -34,21 +36,95 @@ from .warp import Warp
 logger = logging.getLogger(__name__)
 
 
+def _has_cuda_tensor(obj) -> bool:
+    if isinstance(obj, torch.Tensor):
+        return obj.is_cuda
+    if isinstance(obj, dict):
+        return any(_has_cuda_tensor(v) for v in obj.values())
+    if isinstance(obj, (list, tuple)):
+        return any(_has_cuda_tensor(v) for v in obj)
+    return False
+
+
+class _DualOperator:
+    """A seam object that runs the CUDA operator for CUDA tensors and the reference's own object for everything else.
+
+    The reference keeps calling `solver.imager` / `solver.warper` / `solver.cost_func` with numpy arrays outside the
+    scipy objective (`visualize_one_batch_warp`, `create_clipped_iwe_for_visualization`, the metrics, the Optuna
+    initialiser through `calculate_cost`: src/solver/base.py:280-330, src/solver/patch_contrast_pyramid.py:320-415), so a swap
+    that only understood CUDA tensors would break its run loop.  Methods dispatch per call on their arguments; attributes
+    (image_size, direction, history, required_keys, ...) are the reference object's, and the two histories are kept as one."""
+
+    def __init__(self, cuda_obj, reference_obj):
+        object.__setattr__(self, "_cuda", cuda_obj)
+        object.__setattr__(self, "_reference", reference_obj)
+        if hasattr(reference_obj, "history") and hasattr(cuda_obj, "history"):
+            cuda_obj.history = reference_obj.history  # one shared bookkeeping dict (src/costs/base.py:53-56)
+
+    def __getattr__(self, name):
+        ref = object.__getattribute__(self, "_reference")
+        cuda = object.__getattribute__(self, "_cuda")
+        target = getattr(ref, name) if hasattr(ref, name) else getattr(cuda, name)
+        fast = getattr(cuda, name, None)
+        if not callable(target) or not callable(fast):
+            return target
+
+        def dispatch(*args, **kw):
+            if _has_cuda_tensor(args) or _has_cuda_tensor(kw):
+                return fast(*args, **kw)
+            return target(*args, **kw)
+
+        return dispatch
+
+    def __setattr__(self, name, value):  # e.g. solver code that toggles store_history: keep both sides in step
+        for side in (object.__getattribute__(self, "_reference"), object.__getattribute__(self, "_cuda")):
+            if hasattr(side, name):
+                setattr(side, name, value)
+
+    def clear_history(self):
+        ref = object.__getattribute__(self, "_reference")
+        ref.clear_history()
+        object.__getattribute__(self, "_cuda").history = ref.history
+
+
 def use_b200_operators(solver) -> None:
-    """Swap the solver's duck-typed seam objects (src/solver/base.py:139-147, :185-204) for the CUDA ones."""
+    """Swap the solver's duck-typed seam objects (src/solver/base.py:139-147, :185-204) for dual operators: the CUDA classes
+    for CUDA tensors, the reference's own objects (kept) for numpy / CPU input."""
     image_shape = tuple(solver.imager.image_size)
     pad = tuple(getattr(solver.imager, "outer_padding", (0, 0)))
     unpadded = tuple(int(s - 2 * p) for s, p in zip(image_shape, pad))
-    solver.imager = EventImageConverter(unpadded, outer_padding=pad)
-    solver.warper = Warp(tuple(solver.warper.image_size), calculate_feature=getattr(solver.warper, "calculate_feature", False),
-                         normalize_t=getattr(solver.warper, "normalize_t", True), calib_param=getattr(solver.warper, "calib_param", None))
+    solver.imager = _DualOperator(EventImageConverter(unpadded, outer_padding=pad), solver.imager)
+    solver.warper = _DualOperator(Warp(tuple(solver.warper.image_size), calculate_feature=getattr(solver.warper, "calculate_feature", False),
+                                       normalize_t=getattr(solver.warper, "normalize_t", True),
+                                       calib_param=getattr(solver.warper, "calib_param", None)), solver.warper)
     old = solver.cost_func
     if getattr(old, "name", None) == "hybrid":
         weights = {k: v["weight"] for k, v in old.cost_func.items()}
-        solver.cost_func = b200_costs.HybridCost(direction=old.direction, cost_with_weight=weights, store_history=old.store_history,
-                                                 precision="64")
+        fast = b200_costs.HybridCost(direction=old.direction, cost_with_weight=weights, store_history=old.store_history, precision="64")
     else:
-        solver.cost_func = b200_costs.functions[old.name](direction=old.direction, store_history=old.store_history, precision="64")
+        fast = b200_costs.functions[old.name](direction=old.direction, store_history=old.store_history, precision="64")
+    solver.cost_func = _DualOperator(fast, old)
+
+
+class _Batch:
+    """One cached event batch: the tensor itself (a strong reference, so that neither its storage nor its id() can be
+    recycled while the entry lives), the plans keyed by what they were packed for, the objectives."""
+
+    def __init__(self, events: torch.Tensor):
+        self.events = events
+        self.version = events._version
+        self.t_range = None
+        self.plans: Dict[tuple, EventPlan] = {}
+        self.objectives: Dict[tuple, ContrastObjective] = {}
+
+    def matches(self, events: torch.Tensor) -> bool:
+        return self.events is events and self.version == events._version
+
+    def close(self) -> None:
+        self.objectives.clear()
+        for plan in self.plans.values():
+            plan.close()
+        self.plans.clear()
 
 
 class B200CostMixin:
@@ -57,18 +133,41 @@ class B200CostMixin:
 
     b200_event_order = "pixel"
     b200_process_group = None  # set to a torch.distributed group to shard the events of every rank
+    b200_exchange = "nccl"     # "peer": the two sums over NVLink peer memory inside the kernels (needs symmetric memory)
 
-    # -- cache: one resident plan per event tensor, one fused objective per (plan, cost term, motion model)
-    def _b200_cache(self) -> dict:
-        if not hasattr(self, "_b200_objectives"):
-            self._b200_objectives: Dict[tuple, ContrastObjective] = {}
-            self._b200_plans: Dict[tuple, EventPlan] = {}
-        return self._b200_objectives
+    b200_max_batches = 2  # resident event batches (the current one and its predecessor); older ones are closed
+
+    # -- cache, keyed on the IDENTITY of the event tensor (the reference hands the same tensor to every objective call of an
+    #    optimize(), src/solver/patch_contrast_pyramid.py:186, 252-277).  A data_ptr()-based key would collide as soon as
+    #    the caching allocator recycles the storage of the previous frame's batch.  A solver that clones its events per call
+    #    (src/solver/patch_contrast_base.py:252) gets a fresh, correct plan per call.
+    def _b200_cache(self) -> "OrderedDict[int, _Batch]":
+        if not hasattr(self, "_b200_batches"):
+            self._b200_batches: "OrderedDict[int, _Batch]" = OrderedDict()
+        return self._b200_batches
 
     def b200_release(self) -> None:
         """Drop the resident event copies (call when `optimize()` is done with a batch)."""
-        self._b200_objectives = {}
-        self._b200_plans = {}
+        for batch in self._b200_cache().values():
+            batch.close()
+        self._b200_batches = OrderedDict()
+
+    def _b200_batch(self, events: torch.Tensor) -> _Batch:
+        cache = self._b200_cache()
+        batch = cache.get(id(events))
+        if batch is not None and not batch.matches(events):  # same object, modified in place since: rebuild
+            batch.close()
+            del cache[id(events)]
+            batch = None
+        if batch is None:
+            batch = _Batch(events)
+            cache[id(events)] = batch
+            while len(cache) > self.b200_max_batches:
+                _, old = cache.popitem(last=False)
+                old.close()
+        else:
+            cache.move_to_end(id(events))
+        return batch
 
     def _b200_image_geometry(self) -> Tuple[Tuple[int, int], Tuple[int, int]]:
         pad = tuple(int(p) for p in getattr(self.imager, "outer_padding", (0, 0)))
@@ -76,27 +175,25 @@ class B200CostMixin:
         return (padded[0] - 2 * pad[0], padded[1] - 2 * pad[1]), pad
 
     def _b200_objective(self, events: torch.Tensor, cost_name: str, direction: str, motion_model: str, n_bins: Optional[int]):
-        cache = self._b200_cache()
-        ev_key = (events.data_ptr(), tuple(events.shape), events._version, str(events.device))
-        key = ev_key + (cost_name, direction, motion_model, n_bins, float(self.iwe_config["blur_sigma"]))
-        obj = cache.get(key)
+        batch = self._b200_batch(events)
+        sigma = float(self.iwe_config["blur_sigma"])
+        key = (cost_name, direction, motion_model, n_bins, sigma)
+        obj = batch.objectives.get(key)
         if obj is None:
-            if len(self._b200_plans) > 4:  # a new batch arrived: forget the old ones
-                self.b200_release()
-                cache = self._b200_cache()
             image_size, pad = self._b200_image_geometry()
-            plan = self._b200_plans.get(ev_key)
-            t_range = None
-            if self.b200_process_group is not None:
+            if self.b200_process_group is not None and batch.t_range is None:
                 from .distributed import global_time_range
-                t_range = global_time_range(events, self.b200_process_group)
+                batch.t_range = global_time_range(events, self.b200_process_group)
+            # one plan per (reference times, voxel depth): two hybrid terms with different reference sets never re-pack each other's
+            plan_key = (tuple(d for _, d in COST_TABLE[cost_name][2]), n_bins if motion_model == "dense-flow-voxel" else 0)
+            plan = batch.plans.get(plan_key)
             if plan is None:
-                plan = EventPlan(events, image_size, pad, self.b200_event_order, t_range)
-                self._b200_plans[ev_key] = plan
-            obj = ContrastObjective(plan, image_size, cost=cost_name, motion_model=motion_model, sigma=float(self.iwe_config["blur_sigma"]),
-                                    omit_boundary=True, direction=direction, n_bins=n_bins, orig_events=events,
-                                    process_group=self.b200_process_group)
-            cache[key] = obj
+                plan = EventPlan(events, image_size, pad, self.b200_event_order, batch.t_range)
+                batch.plans[plan_key] = plan
+            obj = ContrastObjective(plan, image_size, cost=cost_name, motion_model=motion_model, sigma=sigma, omit_boundary=True,
+                                    direction=direction, n_bins=n_bins, orig_events=events, process_group=self.b200_process_group,
+                                    exchange=self.b200_exchange)
+            batch.objectives[key] = obj
         return obj
 
     @staticmethod

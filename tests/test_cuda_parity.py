@@ -43,6 +43,17 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
 
 
+def _cost_close(val, ref32, ref64=None, tol=RTOL):
+    """cost within `tol` of the fp64 reference (the north-star bound); against the fp32 reference the bound is widened by
+    exactly how far the fp32 reference itself sits from fp64 (its sequential fp32 scatter_add_ / fp32 statistics drift by
+    up to ~1e-5 on these batches, while the CUDA path accumulates its statistics in fp64)."""
+    val, ref32 = float(val), float(ref32)
+    if ref64 is None:
+        return abs(val - ref32) <= tol * abs(ref32)
+    ref64 = float(ref64)
+    return abs(val - ref64) <= tol * abs(ref64) and abs(val - ref32) <= tol * abs(ref32) + abs(ref32 - ref64)
+
+
 def _oracle_warp(model, ev, motion, d):
     return {"dense-flow": O.warp_dense, "dense-flow-voxel": O.warp_voxel, "2d-translation": O.warp_2dof}[model](ev, motion, d)
 
@@ -119,9 +130,10 @@ def test_modular_pipeline_autograd(B, dev, golden_random, case, sigma):
             loss = cost.calculate(arg)
             (grad,) = torch.autograd.grad(loss, motion)
             ref_v = float(g[f"{case}/f32/cost/{model}/{cn}/s{sigma}"])
+            ref_v64 = float(g[f"{case}/f64/cost/{model}/{cn}/s{sigma}"])
             ref_g = g[f"{case}/f32/grad/{model}/{cn}/s{sigma}"]
-            assert abs(float(loss) - ref_v) <= 2e-5 * abs(ref_v), (model, cn, float(loss), ref_v)
-            assert _rel(grad.cpu().numpy(), ref_g) <= 5e-5, (model, cn)
+            assert _cost_close(loss, ref_v, ref_v64), (model, cn, float(loss), ref_v, ref_v64)
+            assert _rel(grad.cpu().numpy(), ref_g) <= RTOL, (model, cn, _rel(grad.cpu().numpy(), ref_g))
             assert len(cost.get_history()["loss"]) == 1
 
 
@@ -142,8 +154,8 @@ def test_fused_objective_vs_reference_golden(B, dev, golden_random, case, sigma,
             ref_v = float(g[f"{case}/f32/cost/{model}/{cn}/s{sigma}"])
             ref_v64 = float(g[f"{case}/f64/cost/{model}/{cn}/s{sigma}"])
             ref_g = g[f"{case}/f32/grad/{model}/{cn}/s{sigma}"]
-            assert abs(float(val) - ref_v) <= 2e-5 * abs(ref_v), (model, cn, float(val), ref_v)
-            assert _rel(grad.cpu().numpy(), ref_g) <= 5e-5, (model, cn, _rel(grad.cpu().numpy(), ref_g))
+            assert _cost_close(val, ref_v, ref_v64), (model, cn, float(val), ref_v, ref_v64)
+            assert _rel(grad.cpu().numpy(), ref_g) <= RTOL, (model, cn, _rel(grad.cpu().numpy(), ref_g))
             assert grad.shape == motions[model].shape
             # value-only evaluation and the autograd wrapper agree with value_and_grad
             assert abs(float(obj.value(motions[model].to(dev))) - float(val)) <= 1e-6 * abs(float(val))  # atomics: order varies
@@ -152,7 +164,7 @@ def test_fused_objective_vs_reference_golden(B, dev, golden_random, case, sigma,
             assert loss.dtype == torch.float64
             (g2,) = torch.autograd.grad(loss * 2.0, m)
             assert _rel(g2.cpu().numpy(), 2.0 * grad.double().cpu().numpy()) <= 1e-5
-            assert abs(float(val) - ref_v64) <= 2e-5 * abs(ref_v64)
+            assert abs(float(val) - ref_v64) <= RTOL * abs(ref_v64)
 
 
 @pytest.mark.parametrize("pad", (0, 3))
@@ -218,7 +230,7 @@ def test_c1_config(B, dev, golden_c1):
     obj = B.ContrastObjective(ev, (260, 346), cost="image_variance", motion_model="2d-translation")
     val, grad = obj.value_and_grad(th)
     assert abs(float(val) - float(g["c1/2dof/cost"])) <= RTOL * abs(float(g["c1/2dof/cost"]))
-    np.testing.assert_allclose(grad.cpu().numpy(), g["c1/2dof/grad"], rtol=2e-4)
+    np.testing.assert_allclose(grad.cpu().numpy(), g["c1/2dof/grad"], rtol=RTOL)
     flow = torch.from_numpy(g["flow"]).to(dev)
     w, _ = B.Warp((260, 346), normalize_t=True).warp_event(ev, flow, "dense-flow")
     np.testing.assert_array_equal(w[:, :2].cpu().numpy(), g["c1/dense/warped_xy"])
@@ -256,8 +268,8 @@ def test_one_million_events_vs_oracle(B, dev, variants):
         assert obj.plan.set_compact(compact) is compact
         val, grad = obj.value_and_grad(flow.to(dev))
         assert abs(float(val) - float(ref_v64)) <= RTOL * abs(float(ref_v64))
-        assert abs(float(val) - float(ref_v)) <= 3e-5 * abs(float(ref_v))  # the fp32 oracle itself is ~1e-5 off fp64
-        assert _rel(grad.cpu().numpy(), ref_g.numpy()) <= 2e-5
+        assert _cost_close(val, ref_v, ref_v64)
+        assert _rel(grad.cpu().numpy(), ref_g.numpy()) <= RTOL, _rel(grad.cpu().numpy(), ref_g.numpy())
 
 
 def test_full_size_properties(B, dev):
@@ -389,9 +401,9 @@ def test_strip_kernels_every_model_vs_oracle_and_run_kernels(B, dev, model, cost
     v2, g2 = obj.value_and_grad(motion.to(dev))
     ref_v, ref_g = O.objective_value_and_grad(ev, motion, (H, W), **{k: v for k, v in kw.items() if k != "n_bins"})
     ref_v64, _ = O.objective_value_and_grad(ev.double(), motion.double(), (H, W), **{k: v for k, v in kw.items() if k != "n_bins"})
-    assert abs(float(v5) - float(ref_v64)) <= 2e-5 * abs(float(ref_v64)), (float(v5), float(ref_v64))
+    assert _cost_close(v5, ref_v, ref_v64), (float(v5), float(ref_v), float(ref_v64))
     assert abs(float(v5) - float(v2)) <= 1e-6 * abs(float(v2))
-    assert _rel(g5.cpu().numpy(), ref_g.numpy()) <= 1e-4
+    assert _rel(g5.cpu().numpy(), ref_g.numpy()) <= RTOL, _rel(g5.cpu().numpy(), ref_g.numpy())
     assert _rel(g5.cpu().numpy(), g2.cpu().numpy()) <= 1e-5
     # the un-blurred IWE stack of the strip K1 against the oracle's images
     obj.plan.set_variant(5, 5)

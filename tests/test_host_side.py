@@ -209,3 +209,74 @@ def test_cost_plugin_contract_on_the_host():
         h.update_weight({"image_variance": 1.0})
     h.disable_history_register()
     assert h.cost_func["total_variation"]["func"].store_history is False
+
+
+# ------------------------------------------------------------------------------------------------ total variation vs golden
+def test_total_variation_matches_reference_golden():
+    """`TotalVariation` (torch, on the <=16x16 patch grid) against outputs of the reference's own class
+    (tests/golden/make_golden_tv.py): value and autograd gradient, both directions, both precisions, with and without the
+    boundary ring, and the batched form."""
+    import os
+    from conftest import GOLDEN_DIR
+    from event_based_optical_flow_b200.costs import functions
+    g = np.load(os.path.join(GOLDEN_DIR, "reference_tv.npz"))
+    for k, (h, w) in enumerate(g["shapes"]):
+        flow = g[f"{k}/flow"]
+        for direction in ("minimize", "maximize"):
+            for omit in (True, False):
+                for prec, dt, tol in (("32", torch.float32, 1e-6), ("64", torch.float64, 1e-13)):
+                    cost = functions["total_variation"](direction=direction, precision=prec)
+                    f = torch.from_numpy(flow).to(dt).requires_grad_(True)
+                    val = cost.calculate({"flow": f, "omit_boundary": omit})
+                    (grad,) = torch.autograd.grad(val, f)
+                    key = f"{k}/{direction}/{int(omit)}/{prec}"
+                    np.testing.assert_allclose(val.detach().numpy(), g[key + "/value"], rtol=tol, atol=tol, err_msg=key)
+                    np.testing.assert_allclose(grad.numpy(), g[key + "/grad"], rtol=tol, atol=tol, err_msg=key)
+        fb = torch.from_numpy(np.stack([flow, -0.5 * flow])).double()
+        val = functions["total_variation"](direction="minimize", precision="64").calculate({"flow": fb, "omit_boundary": True})
+        np.testing.assert_allclose(val.numpy(), g[f"{k}/batched"], rtol=1e-13, atol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ dual operators
+def test_dual_operator_dispatches_numpy_to_the_reference_object():
+    """`use_b200_operators` must leave the reference's run loop intact: numpy / CPU input goes to the solver's original
+    objects, attributes come from them, and the history stays one dict."""
+    from event_based_optical_flow_b200.solver import _DualOperator, _has_cuda_tensor
+
+    class Ref:
+        image_size = (4, 5)
+        direction = "minimize"
+        store_history = True
+
+        def __init__(self):
+            self.history = {"loss": []}
+            self.calls = []
+
+        def create_iwe(self, events, method="bilinear_vote", sigma=1):
+            self.calls.append(("ref", type(events).__name__))
+            return "ref-result"
+
+        def clear_history(self):
+            self.history = {"loss": []}
+
+    class Fast:
+        store_history = True
+
+        def __init__(self):
+            self.history = {"loss": []}
+
+        def create_iwe(self, events, method="bilinear_vote", sigma=1):
+            raise AssertionError("the CUDA operator must not see numpy input")
+
+    ref, fast = Ref(), Fast()
+    dual = _DualOperator(fast, ref)
+    assert dual.image_size == (4, 5) and dual.direction == "minimize"
+    assert dual.create_iwe(np.zeros((3, 4))) == "ref-result"
+    assert dual.create_iwe(torch.zeros(3, 4), sigma=0) == "ref-result"  # a CPU tensor is the reference's business too
+    assert ref.calls == [("ref", "ndarray"), ("ref", "Tensor")]
+    assert fast.history is ref.history
+    dual.store_history = False
+    assert ref.store_history is False and fast.store_history is False
+    dual.clear_history()
+    assert fast.history is ref.history
+    assert not _has_cuda_tensor({"a": [np.zeros(2), torch.zeros(2)]})

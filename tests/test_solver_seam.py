@@ -82,8 +82,8 @@ def test_mixin_matches_reference_composition_and_oracle(cost_name, sigma):
         (g,) = torch.autograd.grad(loss, m)
         out[tag] = (float(loss), g.cpu().numpy())
         assert loss.dtype == torch.float64
-    assert abs(out["fast"][0] - out["ref"][0]) <= 2e-5 * abs(out["ref"][0])
-    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-4 * np.linalg.norm(out["ref"][1])
+    assert abs(out["fast"][0] - out["ref"][0]) <= 1e-5 * abs(out["ref"][0])
+    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-5 * np.linalg.norm(out["ref"][1])
     hist = fast.cost_func.get_history()
     assert len(hist["loss"]) == 1
     # the oracle (fp32, same dtype as the kernels) for the contrast part
@@ -91,12 +91,14 @@ def test_mixin_matches_reference_composition_and_oracle(cost_name, sigma):
         m = motion.clone().float().requires_grad_(True)
         val = O.objective(ev.float(), _dense(m, shape), shape, motion_model="dense-flow", cost=cost_name, sigma=float(sigma))
         (g,) = torch.autograd.grad(val, m)
-        assert abs(out["fast"][0] - float(val)) <= 2e-5 * abs(float(val))
-        assert np.linalg.norm(out["fast"][1] - g.numpy()) <= 2e-4 * np.linalg.norm(g.numpy())
+        assert abs(out["fast"][0] - float(val)) <= 1e-5 * abs(float(val))
+        assert np.linalg.norm(out["fast"][1] - g.numpy()) <= 1e-5 * np.linalg.norm(g.numpy())
     # second call re-uses the resident plan
-    n_plans = len(fast._b200_plans)
+    (batch,) = fast._b200_cache().values()
+    n_plans, n_obj = len(batch.plans), len(batch.objectives)
     fast.calculate_cost(evd, _dense(motion.to(dev), shape), "dense-flow", motion.to(dev))
-    assert len(fast._b200_plans) == n_plans == 1
+    assert len(fast._b200_cache()) == 1 and len(batch.plans) == n_plans and len(batch.objectives) == n_obj
+    assert batch.events is evd
 
 
 def test_use_b200_operators_swaps_seam_objects():
@@ -105,8 +107,9 @@ def test_use_b200_operators_swaps_seam_objects():
     slv = _ReferenceSeam(B, (20, 30), "image_variance", 0, pad=2)
     slv.cost_func.direction = "minimize"
     use_b200_operators(slv)
-    assert isinstance(slv.imager, B.EventImageConverter) and slv.imager.image_size == (24, 34)
-    assert isinstance(slv.warper, B.Warp) and slv.warper.normalize_t is True
+    # dual operators: the CUDA classes for CUDA tensors, the solver's original objects for numpy / CPU input
+    assert isinstance(slv.imager._cuda, B.EventImageConverter) and tuple(slv.imager.image_size) == (24, 34)
+    assert isinstance(slv.warper._cuda, B.Warp) and slv.warper.normalize_t is True
     assert slv.cost_func.name == "image_variance"
 
 
@@ -190,7 +193,7 @@ def test_mixin_time_aware_motion_to_dense_flow(pyramid):
         (g,) = torch.autograd.grad((vox * cot.to(d)).sum(), m)
         out[tag] = (vox.detach().cpu().numpy(), g.cpu().numpy())
     np.testing.assert_allclose(out["fast"][0], out["ref"][0], rtol=1e-5, atol=2e-5)
-    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-4 * np.linalg.norm(out["ref"][1])
+    assert np.linalg.norm(out["fast"][1] - out["ref"][1]) <= 1e-5 * np.linalg.norm(out["ref"][1])
     # ... and the whole objective through the mixin's calculate_cost on the voxel it produced
     evd = ev.to(dev)
     m = motion.clone().to(dev).requires_grad_(True)
@@ -200,5 +203,68 @@ def test_mixin_time_aware_motion_to_dense_flow(pyramid):
     val = O.objective(ev.float(), ref.motion_to_dense_flow(m32), shape, motion_model="dense-flow-voxel",
                       cost="multi_focal_normalized_gradient_magnitude", sigma=1.0)
     (g_ref,) = torch.autograd.grad(val, m32)
-    assert abs(float(loss) - float(val)) <= 2e-5 * abs(float(val))
-    assert np.linalg.norm(g.cpu().numpy() - g_ref.numpy()) <= 5e-4 * np.linalg.norm(g_ref.numpy())
+    assert abs(float(loss) - float(val)) <= 1e-5 * abs(float(val))
+    assert np.linalg.norm(g.cpu().numpy() - g_ref.numpy()) <= 1e-5 * np.linalg.norm(g_ref.numpy())
+
+
+# ------------------------------------------------------------------------------------------------ cache / second order
+def _seam_solver(B, shape, cost_name="image_variance", sigma=0):
+    from event_based_optical_flow_b200.solver import B200CostMixin
+
+    class Fast(B200CostMixin, _ReferenceSeam):
+        pass
+
+    return Fast(B, shape, cost_name, sigma)
+
+
+def test_two_frames_of_equal_size_do_not_share_a_plan(dev=None):
+    """The reference builds a fresh events tensor per frame with a fixed n_events_per_batch; when the previous frame's tensor
+    is freed the caching allocator hands the same address to the next one.  The mixin's cache is keyed on tensor identity
+    (and keeps the tensor alive), so frame 2 must be optimised against frame 2's events."""
+    import event_based_optical_flow_b200 as B
+    dev = torch.device("cuda:0")
+    shape, n = (48, 64), 20000
+    slv = _seam_solver(B, shape)
+    rng = np.random.default_rng(11)
+    flow = torch.from_numpy(rng.uniform(-4, 4, (2,) + shape)).to(dev)
+    results, ptrs = [], []
+    for frame in range(3):
+        ev_np = np.stack([rng.integers(0, shape[0], n), rng.integers(0, shape[1], n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
+        events = torch.from_numpy(ev_np).double().requires_grad_().to(dev)  # what run_scipy_over_scale does per frame
+        ptrs.append(events.data_ptr())
+        for _ in range(2):  # several objective calls per frame hit the cache
+            loss = slv.calculate_cost(events, flow, "dense-flow")
+        ref = O.objective(torch.from_numpy(ev_np), flow.cpu(), shape, motion_model="dense-flow", cost="image_variance", sigma=0.0)
+        results.append((float(loss), float(ref)))
+        assert len(slv._b200_cache()) <= slv.b200_max_batches
+        del events, loss
+    for got, ref in results:
+        assert abs(got - ref) <= 1e-5 * abs(ref), results
+    assert len({r[1] for r in results}) == 3  # (the three frames really differ)
+
+
+def test_mixin_supports_hessian_vector_products():
+    """Newton-CG / trust-* go through torch.autograd.functional.vhp (scipy_autograd/torch_wrapper.py:51-73); the mixin builds
+    its objective from an EventPlan, which must not lose the event tensor the second-order path needs."""
+    import event_based_optical_flow_b200 as B
+    dev = torch.device("cuda:0")
+    ev, motion, shape = _problem(seed=5, n=20000)
+    slv = _seam_solver(B, shape)
+    evd = ev.to(dev)
+
+    def cost_of(m):
+        return slv.calculate_cost(evd, _dense(m, shape), "dense-flow", m)
+
+    m0 = motion.to(dev)
+    v = torch.from_numpy(np.random.default_rng(2).standard_normal(tuple(motion.shape))).to(dev)
+    _, hv = torch.autograd.functional.vhp(cost_of, m0, v)
+    f64 = lambda m: O.objective(ev, _dense(m, shape), shape, motion_model="dense-flow", cost="image_variance", sigma=0.0)  # noqa: E731
+    _, hv_ref = torch.autograd.functional.vhp(f64, motion, v.cpu())
+    f32 = lambda m: O.objective(ev.float(), _dense(m, shape), shape, motion_model="dense-flow", cost="image_variance", sigma=0.0)  # noqa: E731
+    _, hv_ref32 = torch.autograd.functional.vhp(f32, motion.float(), v.cpu().float())
+    rel = float(torch.linalg.norm(hv.cpu() - hv_ref) / torch.linalg.norm(hv_ref))
+    rel32 = float(torch.linalg.norm(hv_ref32.double() - hv_ref) / torch.linalg.norm(hv_ref))
+    print(f"H v through the mixin: rel vs fp64 oracle {rel:.2e} (fp32 oracle vs fp64 oracle: {rel32:.2e})")
+    # the second-order path composes the modular fp32 kernels; its bound is the fp32 reference's own distance from fp64
+    # (measured: 1.4e-5 here against 1e-5 .. 1e-4 for the fp32 oracle), never looser than 5e-5
+    assert rel <= max(1e-5, min(5e-5, 3 * rel32)), (rel, rel32)
