@@ -321,12 +321,20 @@ def run_b200(args) -> None:
         with torch.cuda.graph(graph):
             step_into(motion_buf, cost_buf, grad_buf)
 
+    def align():
+        """Sharded runs: an in-stream cross-GPU barrier between the L2 flush and the start event.  The flush (1 GiB of memory
+        traffic per rank, ~250 us) is not part of a step, but the ranks drift apart by several microseconds while each runs
+        its own; without re-aligning them the first exchange of the step would be charged that drift."""
+        if world > 1 and getattr(obj, "_symm", None) is not None:
+            obj._symm.barrier(channel=0)
+
     def run_steps(count: int, first: int):
         """-> per-step device milliseconds (CUDA events on the launching stream), L2 flushed before every step."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(count)]
         for k in range(count):
             motion_buf.copy_(motions[(first + k) % N_FLOWS])  # outside the timed bracket: the motion is "already resident"
             flush_l2()
+            align()
             evs[k][0].record()
             if graph is not None:
                 graph.replay()
@@ -565,7 +573,8 @@ def run_b200(args) -> None:
                                   "time-aware": "16x16 tile motion, |f|<=10px, fresh per step"}[cfg["model"]],
                        "event_order": args.order, "packed_event_bytes": 4.5 if strips else (8 if compact else 16),
                        "vote_variant": args.vote_variant, "grad_variant": args.grad_variant, "cuda_graph": graph is not None,
-                       "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)",
+                       "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)"
+                             + ("; ranks re-aligned by an in-stream barrier between the flush and the start event" if world > 1 and args.exchange == "peer" else ""),
                        "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
                                        {"nccl": "NCCL all-reduce",
                                         "peer": "NVLink peer-memory reads behind in-kernel flags (no collective, no barrier kernel)"}[args.exchange])

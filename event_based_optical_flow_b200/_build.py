@@ -16,9 +16,10 @@ LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200.so")
 SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_mid.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu")
 HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", "cmax_runs.cuh", "cmax_objective.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
-# CMAX_MEASURE=1 in the environment of the BUILD compiles the measurement aids in (partial stage masks, CMAX_PDL=0, phase
-# stamps of the image kernel); the release build has none of them, so nothing in a process's environment can change its results
-NVCC_FLAGS = (*(("-DCMAX_MEASURE",) if os.environ.get("CMAX_MEASURE") else ()), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
+# `--measure` builds a SECOND library, lib/libcmax_b200_measure.so, with the measurement aids compiled in (-DCMAX_MEASURE:
+# partial stage masks, CMAX_PDL=0, phase stamps of the image / exchange kernels).  The release library has none of them and
+# nothing in a process's environment selects the other file: a probe script asks for it explicitly (_lib.use_measure_library()).
+NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared")
 
 
@@ -57,6 +58,30 @@ def is_stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 
+MEASURE_LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200_measure.so")
+
+
+def build_measure_library(verbose: bool = False) -> str:
+    """lib/libcmax_b200_measure.so: every source recompiled with -DCMAX_MEASURE (its own object directory)."""
+    obj_dir = os.path.join(LIB_DIR, "obj_measure")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        procs.append((src, obj, subprocess.Popen([nvcc, "-DCMAX_MEASURE", *COMPILE_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)],
+                                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for src, _, proc in procs:
+        out, err = proc.communicate()
+        if proc.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src} ({proc.returncode}):\n{out}\n{err}")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", MEASURE_LIB_PATH, *[o for _, o, _ in procs]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc link failed ({proc.returncode}):\n{proc.stdout}\n{proc.stderr}")
+    return MEASURE_LIB_PATH
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into lib/libcmax_b200.so; returns the path.  No-op when up to date.  Every source is its own
     translation unit (no relocatable device code), so stale objects are recompiled in parallel and then linked."""
@@ -89,4 +114,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--measure" in sys.argv:
+        print(build_measure_library(verbose="-v" in sys.argv))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -98,8 +98,20 @@ class CmaxError(RuntimeError):
         super().__init__(f"{fn} failed with status {status}: {message}")
 
 
+_use_measure = False
+
+
+def use_measure_library() -> None:
+    """Probe scripts only: load lib/libcmax_b200_measure.so (`python -m event_based_optical_flow_b200._build --measure`)
+    instead of the release library.  Must be called before the first `load()`; the product never calls it."""
+    global _use_measure
+    if _lib is not None:
+        raise RuntimeError("use_measure_library() must be called before the library is loaded")
+    _use_measure = True
+
+
 def library_path() -> str:
-    return _build.LIB_PATH
+    return _build.MEASURE_LIB_PATH if _use_measure else _build.LIB_PATH
 
 
 def load() -> C.CDLL:

@@ -21,30 +21,24 @@ namespace cmax {
 // source rank has reached e.  Two flag arrays alternate per evaluation (IWE, gradient), which is what makes buffer reuse
 // safe without further synchronisation: a rank overwrites its partial IWE for evaluation e+1 only after it has seen
 // every peer's gradient flag of e, and a peer raises that flag (stream order) after it has finished reading the IWEs of e.
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+// Flags are written and polled with RELAXED system-scope accesses and there is NO system-scope fence anywhere: measured on
+// 2 x B200, a fence.sys costs 2-3 us where it stands (st.release.sys = one per peer; one per consumer CTA after the poll
+// turned a 58 us step into 71 us).  What makes the protocol correct without them: every buffer a peer reads lives in the
+// PRODUCER's memory, whose L2 is the point of coherence for its own SMs and for NVLink peer reads alike -- a gpu-scope
+// fence (all prior writes performed at that L2) before the posted flag store is enough for a reader that first sees the
+// flag and then issues its loads; the consumers' loads are .cg (never served from an L1) and control-dependent on the poll.
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-
-// Block until flags[0..n) have all reached `epoch` (every CTA of a consumer calls this).  A peer that never arrives
-// (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which surfaces as a CUDA error.
-__device__ __forceinline__ void wait_flags(const uint32_t* __restrict__ flags, uint32_t epoch, int n) {
-  if ((int)threadIdx.x < n) {
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
-      if (clock64() - t0 > 8000000000ll) __trap();
-    }
-  }
-  __syncthreads();
 }
 
 struct PeerEx {
@@ -54,6 +48,29 @@ struct PeerEx {
   const uint32_t* flags;                   // this rank's own flag array
   uint32_t* epoch;                         // this rank's evaluation counter (advanced by image_kernel)
 };
+
+// Block until flags[0..n) have all reached `epoch` (every CTA of a consumer calls this).  A peer that never arrives
+// (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which surfaces as a CUDA error.
+__device__ __forceinline__ void wait_flags(const uint32_t* __restrict__ flags, uint32_t epoch, int n) {
+  if ((int)threadIdx.x < n) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
+      if (clock64() - t0 > 8000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+// Publish: the calling WARP raises this rank's flag on every peer.  Everything this rank wrote before (ordered before the
+// caller by barriers / the arrival counter) is performed at this GPU's L2 after the fence; the flag stores themselves are
+// posted, one lane per peer, in parallel.
+__device__ __forceinline__ void raise_flags(const PeerEx& px, uint32_t epoch) {
+  __threadfence();
+  __syncwarp();
+  const int lane = threadIdx.x & 31;
+  if (lane < px.n) st_relaxed_sys(px.flag_at[lane], epoch);
+}
+
 
 // Grid-wide barrier of a co-resident grid: `bar` counts arrivals (cleared before the launch), every CTA arrives once.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_ctas, bool wait) {
@@ -95,6 +112,12 @@ struct ImageArgs {
   PeerEx px;
 };
 
+#ifdef CMAX_MEASURE  // measurement builds: per-CTA globaltimer stamps of the phases (scripts/image_probe.py)
+#define STAMP(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[i] = t_; } } while (0)
+#else
+#define STAMP(i)
+#endif
+
 // IWE[r,c] = acc[r,c].x + acc[r-1,c].y + acc[r,c-1].z + acc[r-1,c-1].w.  Every scalar component of every accumulator
 // cell has exactly ONE reader, which also zeroes it: the accumulators are clean again for the next CM iteration and no
 // memset is ever enqueued (components no pixel reads only collect votes of out-of-image corners and are never looked at).
@@ -122,11 +145,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
   __shared__ double sh_cost;
   __shared__ float sh_aff[2 * CMAX_MAX_REFS];
   __shared__ uint32_t sh_epoch;
-#ifdef CMAX_MEASURE  // measurement builds: per-CTA globaltimer stamps of the phases (scripts/image_probe.py)
+#ifdef CMAX_MEASURE
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.slots) + 2048 + blockIdx.x * 8;
-#define STAMP(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[i] = t_; } } while (0)
-#else
-#define STAMP(i)
 #endif
   STAMP(0);
   pdl_trigger();  // K3 may be scheduled (it prefetches its first event tile, then waits for this grid to complete)
@@ -221,13 +241,12 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     if (threadIdx.x == 0) {
       __threadfence();
       last = (atomicAdd(&a.bar[0], 1u) == gridDim.x - 1);
-      if (last) {  // every CTA of this rank has folded (and has read the epoch): publish
-        __threadfence_system();
-        for (int q = 0; q < a.px.n; ++q) st_release_sys(a.px.flag_at[q], epoch);
-        *a.px.epoch = epoch;
-      }
+      if (last) *a.px.epoch = epoch;  // (every CTA has read the old value by now)
     }
+    __syncthreads();
+    if (last && wid == 0) raise_flags(a.px, epoch);  // every CTA of this rank has folded: publish
     wait_flags(a.px.flags, epoch, a.px.n);
+    STAMP(7);
     for (int img = 0; img < a.n_ref; ++img) {
       double s = 0.0, q = 0.0;
       auto account = [&](unsigned p, float v) {
@@ -355,13 +374,15 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
 // ------------------------------------------------------------------------------------------------ gradient exchange
 // out[i] = sum over ranks of part[r][i], rank order.  CTA 0 raises this rank's gradient flag on every peer first (K3 is
 // complete: stream order), then every CTA waits for all ranks' flags and pulls.  n == 0 closes a value-only evaluation.
-__global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n, float* __restrict__ out, unsigned long long* probe) {
+#ifdef CMAX_MEASURE
+  unsigned long long* stamps = probe + (blockIdx.x & 63) * 8;
+#endif
+  STAMP(0);
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(px.epoch);  // already advanced by this evaluation's image_kernel
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    __threadfence_system();
-    for (int q = 0; q < px.n; ++q) st_release_sys(px.flag_at[q], epoch);
-  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) raise_flags(px, epoch);
   wait_flags(px.flags, epoch, px.n);
+  STAMP(1);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
   if ((n & 3) == 0) {
     for (int64_t i = tid; i < (n >> 2); i += nthr) {
@@ -384,6 +405,7 @@ __global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n
       out[i] = v;
     }
   }
+  STAMP(2);
 }
 
 // 2-dof gradient: the CTAs accumulate in two doubles (off_misc), narrowed here.
@@ -740,7 +762,7 @@ int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const floa
   const int64_t n = want_grad ? (int64_t)n_motion : 0;
   const int64_t work = (n & 3) == 0 ? n / 4 : n;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)num_sms() * 2));
-  grad_exchange_kernel<<<grid, 256, 0, s>>>(gx, n, grad_motion);
+  grad_exchange_kernel<<<grid, 256, 0, s>>>(gx, n, grad_motion, reinterpret_cast<unsigned long long*>(w.slots) + 2048 + 148 * 8);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
 }

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""One-off probe (library built with CMAX_MEASURE=1 python -m event_based_optical_flow_b200._build --force): per-CTA globaltimer stamps of the image kernel inside the graph-replayed CM iteration."""
+"""One-off probe (library lib/libcmax_b200_measure.so: python -m event_based_optical_flow_b200._build --measure): per-CTA globaltimer stamps of the image kernel inside the graph-replayed CM iteration."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
+from event_based_optical_flow_b200 import _lib as _L
+_L.use_measure_library()
 from event_based_optical_flow_b200 import ContrastObjective, _lib
 dev = torch.device("cuda:0")
 n = int(os.environ.get("PROBE_N", 5_000_000))
