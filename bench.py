@@ -164,22 +164,53 @@ def oracle_value_and_grad(cfg, ev, motion, dtype):
     return value.detach(), grad
 
 
+def reference_value_and_grad(R, cfg, ev, motion):
+    """One CM evaluation with the UNMODIFIED reference classes (baseline/_ref, see oracle/reference_loader.py), composed the
+    way its solver composes them (src/solver/patch_contrast_base.py:289-352): Warp.warp_event -> EventImageConverter.create_iwe ->
+    cost.calculate -> torch.autograd.grad.  Configurations 1 and 2 (one warp, variance)."""
+    import torch
+    size = (cfg["H"], cfg["W"])
+    warper = R.warp.Warp(size, calculate_feature=False, normalize_t=True)
+    imager = R.event_image_converter.EventImageConverter(size)
+    cost = R.costs.functions[cfg["cost"]](direction="minimize", store_history=False)
+    m = motion.detach().clone().requires_grad_(True)
+    warped, _ = warper.warp_event(ev, m, cfg["model"], direction="first")
+    iwe = imager.create_iwe(warped, "bilinear_vote", cfg["sigma"])
+    loss = cost.calculate({"iwe": iwe, "omit_boundary": True})
+    (grad,) = torch.autograd.grad(loss, m)
+    return loss.detach(), grad
+
+
+def load_reference_for(cfg):
+    """The unmodified reference, when it is installed and this configuration is one it is composed for here; else None (the
+    oracle port times instead)."""
+    if cfg["model"] == "time-aware":
+        return None
+    try:
+        from oracle import reference_loader
+        return reference_loader.load()
+    except Exception:
+        return None
+
+
 def cpu_reference_steps(cfg, ev_np: np.ndarray, motions_np: np.ndarray, steps: int, warmup: int):
-    """fp32, all host threads.  Returns (seconds per step list, threads)."""
+    """fp32, all host threads.  Returns (seconds per step list, threads, kind): kind "reference" = the unmodified reference's own
+    classes, "port" = the oracle restatement (time-aware configurations, or no baseline/_ref)."""
     import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     ev = torch.from_numpy(ev_np)
+    R = load_reference_for(cfg)
     times = []
     for i in range(warmup + steps):
         m = torch.from_numpy(motions_np[i % len(motions_np)])
         t0 = time.perf_counter()
-        val, _ = oracle_value_and_grad(cfg, ev, m, torch.float32)
+        val, _ = reference_value_and_grad(R, cfg, ev, m) if R is not None else oracle_value_and_grad(cfg, ev, m, torch.float32)
         float(val)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return times, threads
+    return times, threads, ("reference" if R is not None else "port")
 
 
 def reference_sample(cfg) -> int:
@@ -195,17 +226,19 @@ def run_reference(args) -> None:
     n = reference_sample(cfg)
     ev = synth_events(n, 0, cfg["H"], cfg["W"])
     motions = synth_motions(cfg, N_FLOWS, seed=100)
-    times, threads = cpu_reference_steps(cfg, ev, motions, args.steps, args.warmup)
+    times, threads, kind = cpu_reference_steps(cfg, ev, motions, args.steps, args.warmup)
     sec = float(np.mean(times))
     value = n / sec
     whole = "the full batch" if n == cfg["events"] else f"a bounded sample of the {cfg['events']}-event batch"
-    sample = f"{n} events per step ({whole}), fp32, torch CPU ops, {threads} threads"
+    sample = (f"{n} events per step ({whole}), fp32, {threads} threads; " +
+              ("the unmodified reference classes (Warp -> EventImageConverter -> cost -> autograd) from baseline/_ref" if kind == "reference"
+               else "the oracle restatement of the reference (oracle/cm_oracle.py)"))
     line = {
         "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "events": n, "image": [cfg["H"], cfg["W"]]},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -272,6 +305,21 @@ def run_b200(args) -> None:
     motions = torch.from_numpy(motions_np).to(dev)
     group = dist.group.WORLD if world > 1 else None
     t_range = global_time_range(ev, group)
+    reshard_ms = None
+    if world > 1 and args.shard == "pixel":
+        # every rank was handed a time slice (what a streaming source delivers); one all-to-all turns the slices into
+        # contiguous slices of the pixel-ordered stream, which makes both per-iteration exchanges local (distributed.py)
+        from event_based_optical_flow_b200.distributed import reshard_events_by_pixel
+        reshard_events_by_pixel(ev, (Hc, Wc_), group)  # warm-up (NCCL channel set-up)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        ev = reshard_events_by_pixel(ev, (Hc, Wc_), group)
+        torch.cuda.synchronize()
+        reshard_ms = (time.perf_counter() - t0) * 1e3
+        n_local = int(ev.shape[0])
+    else:
+        n_local = n
 
     # ---- one-time cost of making the batch resident (validation, sort, strips): host wall clock around plan creation,
     # which ends with the plan's single stream synchronisation
@@ -412,8 +460,15 @@ def run_b200(args) -> None:
         costs = [torch.empty_like(cost_buf) for _ in range(world)]
         dist.all_gather(grads, grad_buf)
         dist.all_gather(costs, cost_buf)
-        shards = [torch.empty_like(ev) for _ in range(world)] if rank == 0 else None
-        dist.gather(ev, shards, dst=0)
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([ev.shape[0]], dtype=torch.int64, device=dev))
+        n_max = int(max(int(c) for c in counts))
+        padded = torch.zeros((n_max, 4), dtype=ev.dtype, device=dev)
+        padded[:ev.shape[0]] = ev
+        shards = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, shards, dst=0)
+        if rank == 0:
+            shards = [sh[:int(c)] for sh, c in zip(shards, counts)]
         if rank == 0:
             args_single = argparse.Namespace(**{**vars(args), "exchange": "nccl"})
             full_ev = torch.cat(shards)
@@ -550,10 +605,15 @@ def run_b200(args) -> None:
                 "what": "cost vs the fp64 oracle, gradient norm-wise vs the same-dtype (fp32) oracle; the fp64 rows show how far "
                         "fp32 itself is from fp64 (the gradient is discontinuous where a floor index flips)",
             }
-            times, threads = cpu_reference_steps(cfg, ev_cpu, motions_np, steps=3 if cfg["model"] == "time-aware" else 5, warmup=1)
-            cpu = {"value": n_cpu / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": "port",
+            times, threads, kind = cpu_reference_steps(cfg, ev_cpu, motions_np, steps=3 if cfg["model"] == "time-aware" else 5, warmup=1)
+            cpu = {"value": n_cpu / float(np.mean(times)), "unit": UNIT, "cores": threads, "kind": kind,
                    "sample": f"{len(times)} timed + 1 warm-up CM iterations over {n_cpu} events "
-                             f"({'the full batch' if n_cpu == n else 'a bounded sample of the batch'}), fp32 torch CPU ops"}
+                             f"({'the full batch' if n_cpu == n else 'a bounded sample of the batch'}), fp32, "
+                             + ("the unmodified reference classes from baseline/_ref" if kind == "reference" else "the oracle restatement")}
+            if kind == "reference":  # the parity object names what it was checked against; add the live reference next to the oracle
+                vr, gr = reference_value_and_grad(load_reference_for(cfg), cfg, torch.from_numpy(ev_cpu), m0)
+                parity["cost_rel_vs_fp32_reference"] = abs(float(c_gpu) - float(vr)) / abs(float(vr))
+                parity["grad_rel_vs_fp32_reference"] = float(torch.linalg.norm(g_gpu.cpu().double() - gr.double()) / torch.linalg.norm(gr.double()))
 
         clocks = sampler.finish() if sampler else None
         if cfg["model"] == "time-aware":
@@ -562,6 +622,8 @@ def run_b200(args) -> None:
             # K1 vote, image kernel (fold + variance + cost + gradient quads), K3 grad; sharded "peer": + the gradient-exchange
             # kernel (the IWE exchange lives inside the image kernel); "nccl": K1, fold, cost, K3 (+ 2 NCCL all-reduces)
             per_step_kernels = (3 if world == 1 else 4) + (1 if cfg["model"] == "2d-translation" else 0)
+        if reshard_ms is not None:
+            plan_ms += reshard_ms  # the one-time all-to-all belongs to making the batch resident
         amortised_ms = ms_per_step + plan_ms / 50.0
         line = {
             "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -575,14 +637,15 @@ def run_b200(args) -> None:
                        "vote_variant": args.vote_variant, "grad_variant": args.grad_variant, "cuda_graph": graph is not None,
                        "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB written, then {L2_FLUSH_BYTES >> 20} MiB read so no dirty lines remain)"
                              + ("; ranks re-aligned by an in-stream barrier between the flush and the start event" if world > 1 and args.exchange == "peer" else ""),
-                       "parallelism": (f"events sharded x{world}, sum(IWE)+sum(grad) per step via " +
+                       "parallelism": (f"events sharded x{world} (" + ("time slices re-distributed once into contiguous slices of the pixel-ordered stream"
+                                                                      if args.shard == "pixel" else "contiguous time slices") + "), sum(IWE)+sum(grad) per step via " +
                                        {"nccl": "NCCL all-reduce",
                                         "peer": "NVLink peer-memory reads behind in-kernel flags (no collective, no barrier kernel)"}[args.exchange])
                        if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host pinned motion -> device, step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
             "gpu_launches": per_step_kernels * args.steps if per_step_kernels else None,
-            "plan_ms": plan_ms, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
+            "plan_ms": plan_ms, "reshard_ms": reshard_ms, "events_this_rank": n_local, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
             "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
         }
     if line is not None:
@@ -614,6 +677,9 @@ def main():
     ap.add_argument("--no-compact", action="store_true", help="force the 16-byte packed-event format")
     ap.add_argument("--exchange", choices=("nccl", "peer"), default="peer",
                     help="multi-GPU: NCCL all-reduces between the stages, or NVLink peer reads behind flags inside the kernels")
+    ap.add_argument("--shard", choices=("pixel", "time"), default="pixel",
+                    help="multi-GPU: 'time' keeps the contiguous time slices every rank is handed; 'pixel' (default) re-distributes them once "
+                         "(one all-to-all at plan time) into contiguous slices of the pixel-ordered stream, which keeps both exchanges local")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the parity / cpu_baseline legs (used under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -16,7 +16,7 @@ MAX_BINS = 64
 MAX_PEERS = 8
 
 OK, ERR_ARG, ERR_CUDA, ERR_SOURCE_OOB, ERR_WORKSPACE = 0, 1, 2, 3, 4
-MOTION = {"dense-flow": 0, "dense-flow-voxel": 1, "2d-translation": 2, "rigid-optical-flow": 2}
+MOTION = {"dense-flow": 0, "dense-flow-voxel": 1, "2d-translation": 2, "rigid-optical-flow": 2, "tile-flow": 3}
 VOTE = {"bilinear_vote": 0, "count": 1}
 STAT = {"variance": 0, "gradmag": 1}
 FORM = {"plain": 0, "normalized": 1, "multifocal": 2}
@@ -69,6 +69,7 @@ _SIGNATURES = {
     "cmax_plan_info": (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(C.c_int32)]),
     "cmax_plan_strips": (_i, [_p, C.POINTER(_i64)]),
     "cmax_plan_set_refs": (_i, [_p, C.POINTER(Ref), _i, _i, _p]),
+    "cmax_plan_set_tile_flow": (_i, [_p, _i, _i, _i, _i, _i, _i, _f]),
     "cmax_plan_set_variant": (_i, [_p, _i, _i]),
     "cmax_plan_set_stage_mask": (_i, [_p, _i]),
     "cmax_plan_set_compact": (_i, [_p, _i, C.POINTER(C.c_int32), _p]),

@@ -8,7 +8,8 @@ namespace cmax {
 
 // ---- variance: sum and sum of squares over the crop; last CTA finalises.   src/costs/image_variance.py:37-58
 __global__ void __launch_bounds__(kStatBlock) variance_stats_kernel(const float* __restrict__ images, int Hp, int Wp, int omit,
-                                                                    StatAcc* __restrict__ acc, double* __restrict__ stats) {
+                                                                    StatAcc* __restrict__ acc, double* __restrict__ slots,
+                                                                    double* __restrict__ stats) {
   __shared__ double red[kStatBlock / 32];
   const int img = blockIdx.y;
   const float* I = images + (int64_t)img * Hp * Wp;
@@ -22,7 +23,13 @@ __global__ void __launch_bounds__(kStatBlock) variance_stats_kernel(const float*
     s += v;
     q += v * v;
   }
-  variance_commit(s, q, M, gridDim.x, &acc[img], stats + 4 * img, red);
+  if (slots_commit(s, q, gridDim.x, blockIdx.x, &acc[img], slots + (size_t)img * 2 * kStatMaxCtas, red) && threadIdx.x == 0) {
+    const double mean = s / (double)M;
+    stats[4 * img + 0] = (q - s * mean) / (double)(M - 1);  // unbiased (torch.var default)
+    stats[4 * img + 1] = mean;
+    stats[4 * img + 2] = (double)M;
+    stats[4 * img + 3] = 0.0;
+  }
 }
 
 // d var / d I = 2/(M-1) (I - mean) inside the crop, 0 on the border
@@ -46,8 +53,8 @@ __device__ __forceinline__ float px(const float* __restrict__ I, int Hp, int Wp,
 }
 
 __global__ void __launch_bounds__(kStatBlock) gradmag_stats_kernel(const float* __restrict__ images, int Hp, int Wp, int omit,
-                                                                   StatAcc* __restrict__ acc, double* __restrict__ stats,
-                                                                   float* __restrict__ gxy /* [n_img,2,Hp,Wp] or NULL */) {
+                                                                   StatAcc* __restrict__ acc, double* __restrict__ slots,
+                                                                   double* __restrict__ stats, float* __restrict__ gxy /* [n_img,2,Hp,Wp] or NULL */) {
   __shared__ double red[kStatBlock / 32];
   const int img = blockIdx.y;
   const int64_t HW = (int64_t)Hp * Wp;
@@ -71,18 +78,9 @@ __global__ void __launch_bounds__(kStatBlock) gradmag_stats_kernel(const float* 
       gxy[(img * 2 + 1) * HW + k] = gy;
     }
   }
-  s = block_sum(s, red);
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    atomicAdd(&acc[img].sum, s);
-    __threadfence();
-    last = (atomicAdd(&acc[img].done, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    const double S = *(volatile double*)&acc[img].sum;
-    stats[4 * img + 0] = S / (double)M;
+  double unused = 0.0;
+  if (slots_commit(s, unused, gridDim.x, blockIdx.x, &acc[img], slots + (size_t)img * 2 * kStatMaxCtas, red) && threadIdx.x == 0) {
+    stats[4 * img + 0] = s / (double)M;
     stats[4 * img + 1] = 0.0;
     stats[4 * img + 2] = (double)M;
     stats[4 * img + 3] = 0.0;
@@ -118,7 +116,7 @@ __global__ void combine_cost_kernel(const double* __restrict__ stats, CombineDev
 void launch_combine(const double* stats, const CombineDev& cd, cudaStream_t s) { combine_cost_kernel<<<1, 32, 0, s>>>(stats, cd); }
 
 static inline int stat_grid(int64_t n) {
-  return (int)std::max<int64_t>(1, std::min<int64_t>((n + kStatBlock - 1) / kStatBlock, num_sms() * 2));
+  return (int)std::max<int64_t>(1, std::min<int64_t>({(n + kStatBlock - 1) / kStatBlock, (int64_t)num_sms() * 2, (int64_t)kStatMaxCtas}));
 }
 
 }  // namespace cmax
@@ -130,7 +128,8 @@ extern "C" {
 size_t cmax_stats_workspace_bytes(int n_img, int Hp, int Wp) {
   if (n_img < 1 || Hp < 1 || Wp < 1) return 0;
   const size_t acc = ((size_t)n_img * sizeof(StatAcc) + 255) / 256 * 256;
-  return acc + (size_t)n_img * 2 * Hp * Wp * sizeof(float);
+  const size_t slots = (size_t)n_img * 2 * kStatMaxCtas * sizeof(double);  // per-CTA partial sums (deterministic reduction)
+  return acc + slots + (size_t)n_img * 2 * Hp * Wp * sizeof(float);
 }
 
 int cmax_image_stats(const float* images, int n_img, int Hp, int Wp, int stat, int omit_boundary, double* d_stats, float* grad,
@@ -142,15 +141,16 @@ int cmax_image_stats(const float* images, int n_img, int Hp, int Wp, int stat, i
   cudaStream_t s = as_stream(stream);
   const size_t acc_bytes = ((size_t)n_img * sizeof(StatAcc) + 255) / 256 * 256;
   StatAcc* acc = static_cast<StatAcc*>(workspace);
-  float* gxy = reinterpret_cast<float*>(static_cast<char*>(workspace) + acc_bytes);
+  double* slots = reinterpret_cast<double*>(static_cast<char*>(workspace) + acc_bytes);
+  float* gxy = reinterpret_cast<float*>(static_cast<char*>(workspace) + acc_bytes + (size_t)n_img * 2 * kStatMaxCtas * sizeof(double));
   CMAX_CUDA_CHECK(cudaMemsetAsync(acc, 0, (size_t)n_img * sizeof(StatAcc), s));
   const int64_t HW = (int64_t)Hp * Wp;
   dim3 grid(stat_grid(HW), n_img);
   if (stat == CMAX_STAT_VARIANCE) {
-    variance_stats_kernel<<<grid, kStatBlock, 0, s>>>(images, Hp, Wp, omit_boundary ? 1 : 0, acc, d_stats);
+    variance_stats_kernel<<<grid, kStatBlock, 0, s>>>(images, Hp, Wp, omit_boundary ? 1 : 0, acc, slots, d_stats);
     if (grad) variance_grad_kernel<<<grid, 256, 0, s>>>(images, Hp, Wp, omit_boundary ? 1 : 0, d_stats, grad);
   } else {
-    gradmag_stats_kernel<<<grid, kStatBlock, 0, s>>>(images, Hp, Wp, omit_boundary ? 1 : 0, acc, d_stats, grad ? gxy : nullptr);
+    gradmag_stats_kernel<<<grid, kStatBlock, 0, s>>>(images, Hp, Wp, omit_boundary ? 1 : 0, acc, slots, d_stats, grad ? gxy : nullptr);
     if (grad) gradmag_grad_kernel<<<grid, 256, 0, s>>>(gxy, Hp, Wp, d_stats, grad);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());

@@ -119,11 +119,16 @@ __global__ void __launch_bounds__(256) keys_kernel(const float* __restrict__ ev,
                                                    int32_t* __restrict__ status) {
   const int64_t step = (int64_t)gridDim.x * blockDim.x;
   bool bad = false, frac = false;
+  int hi1 = 0, ilo = 0;  // max(row + 1), max(H - row) over the valid events: 0 = none (status[2], status[3])
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
     int r, c;
     const float x = __ldg(ev + i * stride), y = __ldg(ev + i * stride + 1);
     const bool ok = source_pixel(x, y, H, W, &r, &c);
     bad |= !ok;
+    if (ok) {
+      hi1 = max(hi1, r + 1);
+      ilo = max(ilo, H - r);
+    }
     frac |= (x != truncf(x)) || (y != truncf(y));
     if (keys != nullptr) {
       uint32_t key = 0u;
@@ -137,6 +142,12 @@ __global__ void __launch_bounds__(256) keys_kernel(const float* __restrict__ ev,
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(status, 1);
   if (__any_sync(0xffffffffu, frac) && (threadIdx.x & 31) == 0) atomicOr(status, 2);
+  hi1 = __reduce_max_sync(0xffffffffu, hi1);
+  ilo = __reduce_max_sync(0xffffffffu, ilo);
+  if ((threadIdx.x & 31) == 0 && hi1 > 0) {
+    atomicMax(status + 2, hi1);
+    atomicMax(status + 3, ilo);
+  }
 }
 
 // key_first[k] = index of the first event whose key is >= k (k in [0, n_keys]); events of key k are
@@ -265,7 +276,7 @@ static bool plan_layout(int64_t n, int H, int W, int order, PlanLayout* out) {
   size_t off = 0;
   L.off_params = off; off = align_up(off + sizeof(cmax_time_params_t), 256);
   L.off_minmax = off; off = align_up(off + 2 * sizeof(float), 256);
-  L.off_status = off; off = align_up(off + 2 * sizeof(int32_t), 256);  // [status bits, number of strips]
+  L.off_status = off; off = align_up(off + 4 * sizeof(int32_t), 256);  // [status bits, number of strips, max(row+1), max(H-row)]
   L.off_packed = off; off = align_up(off + (size_t)packed_slots(n) * sizeof(float4), 256);
   if (order != CMAX_ORDER_ASIS) {
     L.key_bits = bits_for((uint64_t)L.n_tiles * (order == CMAX_ORDER_PIXEL ? kTile * kTile : 1));
@@ -426,7 +437,7 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   // validation are safe on invalid input (an invalid event sorts under key 0), so the host can afford to learn about it last.
   int rc = CMAX_OK;
   float h_mm[2] = {t_min, t_max};
-  int32_t h_status[2] = {0, 0};  // [status bits, number of strips]
+  int32_t h_status[4] = {0, 0, 0, 0};  // [status bits, number of strips, max(source row + 1), max(H - source row)]
   const bool try_strips = sort && n > 0 && order == CMAX_ORDER_PIXEL && H < (1 << 13) && W < (1 << 13);
   uint32_t *kfirst = nullptr, *kstrip0 = nullptr;
   const uint32_t* sorted_keys = nullptr;
@@ -436,7 +447,7 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
     if (e__ != cudaSuccess) { rc = cuda_fail(e__, #call); goto fail; } \
   } while (0)
 
-  PLAN_CHECK(cudaMemsetAsync(p->d_status, 0, 2 * sizeof(int32_t), s));
+  PLAN_CHECK(cudaMemsetAsync(p->d_status, 0, 4 * sizeof(int32_t), s));
   {
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(num_sms() * 8, (n + 255) / 256));
     cub::DoubleBuffer<uint32_t> dk(reinterpret_cast<uint32_t*>(ws + L.off_keys[0]), reinterpret_cast<uint32_t*>(ws + L.off_keys[1]));
@@ -484,6 +495,8 @@ int cmax_plan_create(cmax_plan_t** plan, const float* events, int64_t n, int ev_
   p->compact = p->compact_ok;
   p->t_min = h_mm[0];
   p->t_max = h_mm[1];
+  p->src_row_lo = h_status[2] > 0 ? H - h_status[3] : H;  // rows that hold a source pixel of this batch (empty: lo > hi)
+  p->src_row_hi = h_status[2] - 1;
   // strips: integer coordinates, and dense enough that padding every pixel's run to whole strips stays below 50 %
   if (try_strips && p->compact_ok && (int64_t)(uint32_t)h_status[1] <= L.strip_capacity - 32) {
     p->strips = ws + L.off_strips;
@@ -521,6 +534,17 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 int cmax_plan_strips(const cmax_plan_t* plan, int64_t* h_n_strips) {
   CMAX_REQUIRE(plan != nullptr && h_n_strips != nullptr, "cmax_plan_strips: NULL argument");
   *h_n_strips = plan->strips != nullptr ? plan->n_strips : 0;
+  return CMAX_OK;
+}
+
+int cmax_plan_set_tile_flow(cmax_plan_t* plan, int hp, int wp, int pad_h, int pad_w, int sh, int sw, float t_scale) {
+  CMAX_REQUIRE(plan != nullptr, "cmax_plan_set_tile_flow: plan is NULL");
+  CMAX_REQUIRE(hp >= 1 && wp >= 1 && (int64_t)hp * wp <= 1024, "cmax_plan_set_tile_flow: the patch grid must have between 1 and 1024 nodes (got %dx%d)", hp, wp);
+  TileGeom g;
+  const int rc = make_tile_geom("cmax_plan_set_tile_flow", hp, wp, pad_h, pad_w, sh, sw, plan->H, plan->W, &g);
+  if (rc) return rc;
+  plan->tile = g;
+  plan->t_scale = t_scale;
   return CMAX_OK;
 }
 

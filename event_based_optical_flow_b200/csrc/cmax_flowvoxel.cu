@@ -43,12 +43,12 @@ struct FvAdjJob {
   const float* f[kFvK];  // input level of step s (the level whose cotangent step s produces)
   const float* gv[kFvK]; // cotangent arriving directly at that level (or NULL)
   float* out;            // cotangent of the near level
-  int accumulate;        // out += instead of out =
+  int accumulate;        // 0: out = ; 1: atomicAdd into a pre-zeroed buffer (the two sides of t0 finish in any order: a + b == b + a)
   int k;
   float sgn;
 };
 struct FvAdjArgs {
-  FvAdjJob job;
+  FvAdjJob job[2];       // blockIdx.z: the two sides of t0 run concurrently
   int H, W, scheme;
   float dt;
 };
@@ -211,7 +211,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArgs a) {
   __shared__ float wbuf[2][2][kFvCells];  // cotangent, ping-pong
   __shared__ float fbuf[2][kFvCells];     // input level of the current step (times the direction sign)
-  const FvAdjJob& job = a.job;
+  const FvAdjJob& job = a.job[blockIdx.z];
   const int k = job.k, H = a.H, W = a.W;
   const int64_t HW = (int64_t)H * W;
   const FvRegion R = fv_region(k);
@@ -268,8 +268,8 @@ __global__ void __launch_bounds__(kFvThreads) flow_voxel_adjoint_kernel(FvAdjArg
       NV[c] = gv;
       if (s == k && li >= k && li < k + kFvTH && lj >= k && lj < k + kFvTW) {
         if (job.accumulate) {
-          job.out[p] += gu;
-          job.out[HW + p] += gv;
+          atomicAdd(job.out + p, gu);
+          atomicAdd(job.out + HW + p, gv);
         } else {
           job.out[p] = gu;
           job.out[HW + p] = gv;
@@ -322,9 +322,9 @@ static void launch_fwd(const FvGeom& g, const FvFwdArgs& a, int njobs, cudaStrea
   if (g.scheme == CMAX_SCHEME_UPWIND) flow_voxel_kernel<0><<<fv_grid(g, njobs), kFvThreads, 0, s>>>(a);
   else flow_voxel_kernel<1><<<fv_grid(g, njobs), kFvThreads, 0, s>>>(a);
 }
-static void launch_adj(const FvGeom& g, const FvAdjArgs& a, cudaStream_t s) {
-  if (g.scheme == CMAX_SCHEME_UPWIND) flow_voxel_adjoint_kernel<0><<<fv_grid(g, 1), kFvThreads, 0, s>>>(a);
-  else flow_voxel_adjoint_kernel<1><<<fv_grid(g, 1), kFvThreads, 0, s>>>(a);
+static void launch_adj(const FvGeom& g, const FvAdjArgs& a, int njobs, cudaStream_t s) {
+  if (g.scheme == CMAX_SCHEME_UPWIND) flow_voxel_adjoint_kernel<0><<<fv_grid(g, njobs), kFvThreads, 0, s>>>(a);
+  else flow_voxel_adjoint_kernel<1><<<fv_grid(g, njobs), kFvThreads, 0, s>>>(a);
 }
 
 }  // namespace cmax
@@ -333,7 +333,7 @@ using namespace cmax;
 
 extern "C" {
 
-size_t cmax_flow_voxel_workspace_bytes(int H, int W) { return (H < 1 || W < 1) ? 0 : (size_t)2 * 2 * (size_t)H * W * sizeof(float); }
+size_t cmax_flow_voxel_workspace_bytes(int H, int W) { return (H < 1 || W < 1) ? 0 : (size_t)4 * 2 * (size_t)H * W * sizeof(float); }
 
 int cmax_flow_voxel(const float* dense, int H, int W, int time_bin, int scheme, int t0_middle, float* voxel, cmax_stream_t stream) {
   CMAX_REQUIRE(dense != nullptr && voxel != nullptr, "cmax_flow_voxel: NULL pointer");
@@ -390,25 +390,33 @@ int cmax_flow_voxel_backward(const float* dense, const float* voxel, const float
   }
   CMAX_REQUIRE((n[0] <= kFvK && n[1] <= kFvK) || workspace != nullptr,
                "cmax_flow_voxel_backward: more than %d levels on one side of t0 needs the workspace", kFvK);
-  float* carry[2] = {static_cast<float*>(workspace), workspace ? static_cast<float*>(workspace) + L : nullptr};
+  // carry buffers between the chunks of one side (only chains of more than 8 levels need them): two per side, ping-pong
+  float* carry[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  if (workspace != nullptr) {
+    float* wsf = static_cast<float*>(workspace);
+    carry[0][0] = wsf; carry[0][1] = wsf + L; carry[1][0] = wsf + 2 * L; carry[1][1] = wsf + 3 * L;
+  }
+  const bool both = n[0] > 0 && n[1] > 0;
+  if (both) CMAX_CUDA_CHECK(cudaMemsetAsync(grad_dense, 0, (size_t)L * sizeof(float), s));  // the two sides add into it
   FvAdjArgs a;
   a.H = H; a.W = W; a.scheme = scheme; a.dt = g.dt;
-  bool have_out = false;
   bool t0_direct = !g.wrap;  // the cotangent of level t0 reaches the input directly (voxel[t0] = dense): add it exactly once
-  for (int side = 0; side < 2; ++side) {
-    if (n[side] == 0) continue;
-    // walk from the far level back towards t0: step q undoes the forward step that produced lv[side][n-1-q]; its input
-    // level is lv[side][n-2-q], or the dense input itself for the first forward step of the side
-    int done = 0, pp = 0;
-    const float* w = grad_voxel + (int64_t)lv[side][n[side] - 1] * L;
-    while (done < n[side]) {
-      FvAdjJob& j = a.job;
+  int done[2] = {0, 0}, pp[2] = {0, 0};
+  const float* w[2] = {n[0] ? grad_voxel + (int64_t)lv[0][n[0] - 1] * L : nullptr, n[1] ? grad_voxel + (int64_t)lv[1][n[1] - 1] * L : nullptr};
+  // each side walks from its far level back towards t0 (step q undoes the forward step that produced lv[side][n-1-q]; its
+  // input level is lv[side][n-2-q], or the dense input itself for the first forward step of the side); wave = chunk of both
+  // sides in ONE launch
+  while (done[0] < n[0] || done[1] < n[1]) {
+    int nj = 0;
+    for (int side = 0; side < 2; ++side) {
+      if (done[side] >= n[side]) continue;
+      FvAdjJob& j = a.job[nj++];
       memset(&j, 0, sizeof(j));
-      j.k = std::min(kFvK, n[side] - done);
-      j.w_init = w;
+      j.k = std::min(kFvK, n[side] - done[side]);
+      j.w_init = w[side];
       j.sgn = side == 0 ? 1.f : -1.f;
       for (int q = 0; q < j.k; ++q) {
-        const int in = n[side] - 2 - (done + q);  // index into lv of the step's input level; -1 = the dense input
+        const int in = n[side] - 2 - (done[side] + q);  // index into lv of the step's input level; -1 = the dense input
         if (in >= 0) {
           j.f[q] = voxel + (int64_t)lv[side][in] * L;
           j.gv[q] = grad_voxel + (int64_t)lv[side][in] * L;
@@ -418,19 +426,18 @@ int cmax_flow_voxel_backward(const float* dense, const float* voxel, const float
           t0_direct = false;
         }
       }
-      done += j.k;
-      if (done == n[side]) {
+      done[side] += j.k;
+      if (done[side] == n[side]) {
         j.out = grad_dense;
-        j.accumulate = have_out ? 1 : 0;
+        j.accumulate = both ? 1 : 0;
       } else {
-        j.out = carry[pp];
+        j.out = carry[side][pp[side]];
         j.accumulate = 0;
-        w = carry[pp];
-        pp ^= 1;
+        w[side] = carry[side][pp[side]];
+        pp[side] ^= 1;
       }
-      launch_adj(g, a, s);
     }
-    have_out = true;
+    launch_adj(g, a, nj, s);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;

@@ -767,6 +767,8 @@ FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.n_strips = p->n_strips;
   a.strip_tile_bytes = p->strip_tile_bytes;
   a.zero256 = nullptr;
+  a.tile = p->tile;
+  a.t_scale = p->t_scale;
   return a;
 }
 

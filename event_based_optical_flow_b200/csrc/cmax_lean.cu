@@ -50,12 +50,14 @@ struct StripTileBytes {
 
 // Per-strip constants.
 struct StripHead {
-  int count, src;
+  int count, src, row, col;
   f32x2 xy;
 };
 __device__ __forceinline__ StripHead strip_head(uint32_t h, int W) {
   StripHead s;
   const unsigned row = h >> 17, col = (h >> 4) & 0x1FFFu;
+  s.row = (int)row;
+  s.col = (int)col;
   s.count = (int)(h & 0xFu);
   s.src = (int)(row * (unsigned)W + col);
   s.xy = pk2(small_int_to_float(row), small_int_to_float(col));
@@ -93,7 +95,17 @@ template <int MODEL, int NREF, bool PRE_DT>
 __device__ __forceinline__ f32x2 lean_warp(f32x2 xy, float tz, f32x2 f, const RefRegs<NREF>& rr, int r, float& dt) {
   dt = PRE_DT ? tz : __fdiv_rn(__fsub_rn(tz, rr.ref[r]), rr.period[r]);
   if (MODEL == CMAX_MOTION_2DOF) return add2(xy, mul2_rounded(f, dt));  // src/warp.py:507-514
-  return sub2(xy, mul2_rounded(f, dt));                                   // src/warp.py:306-307
+  return sub2(xy, mul2_rounded(f, dt));                                   // src/warp.py:306-307 (dense flow, or the tile flow at this pixel)
+}
+
+// Tile flow (CMAX_MOTION_TILE): the dense flow is never materialised -- every strip evaluates the patch grid at ITS source
+// pixel with the up-sampling kernel's own expression (tile_value, bit-identical), times t_scale (the reference multiplies the
+// up-sampled flow by it, src/solver/patch_contrast_pyramid.py:452-453).  The <= 2 KB grid stays in L1.
+constexpr int kTileMaxNodes = 1024;  // patch grids up to 32 x 32
+__device__ __forceinline__ f32x2 tile_flow_at(const FusedArgs& a, const StripHead& h, TileTaps& t) {
+  t = tile_taps(a.tile, h.row, h.col);
+  const int np = a.tile.hp * a.tile.wp;
+  return pk2(__fmul_rn(tile_value(a.motion, a.tile, t), a.t_scale), __fmul_rn(tile_value(a.motion + np, a.tile, t), a.t_scale));
 }
 
 // Time-aware (voxel) model: the flow vector depends on the event's time bin (src/warp.py:346-357).  The bin of every event
@@ -188,6 +200,10 @@ __global__ void __launch_bounds__(kRunThreads) vote_strips_kernel(FusedArgs a, f
     const StripTile* T = reinterpret_cast<const StripTile*>(pipe.buf[stage]);
     const StripHead h = strip_head(T->head[lane], a.W);
     if (MODEL == CMAX_MOTION_DENSE) f = pk2(__ldg(a.motion + h.src), __ldg(a.motion + HW + h.src));
+    if (MODEL == CMAX_MOTION_TILE) {
+      TileTaps taps;
+      f = tile_flow_at(a, h, taps);
+    }
     const float4 ta = T->t[0][lane], tb = T->t[1][lane];
     const float tz[kRunE] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
     uint2 bins[NREF];
@@ -273,11 +289,19 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
   constexpr uint32_t kTile = StripTileBytes<MODEL, NREF>::value;
   __shared__ TilePipe<kTile> pipes[kRunWarps];
   __shared__ double red2[2][kRunWarps];
+  // tile flow: dL/d(patch grid) of this CTA, accumulated in shared memory (the adjoint of the up-sampling: every source pixel
+  // hands its flow gradient to its <= 4 grid nodes) and added to the global gradient once per CTA
+  __shared__ float sgrad[MODEL == CMAX_MOTION_TILE ? 2 * kTileMaxNodes : 1];
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
   const int lane = threadIdx.x & 31;
   const int off_r = a.pad_h + 1 - 0x4B400000, off_c = a.pad_w + 1 - 0x4B400000;
   const int outside = (int)a.cells - 1;
+  const int np = a.tile.hp * a.tile.wp;
+  if (MODEL == CMAX_MOTION_TILE) {
+    for (int k = threadIdx.x; k < 2 * np; k += kRunThreads) sgrad[k] = 0.f;
+    __syncthreads();
+  }
   TilePipe<kTile>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
   const int64_t n_tiles = (a.n_strips + 31) / 32;
@@ -296,6 +320,8 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     const StripTile* T = reinterpret_cast<const StripTile*>(pipe.buf[stage]);
     const StripHead h = strip_head(T->head[lane], a.W);
     if (MODEL == CMAX_MOTION_DENSE) f = pk2(__ldg(a.motion + h.src), __ldg(a.motion + HW + h.src));
+    TileTaps taps;
+    if (MODEL == CMAX_MOTION_TILE) f = tile_flow_at(a, h, taps);
     const float4 ta = T->t[0][lane], tb = T->t[1][lane];
     const float tz[kRunE] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
     uint2 bins[NREF];
@@ -324,6 +350,25 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
         atomicAdd(gmotion + h.src, g0);
         atomicAdd(gmotion + HW + h.src, g1);
       }
+    } else if (MODEL == CMAX_MOTION_TILE) {
+      // dense[c] = -t_scale * sum_ab Wr[a] Wc[b] m[c,a,b]  =>  dL/dm[c,a,b] += -t_scale * Wr[a] Wc[b] * dL/ddense[c]
+      if (h.count > 0) {
+        float g0, g1;
+        upk2(st.g[0], g0, g1);
+        g0 *= -a.t_scale;
+        g1 *= -a.t_scale;
+        const float wr[2] = {1.0f - taps.lr, taps.lr}, wc[2] = {1.0f - taps.lc, taps.lc};
+        const int an[2] = {taps.a0, taps.a1}, bn[2] = {taps.b0, taps.b1};
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const float w = wr[u] * wc[v];
+            const int node = an[u] * a.tile.wp + bn[v];
+            atomicAdd(&sgrad[node], w * g0);
+            atomicAdd(&sgrad[np + node], w * g1);
+          }
+      }
     } else if (MODEL == CMAX_MOTION_VOXEL) {
 #pragma unroll
       for (int q = 0; q < NREF; ++q) {
@@ -339,6 +384,13 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
       upk2(st.g[0], g0, g1);
       t0 -= (double)g0;
       t1 -= (double)g1;
+    }
+  }
+  if (MODEL == CMAX_MOTION_TILE) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * np; k += kRunThreads) {
+      const float v = sgrad[k];
+      if (v != 0.f) atomicAdd(gmotion + k, v);
     }
   }
   if (MODEL == CMAX_MOTION_2DOF) {
@@ -417,6 +469,7 @@ int strips_tile_bytes_for(int motion_model, int n_ref) {
 void launch_vote_strips(int motion_model, int n_ref, cudaStream_t s, const FusedArgs& a, float4* acc) {
   if (motion_model == CMAX_MOTION_DENSE) vote_strips_m<CMAX_MOTION_DENSE>(n_ref, s, a, acc);
 #ifndef CMAX_LEAN_DEV
+  else if (motion_model == CMAX_MOTION_TILE) vote_strips_m<CMAX_MOTION_TILE>(n_ref, s, a, acc);
   else if (motion_model == CMAX_MOTION_VOXEL) vote_strips_m<CMAX_MOTION_VOXEL>(n_ref, s, a, acc);
   else vote_strips_m<CMAX_MOTION_2DOF>(n_ref, s, a, acc);
 #endif
@@ -424,6 +477,7 @@ void launch_vote_strips(int motion_model, int n_ref, cudaStream_t s, const Fused
 void launch_grad_strips(int motion_model, int n_ref, bool pdl, cudaStream_t s, const FusedArgs& a, const float4* gq, float* gmotion) {
   if (motion_model == CMAX_MOTION_DENSE) grad_strips_m<CMAX_MOTION_DENSE>(n_ref, pdl, s, a, gq, gmotion);
 #ifndef CMAX_LEAN_DEV
+  else if (motion_model == CMAX_MOTION_TILE) grad_strips_m<CMAX_MOTION_TILE>(n_ref, pdl, s, a, gq, gmotion);
   else if (motion_model == CMAX_MOTION_VOXEL) grad_strips_m<CMAX_MOTION_VOXEL>(n_ref, pdl, s, a, gq, gmotion);
   else grad_strips_m<CMAX_MOTION_2DOF>(n_ref, pdl, s, a, gq, gmotion);
 #endif

@@ -16,7 +16,7 @@ namespace cmax {
 // ------------------------------------------------------------------------------------------------ cross-GPU signalling
 // One process per GPU; workspaces, partial gradients and flags live in symmetric (peer-mapped) memory.  A flag is a
 // monotonically increasing evaluation counter: rank r stores epoch e into ITS slot of every rank's flag array once its
-// partial result of evaluation e is complete and visible (one fence.sys + one posted store per peer, issued by the last
+// partial result of evaluation e is complete and visible (one gpu-scope fence + one posted store per peer, issued by the last
 // CTA to finish -- no barrier kernel, no round trip), and a consumer spins on its OWN (local) flag array until every
 // source rank has reached e.  Two flag arrays alternate per evaluation (IWE, gradient), which is what makes buffer reuse
 // safe without further synchronisation: a rank overwrites its partial IWE for evaluation e+1 only after it has seen
@@ -27,13 +27,13 @@ namespace cmax {
 // PRODUCER's memory, whose L2 is the point of coherence for its own SMs and for NVLink peer reads alike -- a gpu-scope
 // fence (all prior writes performed at that L2) before the posted flag store is enough for a reader that first sees the
 // flag and then issues its loads; the consumers' loads are .cg (never served from an L1) and control-dependent on the poll.
-__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_v4(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   unsigned int v;
@@ -41,36 +41,45 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   return v;
 }
 
+// A flag is one 16-byte RECORD {epoch, row_lo, row_hi, -}, written with one 16-byte store and polled with 16-byte loads: next
+// to "my partial result of evaluation `epoch` is complete" it tells the reader which image rows of that partial result can be
+// non-zero at all.  A reader skips the peers whose range misses its rows (exact: what it skips are zeros), so when the
+// shards are spatially compact (distributed.reshard_events_by_pixel) the exchange moves the overlaps only instead of N whole
+// images per rank; for time-sliced shards the ranges are the whole image and nothing changes.
 struct PeerEx {
   int n, rank;                             // n == 0: not sharded
   const float* part[CMAX_MAX_PEERS];       // every rank's partial buffer (rank order)
-  uint32_t* flag_at[CMAX_MAX_PEERS];       // this rank's slot in rank q's flag array
-  const uint32_t* flags;                   // this rank's own flag array
+  uint4* rec_at[CMAX_MAX_PEERS];           // this rank's record in rank q's block
+  const uint4* recs;                       // this rank's own block, one record per source rank
   uint32_t* epoch;                         // this rank's evaluation counter (advanced by image_kernel)
 };
 
-// Block until flags[0..n) have all reached `epoch` (every CTA of a consumer calls this).  A peer that never arrives
-// (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which surfaces as a CUDA error.
-__device__ __forceinline__ void wait_flags(const uint32_t* __restrict__ flags, uint32_t epoch, int n) {
+// Block until every source rank's record has reached `epoch` (every CTA of a consumer calls this); the row ranges land in
+// shared memory.  A peer that never arrives (crashed rank) would hang the GPU: after ~4 s the kernel traps instead, which
+// surfaces as a CUDA error.
+__device__ __forceinline__ void wait_flags(const uint4* __restrict__ recs, uint32_t epoch, int n, int* sh_lo, int* sh_hi) {
   if ((int)threadIdx.x < n) {
     const long long t0 = clock64();
-    while ((int32_t)(ld_relaxed_sys(flags + threadIdx.x) - epoch) < 0) {
+    uint4 r = ld_relaxed_sys_v4(recs + threadIdx.x);
+    while ((int32_t)(r.x - epoch) < 0) {
       if (clock64() - t0 > 8000000000ll) __trap();
+      r = ld_relaxed_sys_v4(recs + threadIdx.x);
     }
+    sh_lo[threadIdx.x] = (int)r.y;
+    sh_hi[threadIdx.x] = (int)r.z;
   }
   __syncthreads();
 }
 
-// Publish: the calling WARP raises this rank's flag on every peer.  Everything this rank wrote before (ordered before the
-// caller by barriers / the arrival counter) is performed at this GPU's L2 after the fence; the flag stores themselves are
+// Publish: the calling WARP raises this rank's record on every peer.  Everything this rank wrote before (ordered before the
+// caller by barriers / the arrival counter) is performed at this GPU's L2 after the fence; the record stores themselves are
 // posted, one lane per peer, in parallel.
-__device__ __forceinline__ void raise_flags(const PeerEx& px, uint32_t epoch) {
+__device__ __forceinline__ void raise_flags(const PeerEx& px, uint32_t epoch, int row_lo, int row_hi) {
   __threadfence();
   __syncwarp();
   const int lane = threadIdx.x & 31;
-  if (lane < px.n) st_relaxed_sys(px.flag_at[lane], epoch);
+  if (lane < px.n) st_relaxed_sys_v4(px.rec_at[lane], make_uint4(epoch, (uint32_t)row_lo, (uint32_t)row_hi, 0u));
 }
-
 
 // Grid-wide barrier of a co-resident grid: `bar` counts arrivals (cleared before the launch), every CTA arrives once.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int n_ctas, bool wait) {
@@ -145,6 +154,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
   __shared__ double sh_cost;
   __shared__ float sh_aff[2 * CMAX_MAX_REFS];
   __shared__ uint32_t sh_epoch;
+  __shared__ int sh_lo[CMAX_MAX_PEERS], sh_hi[CMAX_MAX_PEERS];  // sharded: rows of every rank's partial IWE that can be non-zero
 #ifdef CMAX_MEASURE
   unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.slots) + 2048 + blockIdx.x * 8;
 #endif
@@ -187,6 +197,7 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
   };
 
   // ---- phase 1: fold (and, on one GPU, the variance sums of the folded image).  Two pixels per round, loads first.
+  int nz_hi1 = 0, nz_ilo = 0;  // sharded: max(row + 1) / max(Hp - row) over the non-zero pixels of this rank's partial IWEs
   if (a.fold || (a.stats && !SHARDED)) {
     for (int img = 0; img < a.n_ref; ++img) {
       float* A = reinterpret_cast<float*>(a.acc + (size_t)img * cells);
@@ -213,6 +224,16 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
             v1 = ((x1 + y1) + z1) + w1;
             I[p1] = v1;
           }
+          if (SHARDED) {
+            if (v0 != 0.f) {
+              nz_hi1 = max(nz_hi1, (int)r0 + 1);
+              nz_ilo = max(nz_ilo, (int)(Hp - r0));
+            }
+            if (two && v1 != 0.f) {
+              nz_hi1 = max(nz_hi1, (int)r1 + 1);
+              nz_ilo = max(nz_ilo, (int)(Hp - r1));
+            }
+          }
         } else {
           v0 = I[p0];
           if (two) v1 = I[p1];
@@ -237,15 +258,28 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
   // ---- phase 2 (sharded): signal, wait, sum the partial images of all ranks in rank order (bit-identical on every rank)
   if (SHARDED) {
     __shared__ bool last;
+    __shared__ int sh_rows[2];
+    nz_hi1 = __reduce_max_sync(0xffffffffu, nz_hi1);
+    nz_ilo = __reduce_max_sync(0xffffffffu, nz_ilo);
+    if (lane == 0 && nz_hi1 > 0) {
+      atomicMax(&a.bar[2], (unsigned)nz_hi1);
+      atomicMax(&a.bar[3], (unsigned)nz_ilo);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
       last = (atomicAdd(&a.bar[0], 1u) == gridDim.x - 1);
-      if (last) *a.px.epoch = epoch;  // (every CTA has read the old value by now)
+      if (last) {
+        *a.px.epoch = epoch;  // (every CTA has read the old value by now)
+        __threadfence();
+        const int hi1 = (int)ld_relaxed_gpu(&a.bar[2]), ilo = (int)ld_relaxed_gpu(&a.bar[3]);
+        sh_rows[0] = hi1 > 0 ? (int)Hp - ilo : (int)Hp;  // empty: lo > hi
+        sh_rows[1] = hi1 - 1;
+      }
     }
     __syncthreads();
-    if (last && wid == 0) raise_flags(a.px, epoch);  // every CTA of this rank has folded: publish
-    wait_flags(a.px.flags, epoch, a.px.n);
+    if (last && wid == 0) raise_flags(a.px, epoch, sh_rows[0], sh_rows[1]);  // every CTA of this rank has folded: publish
+    wait_flags(a.px.recs, epoch, a.px.n, sh_lo, sh_hi);
     STAMP(7);
     for (int img = 0; img < a.n_ref; ++img) {
       double s = 0.0, q = 0.0;
@@ -259,10 +293,14 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
       if ((HW & 3u) == 0) {
         // 16-byte peer loads, all ranks' loads of a thread in flight together: one NVLink round trip per thread
         for (unsigned p4 = tid; p4 < (HW >> 2); p4 += nthr) {
+          const int row_a = (int)((4u * p4) / Wp), row_b = (int)((4u * p4 + 3u) / Wp);  // rows this group of 4 pixels touches
           float4 part[CMAX_MAX_PEERS];
 #pragma unroll
-          for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-            if (r < a.px.n) part[r] = __ldcg(reinterpret_cast<const float4*>(a.px.part[r] + (size_t)img * HW) + p4);  // L2-coherent: another GPU wrote it
+          for (int r = 0; r < CMAX_MAX_PEERS; ++r) {
+            part[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < a.px.n && row_b >= sh_lo[r] && row_a <= sh_hi[r])  // (a peer whose rows miss these pixels holds zeros there)
+              part[r] = __ldcg(reinterpret_cast<const float4*>(a.px.part[r] + (size_t)img * HW) + p4);  // L2-coherent: another GPU wrote it
+          }
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < CMAX_MAX_PEERS; ++r)
@@ -274,8 +312,10 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
         }
       } else {
         for (unsigned p = tid; p < HW; p += nthr) {
+          const int row = (int)(p / Wp);
           float v = 0.f;
-          for (int r = 0; r < a.px.n; ++r) v += __ldcg(a.px.part[r] + (size_t)img * HW + p);
+          for (int r = 0; r < a.px.n; ++r)
+            if (row >= sh_lo[r] && row <= sh_hi[r]) v += __ldcg(a.px.part[r] + (size_t)img * HW + p);
           a.iwe_full[(size_t)img * HW + p] = v;
           account(p, v);
         }
@@ -372,24 +412,41 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ gradient exchange
-// out[i] = sum over ranks of part[r][i], rank order.  CTA 0 raises this rank's gradient flag on every peer first (K3 is
-// complete: stream order), then every CTA waits for all ranks' flags and pulls.  n == 0 closes a value-only evaluation.
-__global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n, float* __restrict__ out, unsigned long long* probe) {
+// out[i] = sum over ranks of part[r][i], rank order.  CTA 0 raises this rank's gradient record on every peer first (K3 is
+// complete: stream order), then every CTA waits for all ranks' records and pulls.  n == 0 closes a value-only evaluation.
+// The motion gradient is `n / plane` planes of [H, W] (plane == 0: no image structure, e.g. the 2-dof model): a rank's
+// partial gradient is non-zero only in the rows that hold source pixels of ITS events (row_lo .. row_hi, fixed per plan).
+__global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n, int plane, int W, int row_lo, int row_hi, float* __restrict__ out,
+                                                            unsigned long long* probe) {
+  __shared__ int sh_lo[CMAX_MAX_PEERS], sh_hi[CMAX_MAX_PEERS];
 #ifdef CMAX_MEASURE
   unsigned long long* stamps = probe + (blockIdx.x & 63) * 8;
 #endif
   STAMP(0);
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(px.epoch);  // already advanced by this evaluation's image_kernel
-  if (blockIdx.x == 0 && threadIdx.x < 32) raise_flags(px, epoch);
-  wait_flags(px.flags, epoch, px.n);
+  if (blockIdx.x == 0 && threadIdx.x < 32) raise_flags(px, epoch, row_lo, row_hi);
+  wait_flags(px.recs, epoch, px.n, sh_lo, sh_hi);
   STAMP(1);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const unsigned uplane = (unsigned)plane, uW = (unsigned)W;
   if ((n & 3) == 0) {
     for (int64_t i = tid; i < (n >> 2); i += nthr) {
+      int row_a = 0, row_b = 0;
+      if (plane > 0) {
+        const unsigned e0 = (unsigned)((4 * i) % uplane), e1 = (unsigned)((4 * i + 3) % uplane);
+        row_a = (int)(e0 / uW);
+        row_b = (int)(e1 / uW);
+        if (e1 < e0) {  // the group straddles two planes: take every row
+          row_a = 0;
+          row_b = 0x7fffffff;
+        }
+      }
       float4 part[CMAX_MAX_PEERS];
 #pragma unroll
-      for (int r = 0; r < CMAX_MAX_PEERS; ++r)
-        if (r < px.n) part[r] = __ldcg(reinterpret_cast<const float4*>(px.part[r]) + i);
+      for (int r = 0; r < CMAX_MAX_PEERS; ++r) {
+        part[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < px.n && (plane == 0 || (row_b >= sh_lo[r] && row_a <= sh_hi[r]))) part[r] = __ldcg(reinterpret_cast<const float4*>(px.part[r]) + i);
+      }
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < CMAX_MAX_PEERS; ++r)
@@ -400,8 +457,10 @@ __global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n
     }
   } else {
     for (int64_t i = tid; i < n; i += nthr) {
+      const int row = plane > 0 ? (int)((unsigned)(i % uplane) / uW) : 0;
       float v = 0.f;
-      for (int r = 0; r < px.n; ++r) v += __ldcg(px.part[r] + i);
+      for (int r = 0; r < px.n; ++r)
+        if (plane == 0 || (row >= sh_lo[r] && row <= sh_hi[r])) v += __ldcg(px.part[r] + i);
       out[i] = v;
     }
   }
@@ -416,9 +475,15 @@ __global__ void finish_2dof_kernel(const double* __restrict__ acc2, float* __res
 // ------------------------------------------------------------------------------------------------ host side
 static int check_model(const char* fn, const cmax_plan* p, int model) {
   CMAX_REQUIRE(p != nullptr, "%s: plan is NULL", fn);
-  CMAX_REQUIRE(model == CMAX_MOTION_DENSE || model == CMAX_MOTION_VOXEL || model == CMAX_MOTION_2DOF,
+  CMAX_REQUIRE(model == CMAX_MOTION_DENSE || model == CMAX_MOTION_VOXEL || model == CMAX_MOTION_2DOF || model == CMAX_MOTION_TILE,
                "%s: motion model %d not supported", fn, model);
   CMAX_REQUIRE(model != CMAX_MOTION_VOXEL || p->n_bins >= 1, "%s: dense-flow-voxel needs cmax_plan_set_refs(..., n_bins >= 1)", fn);
+  if (model == CMAX_MOTION_TILE) {
+    CMAX_REQUIRE(p->tile.hp > 0, "%s: the tile-flow model needs cmax_plan_set_tile_flow first", fn);
+    CMAX_REQUIRE(p->n == 0 || (p->strips != nullptr && p->vote_variant == 5 && p->grad_variant == 5 &&
+                               p->strip_tile_bytes == strips_tile_bytes_for(CMAX_MOTION_DENSE, p->n_ref)),
+                 "%s: the tile-flow model runs on the strip kernels only (this plan has no strips, or another variant is selected)", fn);
+  }
   return CMAX_OK;
 }
 
@@ -442,6 +507,7 @@ static inline size_t motion_floats(const cmax_plan* p, int motion_model) {
   const size_t HW = (size_t)p->H * p->W;
   if (motion_model == CMAX_MOTION_DENSE) return 2 * HW;
   if (motion_model == CMAX_MOTION_VOXEL) return 2 * (size_t)p->n_bins * HW;
+  if (motion_model == CMAX_MOTION_TILE) return 2 * (size_t)p->tile.hp * p->tile.wp;
   return 2;
 }
 
@@ -483,9 +549,9 @@ static PeerEx peer_ex(const cmax_peers* peers, const float* const* part, int fla
   px.rank = peers->rank;
   for (int r = 0; r < peers->n_peers; ++r) {
     px.part[r] = part[r];
-    px.flag_at[r] = peers->flags[r] + flag_block * CMAX_MAX_PEERS + peers->rank;
+    px.rec_at[r] = reinterpret_cast<uint4*>(peers->flags[r]) + flag_block * CMAX_MAX_PEERS + peers->rank;
   }
-  px.flags = peers->flags[peers->rank] + flag_block * CMAX_MAX_PEERS;
+  px.recs = reinterpret_cast<const uint4*>(peers->flags[peers->rank]) + flag_block * CMAX_MAX_PEERS;
   px.epoch = w.epoch;
   return px;
 }
@@ -514,7 +580,8 @@ static int launch_k1(const cmax_plan* p, int motion_model, const float* motion, 
       const int rc = ensure_packed(p, s);
       if (rc) return rc;
     }
-    launch_vote_any(p, motion_model, s, a, w.acc, w.iwe);
+    if (motion_model == CMAX_MOTION_TILE) launch_vote_strips(motion_model, p->n_ref, s, a, w.acc);
+    else launch_vote_any(p, motion_model, s, a, w.acc, w.iwe);
   }
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
@@ -593,7 +660,8 @@ static int grad_stage(const cmax_plan* p, int motion_model, const float* motion,
       if (rc) return rc;
     }
     float* target = (motion_model == CMAX_MOTION_2DOF) ? reinterpret_cast<float*>(w.acc2) : grad_motion;
-    launch_grad_any(p, motion_model, s, a, w.gq, target);
+    if (motion_model == CMAX_MOTION_TILE) launch_grad_strips(motion_model, p->n_ref, pdl_enabled(), s, a, w.gq, target);
+    else launch_grad_any(p, motion_model, s, a, w.gq, target);
   }
   if (motion_model == CMAX_MOTION_2DOF && (p->stage_mask & 2)) finish_2dof_kernel<<<1, 32, 0, s>>>(w.acc2, grad_motion);
   CMAX_CUDA_CHECK(cudaGetLastError());
@@ -762,7 +830,9 @@ int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const floa
   const int64_t n = want_grad ? (int64_t)n_motion : 0;
   const int64_t work = (n & 3) == 0 ? n / 4 : n;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)num_sms() * 2));
-  grad_exchange_kernel<<<grid, 256, 0, s>>>(gx, n, grad_motion, reinterpret_cast<unsigned long long*>(w.slots) + 2048 + 148 * 8);
+  const int plane = (motion_model == CMAX_MOTION_2DOF || motion_model == CMAX_MOTION_TILE) ? 0 : p->H * p->W;
+  grad_exchange_kernel<<<grid, 256, 0, s>>>(gx, n, plane, p->W, p->src_row_lo, p->src_row_hi, grad_motion,
+                                            reinterpret_cast<unsigned long long*>(w.slots) + 2048 + 148 * 8);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
 }

@@ -33,9 +33,9 @@ static inline ObjLayout obj_layout(int Hp, int Wp) {
   L.off_stats = off;   off = align256(off + (size_t)R * 4 * sizeof(double));
   L.off_affine = off;  off = align256(off + (size_t)R * 2 * sizeof(float));
   L.off_misc = off;    off = align256(off + 2 * sizeof(double));  // 2-dof fp64 staging
-  // [StatAcc block][Sobel pair] is exactly the workspace layout cmax_image_stats expects (cmax_cost.cu)
+  // [StatAcc block][per-CTA slots][Sobel pair] is the workspace cmax_image_stats carves for itself (cmax_cost.cu)
   L.off_statacc = off; off = align256(off + (size_t)R * sizeof(StatAcc));
-  L.off_gxy = off;     off = align256(off + (size_t)R * 2 * L.HW * sizeof(float));
+  L.off_gxy = off;     off = align256(off + (size_t)R * 2 * kStatMaxCtas * sizeof(double) + (size_t)R * 2 * L.HW * sizeof(float));
   L.off_g = off;       off = align256(off + (size_t)R * L.HW * sizeof(float));
   L.off_g2 = off;      off = align256(off + (size_t)R * L.HW * sizeof(float));
   L.off_gq = off;      off = align256(off + (size_t)R * L.cells * sizeof(float4));

@@ -1,6 +1,7 @@
 // Host-side plan handle (opaque to C callers) + tile geometry shared by the fused kernels.
 #pragma once
 #include "cmax_common.cuh"
+#include "cmax_tile.cuh"
 
 namespace cmax {
 
@@ -38,6 +39,8 @@ struct cmax_plan {
   int64_t n;
   int H, W, pad_h, pad_w, Hp, Wp;
   float t_min, t_max;
+  int src_row_lo, src_row_hi;  // rows of the un-warped image that hold events of this batch (a sharded batch that is spatially
+                               // compact publishes them, and its peers skip the rows it cannot have touched)
   int order;         // cmax_order
   int vote_variant;  // see cmax_plan_set_variant
   int grad_variant;
@@ -47,4 +50,6 @@ struct cmax_plan {
   float* d_minmax;               // device [2]
   int32_t* d_status;             // device [1]
   int n_ref, n_bins;
+  cmax::TileGeom tile;  // CMAX_MOTION_TILE geometry (cmax_plan_set_tile_flow); tile.hp == 0: not set
+  float t_scale;
 };

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "cmax_plan.cuh"
+#include "cmax_tile.cuh"
 
 namespace cmax {
 
@@ -22,6 +23,8 @@ struct FusedArgs {
   const cmax_time_params_t* tp;
   int64_t cells;  // (Hp+1)*(Wp+1)
   unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block + grid-barrier counters), or NULL
+  TileGeom tile;          // CMAX_MOTION_TILE: `motion` is the patch grid [2,hp,wp], evaluated per source pixel by the kernels
+  float t_scale;
 };
 
 // Time parameters one CTA needs, staged in shared memory once per CTA.

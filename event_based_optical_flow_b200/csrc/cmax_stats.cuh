@@ -27,29 +27,34 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
-// Adds this CTA's partial (sum, sum of squares) to the image's accumulator; the last CTA of `n_ctas` turns the
-// totals into {unbiased variance, mean, M, 0}.  Call from all threads of the CTA.    src/costs/image_variance.py:47-58
-__device__ __forceinline__ void variance_commit(double s, double q, int64_t M, unsigned int n_ctas, StatAcc* acc,
-                                                double* stats4, double* red) {
+constexpr int kStatMaxCtas = 512;  // per-CTA slots of the statistics kernels (grids are capped at this)
+
+// Deterministic grid-wide sums: every CTA writes its partial (s, q) to ITS slot of the image and counts itself in; the last
+// CTA to arrive sums the slots in a fixed order (thread-strided, then the fixed shuffle tree).  No floating-point atomics:
+// the totals -- hence cost and gradient -- are bit-identical from run to run and, for sharded batches, on every rank, which is
+// what keeps SPMD optimisers in lock-step.  Returns true in the threads of the CTA that holds the totals (valid in thread 0).
+__device__ __forceinline__ bool slots_commit(double& s, double& q, unsigned int n_ctas, unsigned int cta, StatAcc* acc, double* slots,
+                                             double* red) {
   s = block_sum(s, red);
   q = block_sum(q, red);
   __shared__ bool last;
   if (threadIdx.x == 0) {
-    atomicAdd(&acc->sum, s);
-    atomicAdd(&acc->sumsq, q);
+    slots[2 * cta] = s;
+    slots[2 * cta + 1] = q;
     __threadfence();
     last = (atomicAdd(&acc->done, 1u) == n_ctas - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    const double S = *(volatile double*)&acc->sum, Q = *(volatile double*)&acc->sumsq;
-    const double mean = S / (double)M;
-    stats4[0] = (Q - S * mean) / (double)(M - 1);  // unbiased (torch.var default)
-    stats4[1] = mean;
-    stats4[2] = (double)M;
-    stats4[3] = 0.0;
+  if (!last) return false;
+  __threadfence();
+  double ts = 0.0, tq = 0.0;
+  for (unsigned int c = threadIdx.x; c < n_ctas; c += blockDim.x) {
+    ts += __ldcg(slots + 2 * c);
+    tq += __ldcg(slots + 2 * c + 1);
   }
+  s = block_sum(ts, red);
+  q = block_sum(tq, red);
+  return true;
 }
 
 // ---- scalar cost combination, shared by combine_cost_kernel (cmax_cost.cu) and the fold kernel's last CTA

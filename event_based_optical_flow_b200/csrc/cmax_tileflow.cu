@@ -6,49 +6,18 @@
 // Wc (after the replicate padding is folded onto the border nodes).  Forward = one thread per pixel (4 taps per
 // channel, the grid is <= a few hundred floats and lives in L1); adjoint = a gather per grid node over its support --
 // no atomics, so the gradient of the 512-parameter motion is deterministic.
-#include "cmax_common.cuh"
+#include "cmax_tile.cuh"
 
 namespace cmax {
-
-struct TileGeom {
-  int hp, wp;        // patch grid
-  int pad_h, pad_w;  // replicate padding of the grid
-  int sh, sw;        // integer up-sampling factors (the sliding window)
-  int H, W;          // image
-  int h1, w1;        // crop offsets inside the up-sampled padded grid
-};
-
-// Source taps of output index `full` (coordinates of the up-sampled padded grid) along one axis, PyTorch bilinear
-// align_corners=false semantics: src = max(0, (full + 0.5) / s - 0.5); taps i0 = floor(src), i1 = min(i0 + 1, n_pad - 1)
-// with weights (1 - l, l); padded index p -> grid node clamp(p - pad, 0, n - 1) (replicate padding).
-__device__ __forceinline__ void axis_taps(int full, int s, int n, int pad, int* a0, int* a1, float* l1) {
-  const int n_pad = n + 2 * pad;
-  float src = ((float)full + 0.5f) * (1.0f / (float)s) - 0.5f;
-  src = fmaxf(src, 0.0f);
-  const int i0 = (int)src;
-  const int i1 = min(i0 + 1, n_pad - 1);
-  *l1 = src - (float)i0;
-  *a0 = min(max(i0 - pad, 0), n - 1);
-  *a1 = min(max(i1 - pad, 0), n - 1);
-}
 
 __global__ void __launch_bounds__(256) tile_flow_upsample_kernel(const float* __restrict__ motion, TileGeom g, float* __restrict__ dense) {
   const int64_t HW = (int64_t)g.H * g.W;
   const int np = g.hp * g.wp;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(p / g.W), j = (int)(p % g.W);
-    int a0, a1, b0, b1;
-    float lr, lc;
-    axis_taps(i + g.h1, g.sh, g.hp, g.pad_h, &a0, &a1, &lr);
-    axis_taps(j + g.w1, g.sw, g.wp, g.pad_w, &b0, &b1, &lc);
+    const TileTaps t = tile_taps(g, i, j);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const float* m = motion + c * np;
-      const float v00 = __ldg(m + a0 * g.wp + b0), v01 = __ldg(m + a0 * g.wp + b1);
-      const float v10 = __ldg(m + a1 * g.wp + b0), v11 = __ldg(m + a1 * g.wp + b1);
-      const float top = (1.0f - lc) * v00 + lc * v01, bot = (1.0f - lc) * v10 + lc * v11;
-      dense[c * HW + p] = -((1.0f - lr) * top + lr * bot);
-    }
+    for (int c = 0; c < 2; ++c) dense[c * HW + p] = tile_value(motion + c * np, g, t);
   }
 }
 
@@ -105,7 +74,7 @@ __global__ void __launch_bounds__(256) tile_flow_upsample_backward_kernel(const 
   }
 }
 
-static int make_geom(const char* fn, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W, TileGeom* out) {
+int make_tile_geom(const char* fn, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W, TileGeom* out) {
   CMAX_REQUIRE(hp >= 1 && wp >= 1 && pad_h >= 0 && pad_w >= 0 && sh >= 1 && sw >= 1 && H >= 1 && W >= 1,
                "%s: bad geometry (grid %dx%d, pad %d,%d, window %dx%d, image %dx%d)", fn, hp, wp, pad_h, pad_w, sh, sw, H, W);
   TileGeom g;
@@ -129,7 +98,7 @@ int cmax_tile_flow_upsample(const float* motion, int hp, int wp, int pad_h, int 
                             cmax_stream_t stream) {
   CMAX_REQUIRE(motion != nullptr && dense != nullptr, "cmax_tile_flow_upsample: NULL pointer");
   TileGeom g;
-  const int rc = make_geom("cmax_tile_flow_upsample", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
+  const int rc = make_tile_geom("cmax_tile_flow_upsample", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
   if (rc) return rc;
   const int64_t HW = (int64_t)H * W;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((HW + 255) / 256, (int64_t)num_sms() * 4));
@@ -142,7 +111,7 @@ int cmax_tile_flow_upsample_backward(const float* grad_dense, int hp, int wp, in
                                      float* grad_motion, cmax_stream_t stream) {
   CMAX_REQUIRE(grad_dense != nullptr && grad_motion != nullptr, "cmax_tile_flow_upsample_backward: NULL pointer");
   TileGeom g;
-  const int rc = make_geom("cmax_tile_flow_upsample_backward", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
+  const int rc = make_tile_geom("cmax_tile_flow_upsample_backward", hp, wp, pad_h, pad_w, sh, sw, H, W, &g);
   if (rc) return rc;
   CMAX_REQUIRE((size_t)(H + W) * sizeof(float) <= 48 * 1024, "cmax_tile_flow_upsample_backward: image larger than %d pixels in H + W", 48 * 1024 / 4);
   dim3 grid(wp, hp, 2);

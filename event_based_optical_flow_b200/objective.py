@@ -174,7 +174,7 @@ class ContrastObjective:
                  exchange: str = "nccl"):
         if cost not in COST_TABLE:
             raise KeyError(f"cost {cost!r} has no fused CUDA form; available: {sorted(COST_TABLE)}")
-        if motion_model not in _lib.MOTION:
+        if motion_model not in _lib.MOTION or motion_model == "tile-flow":  # (the tile-flow model is reached through TileFlowObjective)
             from .warp import MotionModelKeyError
             raise MotionModelKeyError(motion_model)
         if direction not in ("minimize", "maximize", "natural"):
@@ -302,9 +302,10 @@ class ContrastObjective:
             k = len(self.directions)
             self._iwe_view = self._ws[off:off + 4 * k * Hp * Wp].view(torch.float32).view(k, Hp, Wp)
 
-    def _evaluate(self, m: torch.Tensor, cost: torch.Tensor, grad: Optional[torch.Tensor], stream: int) -> None:
-        """One evaluation: writes cost[0] and (if given) grad.  No host sync, CUDA-graph capturable."""
-        model = _lib.MOTION[self.motion_model]
+    def _evaluate(self, m: torch.Tensor, cost: torch.Tensor, grad: Optional[torch.Tensor], stream: int, motion_model: Optional[str] = None) -> None:
+        """One evaluation: writes cost[0] and (if given) grad.  No host sync, CUDA-graph capturable.  `motion_model` overrides
+        the objective's own (TileFlowObjective evaluates a dense-flow objective with the fused "tile-flow" model)."""
+        model = _lib.MOTION[motion_model or self.motion_model]
         orig = self._orig_stat.data_ptr() if self._orig_stat is not None else None
         gptr = grad.data_ptr() if grad is not None else None
         self.plan.set_refs(self.directions, self.n_bins)  # no-op unless another objective re-packed the shared plan
@@ -416,9 +417,15 @@ class TileFlowObjective:
     """cost(patch motion [2,hp,wp]) with the tile-flow -> dense-flow map of the reference in front of a dense-flow
     `ContrastObjective` (what `objective_scipy` evaluates, src/solver/patch_contrast_pyramid.py:430-462: dense =
     interpolate(motion) * t_scale -> calculate_cost).  The gradient comes back on the patch grid (hp*wp*2 numbers), so
-    the host round trip per optimiser step is a few KB."""
+    the host round trip per optimiser step is a few KB.
 
-    def __init__(self, objective: ContrastObjective, patch_size, sliding_window, patch_shift=(0, 0), t_scale: float = 1.0):
+    `fused` (default: whenever the plan has strips): the event kernels evaluate the map at every source pixel themselves
+    (motion model "tile-flow", cmax_plan_set_tile_flow) -- no dense [2,H,W] flow or gradient exists, a CM iteration stays at
+    three launches, and a sharded objective exchanges 2*hp*wp floats instead of a dense gradient.  Otherwise the up-sampling
+    kernel, the dense objective and the adjoint kernel are composed (same numbers: both evaluate the same expression)."""
+
+    def __init__(self, objective: ContrastObjective, patch_size, sliding_window, patch_shift=(0, 0), t_scale: float = 1.0,
+                 fused: Optional[bool] = None):
         from . import ops
         if objective.motion_model != "dense-flow":
             raise ValueError("TileFlowObjective wraps a dense-flow ContrastObjective")
@@ -427,16 +434,44 @@ class TileFlowObjective:
         self.window = (int(sliding_window[0]), int(sliding_window[1]))
         self.pad = ops.tile_flow_geometry(self.image_shape, patch_size, sliding_window, patch_shift)
         self.t_scale = float(t_scale)
+        can_fuse = objective.plan.n_strips > 0 and objective.plan.n > 0
+        if fused and not can_fuse:
+            raise ValueError("the fused tile-flow model needs a plan with strips (a pixel-ordered batch dense enough to be cut into strips)")
+        self.fused = can_fuse if fused is None else bool(fused)
+        self._geom = None
 
-    def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
-        from . import ops
+    def _set_geometry(self, grid) -> None:
+        geom = (int(grid[0]), int(grid[1]), int(self.pad[0]), int(self.pad[1]), self.window[0], self.window[1], self.t_scale)
+        if geom != self._geom:
+            if geom[0] * geom[1] > 1024:
+                raise ValueError(f"the fused tile-flow model supports patch grids of up to 1024 nodes, got {geom[0]}x{geom[1]}")
+            _lib.call("cmax_plan_set_tile_flow", self.objective.plan.handle, *geom)
+            self._geom = geom
+
+    def _check(self, motion: torch.Tensor) -> None:
         _require_cuda(motion, "motion")
         if motion.dim() != 3 or motion.shape[0] != 2:
             raise ValueError(f"tile-flow motion must be [2,hp,wp], got {tuple(motion.shape)}")
+
+    def value_and_grad(self, motion: torch.Tensor, want_grad: bool = True):
+        from . import ops
+        self._check(motion)
+        obj = self.objective
+        if self.fused:
+            m = motion.detach().to(torch.float32).contiguous()
+            with torch.cuda.device(obj.device):
+                cost = torch.empty(1, dtype=torch.float64, device=obj.device)
+                grad = torch.empty_like(m) if want_grad else None
+                self._set_geometry(m.shape[-2:])
+                obj._evaluate(m, cost, grad, _stream_ptr(), motion_model="tile-flow")
+            if obj._post_sign < 0:
+                cost = -cost
+                grad = -grad if grad is not None else None
+            return cost[0], grad
         dense = ops.tile_flow_upsample(motion, self.image_shape, self.pad, self.window)
         if self.t_scale != 1.0:
             dense = dense * self.t_scale
-        cost, gdense = self.objective.value_and_grad(dense, want_grad)
+        cost, gdense = obj.value_and_grad(dense, want_grad)
         if not want_grad:
             return cost, None
         gm = ops.tile_flow_upsample_backward(gdense, motion.shape[-2:], self.pad, self.window)
@@ -448,10 +483,34 @@ class TileFlowObjective:
         return self.value_and_grad(motion, want_grad=False)[0]
 
     def step_into(self, motion_f32: torch.Tensor, cost_out: torch.Tensor, grad_out: torch.Tensor) -> None:
-        """Evaluation into caller buffers (float64[1] cost, fp32 gradient shaped like the motion); CUDA-graph capturable."""
+        """Evaluation into caller buffers (fp32 motion [2,hp,wp], float64[1] cost, fp32 gradient); CUDA-graph capturable.
+        Fused: allocation-free, three launches."""
+        if self.fused and self.objective._post_sign > 0:
+            self._set_geometry(motion_f32.shape[-2:])
+            self.objective._evaluate(motion_f32, cost_out, grad_out, _stream_ptr(), motion_model="tile-flow")
+            return
         cost, gm = self.value_and_grad(motion_f32)
         cost_out.copy_(cost.reshape(1))
         grad_out.copy_(gm)
+
+    # -- second order: the differentiable composition of the modular operators (tile-flow up-sampling is linear)
+    def modular_cost(self, motion: torch.Tensor) -> torch.Tensor:
+        from . import ops
+        dense = ops.TileFlowFunction.apply(motion, tuple(self.image_shape), tuple(self.pad), tuple(self.window))
+        if self.t_scale != 1.0:
+            dense = dense * self.t_scale
+        return self.objective.modular_cost(dense)
+
+    def differentiable_grad(self, motion: torch.Tensor) -> torch.Tensor:
+        with torch.enable_grad():
+            cost = self.modular_cost(motion)
+            (grad,) = torch.autograd.grad(cost, motion, create_graph=True)
+        return grad.to(motion.dtype)
+
+    def __call__(self, motion: torch.Tensor) -> torch.Tensor:
+        """Autograd-aware scalar in motion's dtype (first order: the fused kernels' analytic gradient; under
+        `create_graph=True` the gradient is rebuilt from the twice-differentiable operators, as for ContrastObjective)."""
+        return _ObjectiveFunction.apply(motion, self)
 
 
 class TimeAwareObjective:

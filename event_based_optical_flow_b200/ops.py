@@ -380,19 +380,82 @@ def flow_voxel_backward(dense: torch.Tensor, voxel: torch.Tensor, grad_voxel: to
     return out
 
 
+# ---- second order of the voxel propagation.  First order runs on the hand-written kernels above (forward bit-identical to the
+# reference, exact adjoint).  A Hessian-vector product (Newton-CG / trust-* on the time-aware configurations,
+# configs/mvsec_indoor_burgers.yaml:48 through scipy_autograd/torch_wrapper.py:51-73) differentiates the ADJOINT once more; the
+# propagation is piecewise quadratic, and rather than a third and fourth kernel family that derivative is taken by torch autograd
+# over the same explicit steps written with torch CUDA ops (T - 1 steps of a dozen elementwise kernels on [2,H,W] images -- a
+# few hundred microseconds, paid only inside hessp calls).  Formulas: src/utils/flow_utils.py:439-493 (upwind), :567-639 (Burgers).
+def _shift(a: torch.Tensor, k: int, dim: int) -> torch.Tensor:
+    """a[i + k] along `dim` with the border replicated."""
+    n = a.shape[dim]
+    idx = torch.clamp(torch.arange(n, device=a.device) + k, 0, n - 1)
+    return a.index_select(dim, idx)
+
+
+def _voxel_step_torch(flow: torch.Tensor, dt: float, scheme: str) -> torch.Tensor:
+    if dt == 0:
+        return flow
+    sgn = 1.0 if dt > 0 else -1.0
+    h = abs(dt)
+    f = flow * sgn
+    u, v = f[0], f[1]
+    zero = torch.zeros_like(u)
+    up, um, vp, vm = torch.maximum(u, zero), torch.minimum(u, zero), torch.maximum(v, zero), torch.minimum(v, zero)
+
+    def one_sided(c):  # (row-backward, row-forward, col-backward, col-forward); zero across the image border
+        return c - _shift(c, -1, -2), _shift(c, 1, -2) - c, c - _shift(c, -1, -1), _shift(c, 1, -1) - c
+
+    if scheme == "upwind":
+        out = []
+        for c in (u, v):
+            rb, rf, cb, cf = one_sided(c)
+            out.append(c - h * (((up * rb + um * rf) + vp * cb) + vm * cf))
+        return torch.stack(out) * sgn
+    u_b, u_f, v_b, v_f = _shift(u, -1, -2), _shift(u, 1, -2), _shift(v, -1, -1), _shift(v, 1, -1)
+    bu = ((u * u) * torch.sign(u) + torch.maximum(torch.sign(u_b), zero) * ((-u_b) * u_b) - torch.minimum(torch.sign(u_f), zero) * (u_f * u_f)) / 2.0
+    bv = ((v * v) * torch.sign(v) + torch.maximum(torch.sign(v_b), zero) * ((-v_b) * v_b) - torch.minimum(torch.sign(v_f), zero) * (v_f * v_f)) / 2.0
+    _, _, u_cb, u_cf = one_sided(u)
+    v_rb, v_rf, _, _ = one_sided(v)
+    return torch.stack([u - h * ((vp * u_cb + vm * u_cf) + bu), v - h * ((up * v_rb + um * v_rf) + bv)]) * sgn
+
+
+def flow_voxel_torch(dense: torch.Tensor, time_bin: int, scheme: str, t0_location: str) -> torch.Tensor:
+    """The propagation as a twice-differentiable composition of torch ops (same levels as `flow_voxel`)."""
+    _voxel_args(scheme, t0_location)
+    T = int(time_bin)
+    h = 1.0 / T
+    t0 = 0 if t0_location == "first" else T // 2
+    levels = [None] * T
+    levels[t0] = dense
+    for i in range(t0, 0, -1):
+        levels[i - 1] = _voxel_step_torch(levels[i], -h, scheme)
+    if scheme == "burgers":  # the reference's backward loop also writes level -1 (flow_utils.py:140-141)
+        levels[T - 1] = _voxel_step_torch(levels[0], -h, scheme)
+    for i in range(t0, T - 1):
+        levels[i + 1] = _voxel_step_torch(levels[i], h, scheme)
+    return torch.stack(levels)
+
+
 class FlowVoxelFunction(torch.autograd.Function):
     """Differentiable `flow_voxel` in the caller's dtype."""
 
     @staticmethod
     def forward(ctx, dense, time_bin, scheme, t0_location):
         vox = flow_voxel(dense, time_bin, scheme, t0_location)
-        ctx.save_for_backward(dense.detach(), vox)
+        ctx.save_for_backward(dense, vox)  # (the input itself: a recorded backward differentiates through it)
         ctx.meta = (scheme, t0_location, dense.dtype)
         return vox.to(dense.dtype)
 
     @staticmethod
-    @once_differentiable
     def backward(ctx, g):
         dense, vox = ctx.saved_tensors
         scheme, t0_location, dtype = ctx.meta
+        if torch.is_grad_enabled() and dense.requires_grad:
+            # the backward itself is being recorded (create_graph=True: a Hessian-vector product): J^T g as a differentiable
+            # function of (dense, g), through the torch-op restatement of the propagation
+            with torch.enable_grad():
+                v = flow_voxel_torch(dense, vox.shape[0], scheme, t0_location)
+                (gd,) = torch.autograd.grad(v, dense, g.to(v.dtype), create_graph=True)
+            return gd, None, None, None
         return flow_voxel_backward(dense, vox, g, scheme, t0_location).to(dtype), None, None, None

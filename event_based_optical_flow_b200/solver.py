@@ -114,13 +114,16 @@ class _Batch:
         self.events = events
         self.version = events._version
         self.t_range = None
+        self.t_scale = None
         self.plans: Dict[tuple, EventPlan] = {}
         self.objectives: Dict[tuple, ContrastObjective] = {}
+        self.tile_objectives: dict = {}
 
     def matches(self, events: torch.Tensor) -> bool:
         return self.events is events and self.version == events._version
 
     def close(self) -> None:
+        self.tile_objectives.clear()
         self.objectives.clear()
         for plan in self.plans.values():
             plan.close()
@@ -213,6 +216,67 @@ class B200CostMixin:
         if name == "total_variation":
             return cost.calculate({"flow": coarse_flow, "omit_boundary": True})
         return None
+
+    # -- the pyramid's objective with the tile-flow map INSIDE the event kernels
+    def objective_scipy(self, motion_array, *args, **kw):
+        """Same contract as `PyramidalPatchContrastMaximization.objective_scipy(motion_array, events, coarser_motion,
+        suppress_log)` (src/solver/patch_contrast_pyramid.py:430-462).  For the configuration that method spends its time in --
+        CUDA events, bilinear patch interpolation, not time-aware -- the loss is evaluated from the patch motion directly: the
+        strip kernels compute interpolate(motion) * t_scale per source pixel and return dL/d(patch motion), so no dense flow
+        or dense gradient is ever built.  Anything else goes to the reference's own method."""
+        events = args[0] if len(args) >= 1 else kw.get("events")
+        pyramid_call = len(args) >= 2 and isinstance(args[1], dict) or "coarser_motion" in kw
+        fast = (pyramid_call and isinstance(events, torch.Tensor) and events.is_cuda and isinstance(motion_array, torch.Tensor)
+                and not getattr(self, "is_time_aware", False) and getattr(self, "filter_type", "bilinear") == "bilinear"
+                and self.iwe_config.get("method", "bilinear_vote") == "bilinear_vote"
+                and getattr(self, "motion_model_for_dense_warp", None) == "dense-flow" and int(getattr(self, "motion_vector_size", 2)) == 2)
+        if not fast:
+            return super().objective_scipy(motion_array, *args, **kw)
+        batch = self._b200_batch(events)
+        if getattr(self, "normalize_t_in_batch", False):
+            if batch.t_scale is None:  # events are constant over an optimize(): one host sync per batch instead of one per call
+                batch.t_scale = float(events[:, 2].max() - events[:, 2].min())
+            t_scale = batch.t_scale
+        else:
+            t_scale = 1.0
+        motion = motion_array.reshape((self.motion_vector_size,) + tuple(self.patch_image_size))
+        if motion.device != events.device:
+            motion = motion.to(events.device)
+        geometry = (tuple(self.patch_size), tuple(self.sliding_window), tuple(self.patch_shift), t_scale)
+
+        def term(cost):
+            name = getattr(cost, "name", None)
+            if name in COST_TABLE:
+                obj = self._b200_objective(events, name, cost.direction, "dense-flow", None)
+                key = (name, cost.direction) + geometry
+                tile = batch.tile_objectives.get(key)
+                if tile is None:
+                    from .objective import TileFlowObjective
+                    tile = TileFlowObjective(obj, geometry[0], geometry[1], geometry[2], t_scale)
+                    batch.tile_objectives[key] = tile
+                loss = tile(motion)
+                self._b200_register(cost, loss)
+                return loss
+            if name == "total_variation":
+                return cost.calculate({"flow": motion, "omit_boundary": True})
+            return None
+
+        cost = self.cost_func
+        if getattr(cost, "name", None) == "hybrid":
+            loss = 0.0
+            for entry in cost.cost_func.values():
+                t = term(entry["func"])
+                if t is None:
+                    return super().objective_scipy(motion_array, *args, **kw)
+                loss = loss + (1.0 / t if entry["weight"] == "inv" else entry["weight"] * t)
+            self._b200_register(cost, loss)
+        else:
+            loss = term(cost)
+            if loss is None:
+                return super().objective_scipy(motion_array, *args, **kw)
+        if not (args[2] if len(args) >= 3 else kw.get("suppress_log", False)):
+            logger.info(f"{loss = }")
+        return loss
 
     def interpolate_dense_flow_from_patch_tensor(self, motion_array: torch.Tensor) -> torch.Tensor:
         """Same contract as src/solver/patch_contrast_base.py:462-506, one CUDA kernel (and one for the adjoint) instead

@@ -47,7 +47,10 @@ typedef enum {
 typedef enum {
   CMAX_MOTION_DENSE = 0, /* "dense-flow"        src/warp.py:263-313 */
   CMAX_MOTION_VOXEL = 1, /* "dense-flow-voxel"  src/warp.py:315-365 */
-  CMAX_MOTION_2DOF = 2   /* "2d-translation" / "rigid-optical-flow"  src/warp.py:483-522 */
+  CMAX_MOTION_2DOF = 2,  /* "2d-translation" / "rigid-optical-flow"  src/warp.py:483-522 */
+  CMAX_MOTION_TILE = 3   /* fused path only: the motion is the patch grid [2,hp,wp] the solver optimises; the event kernels
+                            evaluate the tile-flow -> dense-flow map (src/solver/patch_contrast_base.py:462-506, times t_scale)
+                            at every source pixel themselves and return dL/d(patch grid).  See cmax_plan_set_tile_flow. */
 } cmax_motion;
 
 typedef enum {
@@ -200,6 +203,12 @@ int cmax_plan_info(const cmax_plan_t* plan, float* h_tmin, float* h_tmax, int64_
 int cmax_plan_strips(const cmax_plan_t* plan, int64_t* h_n_strips);
 /* Select reference times / voxel bins for subsequent calls (enqueues one tiny kernel). */
 int cmax_plan_set_refs(cmax_plan_t* plan, const cmax_ref* h_refs, int n_ref, int n_bins, cmax_stream_t stream);
+/* CMAX_MOTION_TILE: geometry of the tile-flow map (arguments as in cmax_tile_flow_upsample: patch grid hp x wp <= 1024 nodes,
+ * replicate padding, integer sliding window) and the factor t_scale the reference multiplies the up-sampled flow by
+ * (src/solver/patch_contrast_pyramid.py:452-453).  The dense flow and its gradient are never materialised: no
+ * [2,H,W] round trip through L2, the gradient that leaves the GPU (or crosses NVLink) is 2 * hp * wp floats.  Needs a plan
+ * with strips (cmax_plan_strips > 0); other batches compose cmax_tile_flow_upsample with the dense model. */
+int cmax_plan_set_tile_flow(cmax_plan_t* plan, int hp, int wp, int pad_h, int pad_w, int sh, int sw, float t_scale);
 /* Kernel variants (all give the same results up to fp32 summation order; kept selectable so that profiles/ can show
  * each design choice measured against the others):
  *   vote_variant / grad_variant 5 (default when the plan has strips, else they fall back to 2) = the strip kernels: one
@@ -278,6 +287,10 @@ int cmax_objective_grad(const cmax_plan_t* plan, int motion_model, const float* 
  *         way; cost; gradient quads  -- the all-reduce of the IWE and the cost are ONE launch;
  *   K3 into this rank's partial gradient -> gradient exchange kernel: raise the gradient flag, wait, sum all ranks'
  *         partial gradients into grad_motion (value only: flags only, which keeps the ranks in step).
+ * A flag is a 16-byte record {evaluation counter, row_lo, row_hi, -}: next to "complete" it says which image rows of the
+ * partial result can be non-zero, and a reader skips the peers whose rows miss its pixels.  With spatially compact shards
+ * (distributed.reshard_events_by_pixel: a contiguous slice of the pixel-ordered stream per rank) the exchanges then move the
+ * overlaps only instead of N whole images per rank; with time-sliced shards the ranges are the whole image.
  * Flags are evaluation counters (monotonic), the two flag arrays alternate per evaluation, and that alternation is what
  * makes re-use of the partial buffers safe without any further synchronisation.  Every rank must call with the same
  * arguments in the same order; a rank that never arrives makes the waiting kernels trap after ~4 s. */
@@ -285,7 +298,8 @@ typedef struct {
   int32_t n_peers, rank;
   const float* iwe[CMAX_MAX_PEERS];  /* rank r's partial IWE stack = its workspace + cmax_objective_iwe_offset */
   const float* grad[CMAX_MAX_PEERS]; /* rank r's partial motion gradient (as many floats as the motion) */
-  uint32_t* flags[CMAX_MAX_PEERS];   /* rank r's flag block: 2 * CMAX_MAX_PEERS uint32, zeroed once by the caller */
+  uint32_t* flags[CMAX_MAX_PEERS];   /* rank r's flag block: 256 bytes (2 x CMAX_MAX_PEERS records of 16 bytes), 16-byte aligned,
+                                        zeroed once by the caller */
 } cmax_peers;
 size_t cmax_objective_iwe_offset(const cmax_plan_t* plan);
 size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan); /* where the summed IWE stack of the last evaluation sits */

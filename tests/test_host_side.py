@@ -280,3 +280,47 @@ def test_dual_operator_dispatches_numpy_to_the_reference_object():
     dual.clear_history()
     assert fast.history is ref.history
     assert not _has_cuda_tensor({"a": [np.zeros(2), torch.zeros(2)]})
+
+
+# ------------------------------------------------------------------------------------------------ pixel re-sharding (gloo)
+def _reshard_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from event_based_optical_flow_b200.distributed import pixel_sort_key, reshard_events_by_pixel, shard_events
+        rng = np.random.default_rng(9)
+        H, W, n = 70, 100, 9001
+        ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
+        ev = torch.from_numpy(ev.astype(np.float32))
+        mine = shard_events(ev, world, rank)               # what every rank is handed: a contiguous time slice
+        got = reshard_events_by_pixel(mine, (H, W))
+        keys = pixel_sort_key(got, (H, W))
+        out[rank] = (got.numpy(), int(keys.min()), int(keys.max()))
+        # events of one pixel keep their time order
+        order = torch.sort(keys, stable=True).indices
+        k_sorted, t_sorted = keys[order], got[order, 2]
+        same = k_sorted[1:] == k_sorted[:-1]
+        assert bool((t_sorted[1:][same] >= t_sorted[:-1][same]).all())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reshard_events_by_pixel_gloo_world3():
+    """One all-to-all turns time slices into contiguous slices of the pixel-ordered stream: nothing lost or duplicated, the
+    key ranges of the ranks are disjoint and ordered, the counts are balanced, time order inside a pixel is kept."""
+    world = 3
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_reshard_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        parts = [out[r] for r in range(world)]
+    rng = np.random.default_rng(9)
+    H, W, n = 70, 100, 9001
+    ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1).astype(np.float32)
+    allev = np.concatenate([p[0] for p in parts])
+    assert allev.shape == ev.shape
+    canon = lambda a: a[np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))]  # noqa: E731
+    np.testing.assert_array_equal(canon(allev), canon(ev))
+    for r in range(world - 1):
+        assert parts[r][2] < parts[r + 1][1], "key ranges must be disjoint and in rank order"
+    counts = [len(p[0]) for p in parts]
+    assert max(counts) - min(counts) <= 0.02 * n + 8, counts

@@ -26,7 +26,7 @@ def _worker(rank, world, port, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         import event_based_optical_flow_b200 as B
-        from event_based_optical_flow_b200.distributed import make_sharded_objective, shard_events
+        from event_based_optical_flow_b200.distributed import make_sharded_objective, reshard_events_by_pixel, shard_events
         rng = np.random.default_rng(7)
         H, W, n = 96, 128, 400_001
         ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
@@ -36,20 +36,23 @@ def _worker(rank, world, port, out):
         for cost, sigma in (("image_variance", 0.0), ("multi_focal_normalized_gradient_magnitude", 1.0)):
             full = B.ContrastObjective(ev, (H, W), cost=cost, motion_model="dense-flow", sigma=sigma)
             v_ref, g_ref = full.value_and_grad(flow)
-            for exchange in ("nccl", "peer"):
-                obj = make_sharded_objective(shard_events(ev, world, rank), (H, W), cost=cost, motion_model="dense-flow", sigma=sigma,
-                                             exchange=exchange, orig_events=shard_events(ev, world, rank))
+            for exchange, reshard in (("nccl", False), ("peer", False), ("peer", True)):
+                mine = shard_events(ev, world, rank)
+                if reshard:  # contiguous slices of the pixel-ordered stream: the exchanges skip the rows a peer cannot have touched
+                    mine = reshard_events_by_pixel(mine, (H, W))
+                obj = make_sharded_objective(mine, (H, W), cost=cost, motion_model="dense-flow", sigma=sigma,
+                                             exchange=exchange, orig_events=mine)
                 for _ in range(3):  # repeated evaluations exercise the buffer-reuse hazards of the peer exchange
                     v, g = obj.value_and_grad(flow)
                 v_only = obj.value(flow)
                 torch.cuda.synchronize()
                 rel_v = abs(float(v) - float(v_ref)) / abs(float(v_ref))
                 rel_g = float(torch.linalg.norm(g - g_ref) / torch.linalg.norm(g_ref))
-                results[(cost, exchange)] = (rel_v, rel_g, abs(float(v_only) - float(v)) / abs(float(v)))
+                results[(cost, exchange, reshard)] = (rel_v, rel_g, abs(float(v_only) - float(v)) / abs(float(v)))
                 # every rank must hold the identical result (SPMD optimisers stay in lock-step)
                 both = [torch.zeros_like(g) for _ in range(world)]
                 dist.all_gather(both, g)
-                assert all(torch.equal(both[0], b) for b in both), (cost, exchange)
+                assert all(torch.equal(both[0], b) for b in both), (cost, exchange, reshard)
         out[rank] = results
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,104 @@
+"""The UNMODIFIED reference solver class driven end to end next to the drop-in (missing #4 / next #8):
+`B200Pyramidal(B200CostMixin, PyramidalPatchContrastMaximization)` exactly as INTEGRATION.md section 3 builds it, both shipped
+YAMLs, `objective_scipy` value and gradient at every pyramid scale against the reference's own class on the CPU (fp64 for the
+value, fp32 for the gradient: the objective's gradient is discontinuous where a floor index flips, so only a same-dtype
+reference can be met to 1e-5), plus a Hessian-vector product through torch.autograd.functional.vhp (what Newton-CG asks for).
+
+The reference lives in baseline/_ref (git-ignored; `__graft_entry__.build()` copies it there when /root/reference is mounted, the
+gpurun payload carries it to the GPU box).  Skipped when it is not there."""
+import os
+from unittest import mock
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import reference_loader as RL
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    ref = RL.load()
+    if ref is None:
+        pytest.skip("the reference is neither installed under baseline/_ref nor mounted at /root/reference")
+    return ref
+
+
+def _solvers(R, config_name):
+    from event_based_optical_flow_b200.solver import B200CostMixin
+    cfg = yaml.safe_load(open(os.path.join(R.root, "configs", config_name)))
+    shape = (cfg["data"]["height"], cfg["data"]["width"])
+    base = R.solver.PyramidalPatchContrastMaximization
+
+    class B200Pyramidal(B200CostMixin, base):  # INTEGRATION.md section 3, verbatim
+        pass
+
+    with mock.patch("torch.cuda.is_available", return_value=False):  # the reference side stays on the CPU
+        ref = base(shape, {}, cfg["solver"], cfg["optimizer"], cfg["output"], None)
+    fast = B200Pyramidal(shape, {}, cfg["solver"], cfg["optimizer"], cfg["output"], None)
+    assert fast._device == "cuda" and ref._device == "cpu"
+    return cfg, shape, ref, fast
+
+
+def _events(rng, n, shape):
+    return np.stack([rng.integers(0, shape[0], n), rng.integers(0, shape[1], n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1).astype(np.float64)
+
+
+def _rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+
+
+@pytest.mark.parametrize("config_name", ["mvsec_indoor_no_timeaware.yaml", "mvsec_indoor_burgers.yaml"])
+@pytest.mark.parametrize("n_events", [30_000, 600_000])  # the YAMLs' batch size (no strips: composed kernels) / a dense batch (strips: fused)
+def test_objective_scipy_matches_the_reference_class(R, config_name, n_events):
+    cfg, shape, ref, fast = _solvers(R, config_name)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    ev = _events(rng, n_events, shape)
+    ev_cuda = torch.from_numpy(ev).double().requires_grad_().to(dev)  # what run_scipy_over_scale builds (patch_contrast_pyramid.py:186)
+    ev64, ev32 = torch.from_numpy(ev).double(), torch.from_numpy(ev).float()
+    for scale in range(1, ref.patch_scales):
+        ref.overload_patch_configuration(scale)
+        fast.overload_patch_configuration(scale)
+        m = rng.uniform(-15, 15, 2 * ref.n_patch)
+        m64 = torch.from_numpy(m).double().requires_grad_(True)
+        m32 = torch.from_numpy(m).float().requires_grad_(True)
+        loss64 = ref.objective_scipy(m64, ev64, {}, True)
+        loss32 = ref.objective_scipy(m32, ev32, {}, True)
+        (g64,) = torch.autograd.grad(loss64, m64)
+        (g32,) = torch.autograd.grad(loss32, m32)
+        mf = torch.from_numpy(m).double().to(dev).requires_grad_(True)
+        loss = fast.objective_scipy(mf, ev_cuda, {}, True)
+        (g,) = torch.autograd.grad(loss, mf)
+        rel_v, rel_g = abs(float(loss) - float(loss64)) / abs(float(loss64)), _rel(g, g32)
+        print(f"{config_name} n={n_events} scale {scale} {tuple(ref.patch_image_size)}: loss rel vs fp64 reference {rel_v:.2e}, "
+              f"grad rel vs fp32 reference {rel_g:.2e} (fp32 reference vs fp64 reference {_rel(g32, g64):.2e})")
+        assert loss.dtype == torch.float64 and g.shape == mf.shape
+        assert rel_v <= 1e-5, (scale, rel_v)
+        assert rel_g <= max(1e-5, 0.05 * _rel(g32, g64)), (scale, rel_g, _rel(g32, g64))
+    if n_events >= 600_000 and not fast.is_time_aware:
+        (batch,) = fast._b200_cache().values()
+        assert batch.tile_objectives and all(t.fused for t in batch.tile_objectives.values()), "a dense batch must run the fused tile-flow kernels"
+
+
+def test_newton_cg_hessian_vector_product_through_the_real_seam(R):
+    """scipy_autograd's Newton-CG path: torch.autograd.functional.vhp over objective_scipy (torch_wrapper.py:51-73)."""
+    for config_name in ("mvsec_indoor_no_timeaware.yaml", "mvsec_indoor_burgers.yaml"):
+        cfg, shape, ref, fast = _solvers(R, config_name)
+        dev = torch.device("cuda:0")
+        rng = np.random.default_rng(1)
+        ev = _events(rng, 30_000, shape)
+        ev_cuda, ev64 = torch.from_numpy(ev).double().to(dev), torch.from_numpy(ev).double()
+        ref.overload_patch_configuration(2)
+        fast.overload_patch_configuration(2)
+        m = rng.uniform(-10, 10, 2 * ref.n_patch)
+        v = rng.standard_normal(2 * ref.n_patch)
+        _, hv = torch.autograd.functional.vhp(lambda x: fast.objective_scipy(x, ev_cuda, {}, True), torch.from_numpy(m).to(dev), torch.from_numpy(v).to(dev))
+        _, hv_ref = torch.autograd.functional.vhp(lambda x: ref.objective_scipy(x, ev64, {}, True), torch.from_numpy(m), torch.from_numpy(v))
+        rel = _rel(hv, hv_ref)
+        print(f"{config_name}: H v rel vs the fp64 reference {rel:.2e}")
+        assert rel <= 5e-3, (config_name, rel)  # fp32 kernels against an fp64 Hessian of a piecewise-smooth cost (tests/test_hvp.py)

@@ -268,3 +268,60 @@ def test_mixin_supports_hessian_vector_products():
     # the second-order path composes the modular fp32 kernels; its bound is the fp32 reference's own distance from fp64
     # (measured: 1.4e-5 here against 1e-5 .. 1e-4 for the fp32 oracle), never looser than 5e-5
     assert rel <= max(1e-5, min(5e-5, 3 * rel32)), (rel, rel32)
+
+
+def test_mixin_objective_scipy_runs_the_fused_tile_flow():
+    """`B200CostMixin.objective_scipy` (pyramid signature) evaluates the loss from the patch motion inside the event kernels;
+    against the reference's own composition (interpolate -> * t_scale -> calculate_cost, restated below from
+    src/solver/patch_contrast_pyramid.py:430-462) running on the CPU oracle."""
+    import event_based_optical_flow_b200 as B
+    from event_based_optical_flow_b200.solver import B200CostMixin
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    H, W, n = 64, 96, 200_000
+    ev = np.stack([rng.integers(0, H, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1)
+    ev = torch.from_numpy(ev).double()
+    grid, window = (4, 6), (16, 16)
+
+    class PyramidLike(_ReferenceSeam):
+        is_time_aware = False
+        filter_type = "bilinear"
+        motion_model_for_dense_warp = "dense-flow"
+        motion_vector_size = 2
+        normalize_t_in_batch = True
+        patch_image_size = grid
+        patch_size = window
+        sliding_window = window
+        patch_shift = (0, 0)
+        current_scale = 1
+
+        def objective_scipy(self, motion_array, events, coarser_motion, suppress_log=False):
+            raise AssertionError("the fused path must not fall through to the reference composition here")
+
+    class Fast(B200CostMixin, PyramidLike):
+        pass
+
+    for cost_name, cw in (("image_variance", None), ("hybrid", {"multi_focal_normalized_gradient_magnitude": 1.0, "total_variation": 0.01})):
+        slv = Fast(B, (H, W), cost_name, 1 if cost_name == "hybrid" else 0, cost_with_weight=cw)
+        motion = torch.from_numpy(rng.uniform(-5, 5, (2,) + grid)).to(dev).requires_grad_(True)
+        evd = ev.to(dev)
+        loss = slv.objective_scipy(motion.reshape(-1), evd, {}, True)
+        (g,) = torch.autograd.grad(loss, motion)
+        assert loss.dtype == torch.float64
+        (batch,) = slv._b200_cache().values()
+        assert all(t.fused for t in batch.tile_objectives.values()) and len(batch.tile_objectives) == 1
+        # the reference's composition on the oracle, fp32 like the kernels
+        t_scale = float(ev[:, 2].max() - ev[:, 2].min())
+        m = motion.detach().cpu().float().requires_grad_(True)
+        dense = O.upsample_tile_flow(m, (H, W), window, window, (0, 0)) * t_scale
+        sigma = 1.0 if cost_name == "hybrid" else 0.0
+        if cost_name == "hybrid":
+            from event_based_optical_flow_b200.costs import functions
+            ref = O.objective(ev.float(), dense, (H, W), motion_model="dense-flow", cost="multi_focal_normalized_gradient_magnitude", sigma=sigma) \
+                + 0.01 * functions["total_variation"]().calculate({"flow": m, "omit_boundary": True})
+        else:
+            ref = O.objective(ev.float(), dense, (H, W), motion_model="dense-flow", cost=cost_name, sigma=sigma)
+        (g_ref,) = torch.autograd.grad(ref, m)
+        assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref)), (cost_name, float(loss), float(ref))
+        rel = float(torch.linalg.norm(g.cpu().double() - g_ref.double()) / torch.linalg.norm(g_ref.double()))
+        assert rel <= 1e-5, (cost_name, rel)
