@@ -93,7 +93,7 @@ def synth_motions(cfg, k: int, seed: int) -> np.ndarray:
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the event kernels, from the committed `ncu --set full`
 # captures under profiles/ (config 2 only; other configurations report traffic null)
-TRAFFIC_SOURCE = "profiles/r02_ncu_r2a.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch"
+TRAFFIC_SOURCE = "profiles/r02_ncu_r2k.txt: dram__bytes_read.sum + dram__bytes_write.sum per launch"
 _TRAFFIC = {"K1 vote (vote_strips_kernel)": 26.09e6, "K3 grad (grad_strips_kernel)": 26.81e6}
 
 

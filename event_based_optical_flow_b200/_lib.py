@@ -82,6 +82,7 @@ _SIGNATURES = {
     "cmax_objective": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, _p, _p, _p]),
     "cmax_objective_iwe_offset": (_sz, [_p]),
     "cmax_objective_full_iwe_offset": (_sz, [_p]),
+    "cmax_objective_probe_offset": (_sz, [_p]),
     "cmax_objective_sharded": (_i, [_p, _i, _p, C.POINTER(CostSpec), _p, _p, C.POINTER(Peers), _p, _p, _p]),
     "cmax_combine_cost": (_i, [_p, _i, _i, _i, _p, C.POINTER(_f), _i, _i, _p, _p, _p]),
 }

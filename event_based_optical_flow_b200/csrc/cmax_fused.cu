@@ -769,6 +769,9 @@ FusedArgs fused_args(const cmax_plan* p, const float* motion) {
   a.zero256 = nullptr;
   a.tile = p->tile;
   a.t_scale = p->t_scale;
+  // strips per pixel of the rows this batch covers: beyond ~16 the same-address reductions of K3 start to serialise
+  const int64_t rows = std::max(1, p->src_row_hi - p->src_row_lo + 1);
+  a.seg_reduce = (p->strips != nullptr && p->n_strips >= 16 * rows * (int64_t)p->W) ? 1 : 0;
   return a;
 }
 

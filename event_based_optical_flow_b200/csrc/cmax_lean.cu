@@ -346,7 +346,27 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
     if (MODEL == CMAX_MOTION_DENSE) {  // one flush per strip: the strip IS one source pixel
       float g0, g1;
       upk2(st.g[0], g0, g1);
-      if (h.count > 0) {
+      if (a.seg_reduce) {
+        // Dense batches (tens of strips per pixel, e.g. a spatially compact shard of a multi-GPU run): the lanes of a warp
+        // hold consecutive strips of the SAME source pixel, and 32 reductions onto one address serialise in the L2 (measured:
+        // K3 11 -> 19 us at 440 events per pixel).  Segmented suffix sum over the runs of equal pixel inside the warp, one
+        // pair of reductions per run.  (warp-uniform branch; sparse batches skip the ~30 shuffle instructions)
+        const int key = h.count > 0 ? h.src : -1 - lane;  // padding strips never merge
+        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float u0 = __shfl_down_sync(0xffffffffu, g0, o), u1 = __shfl_down_sync(0xffffffffu, g1, o);
+          const int uk = __shfl_down_sync(0xffffffffu, key, o);
+          if (lane + o < 32 && uk == key) {
+            g0 += u0;
+            g1 += u1;
+          }
+        }
+        if (h.count > 0 && (lane == 0 || prev != key)) {
+          atomicAdd(gmotion + h.src, g0);
+          atomicAdd(gmotion + HW + h.src, g1);
+        }
+      } else if (h.count > 0) {
         atomicAdd(gmotion + h.src, g0);
         atomicAdd(gmotion + HW + h.src, g1);
       }

@@ -257,8 +257,6 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
 
   // ---- phase 2 (sharded): signal, wait, sum the partial images of all ranks in rank order (bit-identical on every rank)
   if (SHARDED) {
-    __shared__ bool last;
-    __shared__ int sh_rows[2];
     nz_hi1 = __reduce_max_sync(0xffffffffu, nz_hi1);
     nz_ilo = __reduce_max_sync(0xffffffffu, nz_ilo);
     if (lane == 0 && nz_hi1 > 0) {
@@ -267,24 +265,22 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      // The shortest chain from "the slowest CTA has folded" to "the records are on their way": every CTA's writes are
+      // performed at this GPU's L2 (fence) before it counts itself in, so when the count completes nothing is left to wait
+      // for -- the thread that completes it reads the row range and posts the records itself, no further fence or barrier.
       __threadfence();
-      last = (atomicAdd(&a.bar[0], 1u) == gridDim.x - 1);
-      if (last) {
-        *a.px.epoch = epoch;  // (every CTA has read the old value by now)
-        __threadfence();
+      if (atomicAdd(&a.bar[0], 1u) == gridDim.x - 1) {
         const int hi1 = (int)ld_relaxed_gpu(&a.bar[2]), ilo = (int)ld_relaxed_gpu(&a.bar[3]);
-        sh_rows[0] = hi1 > 0 ? (int)Hp - ilo : (int)Hp;  // empty: lo > hi
-        sh_rows[1] = hi1 - 1;
+        *a.px.epoch = epoch;  // (every CTA has read the old value by now)
+        const uint4 rec = make_uint4(epoch, (uint32_t)(hi1 > 0 ? (int)Hp - ilo : (int)Hp), (uint32_t)(hi1 - 1), 0u);  // empty: lo > hi
+        for (int q = 0; q < a.px.n; ++q) st_relaxed_sys_v4(a.px.rec_at[q], rec);
       }
     }
-    __syncthreads();
-    if (last && wid == 0) raise_flags(a.px, epoch, sh_rows[0], sh_rows[1]);  // every CTA of this rank has folded: publish
     wait_flags(a.px.recs, epoch, a.px.n, sh_lo, sh_hi);
     STAMP(7);
     for (int img = 0; img < a.n_ref; ++img) {
       double s = 0.0, q = 0.0;
-      auto account = [&](unsigned p, float v) {
-        const unsigned r = p / Wp, c = p - r * Wp;
+      auto account = [&](unsigned r, unsigned c, float v) {
         if (a.stats && in_crop(r, c)) {
           s += (double)v;
           q += (double)v * (double)v;
@@ -293,7 +289,8 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
       if ((HW & 3u) == 0) {
         // 16-byte peer loads, all ranks' loads of a thread in flight together: one NVLink round trip per thread
         for (unsigned p4 = tid; p4 < (HW >> 2); p4 += nthr) {
-          const int row_a = (int)((4u * p4) / Wp), row_b = (int)((4u * p4 + 3u) / Wp);  // rows this group of 4 pixels touches
+          const unsigned r0 = (4u * p4) / Wp, c0 = 4u * p4 - r0 * Wp;  // (one division per group of 4 pixels)
+          const int row_a = (int)r0, row_b = (int)(c0 + 3u >= Wp ? r0 + 1u : r0);  // rows this group touches
           float4 part[CMAX_MAX_PEERS];
 #pragma unroll
           for (int r = 0; r < CMAX_MAX_PEERS; ++r) {
@@ -308,16 +305,21 @@ __global__ void __launch_bounds__(kMidThreads, 1) image_kernel(ImageArgs a) {
               v.x += part[r].x; v.y += part[r].y; v.z += part[r].z; v.w += part[r].w;
             }
           reinterpret_cast<float4*>(a.iwe_full + (size_t)img * HW)[p4] = v;
-          account(4u * p4, v.x); account(4u * p4 + 1u, v.y); account(4u * p4 + 2u, v.z); account(4u * p4 + 3u, v.w);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (unsigned k = 0; k < 4u; ++k) {
+            const bool wrap = c0 + k >= Wp;
+            account(wrap ? r0 + 1u : r0, wrap ? c0 + k - Wp : c0 + k, vv[k]);
+          }
         }
       } else {
         for (unsigned p = tid; p < HW; p += nthr) {
-          const int row = (int)(p / Wp);
+          const unsigned r0 = p / Wp, c0 = p - r0 * Wp;
           float v = 0.f;
           for (int r = 0; r < a.px.n; ++r)
-            if (row >= sh_lo[r] && row <= sh_hi[r]) v += __ldcg(a.px.part[r] + (size_t)img * HW + p);
+            if ((int)r0 >= sh_lo[r] && (int)r0 <= sh_hi[r]) v += __ldcg(a.px.part[r] + (size_t)img * HW + p);
           a.iwe_full[(size_t)img * HW + p] = v;
-          account(p, v);
+          account(r0, c0, v);
         }
       }
       if (a.stats) commit(img, s, q);
@@ -427,16 +429,17 @@ __global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n
   if (blockIdx.x == 0 && threadIdx.x < 32) raise_flags(px, epoch, row_lo, row_hi);
   wait_flags(px.recs, epoch, px.n, sh_lo, sh_hi);
   STAMP(1);
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
-  const unsigned uplane = (unsigned)plane, uW = (unsigned)W;
-  if ((n & 3) == 0) {
-    for (int64_t i = tid; i < (n >> 2); i += nthr) {
+  // 32-bit index arithmetic (a 64-bit division is a ~150-instruction dependent chain, and every thread has one group to do)
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  const unsigned un = (unsigned)n, uplane = (unsigned)plane, uW = (unsigned)W;
+  if ((un & 3u) == 0) {
+    for (unsigned i = tid; i < (un >> 2); i += nthr) {
       int row_a = 0, row_b = 0;
       if (plane > 0) {
-        const unsigned e0 = (unsigned)((4 * i) % uplane), e1 = (unsigned)((4 * i + 3) % uplane);
+        const unsigned e0 = (4u * i) % uplane;
         row_a = (int)(e0 / uW);
-        row_b = (int)(e1 / uW);
-        if (e1 < e0) {  // the group straddles two planes: take every row
+        row_b = (int)((e0 + 3u) / uW);
+        if (e0 + 3u >= uplane) {  // the group straddles two planes: take every row
           row_a = 0;
           row_b = 0x7fffffff;
         }
@@ -456,8 +459,8 @@ __global__ void __launch_bounds__(256) grad_exchange_kernel(PeerEx px, int64_t n
       reinterpret_cast<float4*>(out)[i] = v;
     }
   } else {
-    for (int64_t i = tid; i < n; i += nthr) {
-      const int row = plane > 0 ? (int)((unsigned)(i % uplane) / uW) : 0;
+    for (unsigned i = tid; i < un; i += nthr) {
+      const int row = plane > 0 ? (int)((i % uplane) / uW) : 0;
       float v = 0.f;
       for (int r = 0; r < px.n; ++r)
         if (plane == 0 || (row >= sh_lo[r] && row <= sh_hi[r])) v += __ldcg(px.part[r] + i);
@@ -787,6 +790,7 @@ int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const floa
   if (rc) return rc;
   rc = check_peers("cmax_objective_sharded", peers);
   if (rc) return rc;
+  CMAX_REQUIRE(motion_floats(plan, motion_model) < ((size_t)1 << 31), "cmax_objective_sharded: the motion has too many elements for the 32-bit exchange index");
   CMAX_REQUIRE(spec->form == CMAX_COST_PLAIN || d_orig_stat != nullptr, "cmax_objective_sharded: normalised costs need d_orig_stat");
   CMAX_REQUIRE(plan->Hp >= 3 && plan->Wp >= 3, "cmax_objective_sharded: images must be at least 3x3");
   CMAX_REQUIRE(plan->vote_variant != 1, "cmax_objective_sharded: vote variant 1 has no per-corner accumulators to fold");
@@ -835,6 +839,14 @@ int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const floa
                                             reinterpret_cast<unsigned long long*>(w.slots) + 2048 + 148 * 8);
   CMAX_CUDA_CHECK(cudaGetLastError());
   return CMAX_OK;
+}
+
+size_t cmax_objective_probe_offset(const cmax_plan_t* plan) {
+  if (plan == nullptr) {
+    set_error("cmax_objective_probe_offset: plan is NULL");
+    return 0;
+  }
+  return obj_layout(plan->Hp, plan->Wp).off_slots + 2048 * sizeof(double);
 }
 
 size_t cmax_objective_iwe_offset(const cmax_plan_t* plan) {

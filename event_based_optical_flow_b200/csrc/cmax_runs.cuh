@@ -23,6 +23,7 @@ struct FusedArgs {
   const cmax_time_params_t* tp;
   int64_t cells;  // (Hp+1)*(Wp+1)
   unsigned int* zero256;  // 64 words K1's first CTA clears (statistics block + grid-barrier counters), or NULL
+  int seg_reduce;         // strip K3: sum the flow gradient over the strips of one pixel inside a warp before the reductions (dense batches)
   TileGeom tile;          // CMAX_MOTION_TILE: `motion` is the patch grid [2,hp,wp], evaluated per source pixel by the kernels
   float t_scale;
 };

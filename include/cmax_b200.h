@@ -302,6 +302,9 @@ typedef struct {
                                         zeroed once by the caller */
 } cmax_peers;
 size_t cmax_objective_iwe_offset(const cmax_plan_t* plan);
+/* Measurement builds (-DCMAX_MEASURE) only: where in the workspace the image / exchange kernels leave their per-CTA
+ * globaltimer stamps (scripts/image_probe.py, scripts/exchange_probe.py); the release library writes nothing there. */
+size_t cmax_objective_probe_offset(const cmax_plan_t* plan);
 size_t cmax_objective_full_iwe_offset(const cmax_plan_t* plan); /* where the summed IWE stack of the last evaluation sits */
 int cmax_objective_sharded(const cmax_plan_t* plan, int motion_model, const float* motion, const cmax_cost_spec* spec,
                            const double* d_orig_stat, void* workspace, const cmax_peers* peers, double* d_cost,

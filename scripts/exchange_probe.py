@@ -15,6 +15,9 @@ dist.init_process_group("nccl", device_id=dev)
 n = int(os.environ.get("PROBE_N", 5_000_000))
 ev_np = bench.synth_events(n, rank); ev_np[:, 2] += 0.05 * rank
 ev = torch.from_numpy(ev_np).to(dev)
+if os.environ.get("PROBE_SHARD", "time") == "pixel":
+    from event_based_optical_flow_b200.distributed import reshard_events_by_pixel
+    ev = reshard_events_by_pixel(ev, (bench.H, bench.W), dist.group.WORLD)
 flows = torch.from_numpy(bench.synth_flows(4, 100)).to(dev)
 obj = ContrastObjective(ev, (bench.H, bench.W), cost="image_variance", process_group=dist.group.WORLD, t_range=global_time_range(ev, dist.group.WORLD), exchange="peer")
 cost = torch.zeros(1, dtype=torch.float64, device=dev); grad = torch.zeros(2, bench.H, bench.W, device=dev); fb = flows[0].clone()
@@ -25,23 +28,25 @@ with torch.cuda.stream(s):
 torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize(); dist.barrier()
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g): obj.step_into(fb, cost, grad)
-def layout(Hp, Wp, R=4):
-    al = lambda v: (v + 255) // 256 * 256
-    cells, HW = (Hp + 1) * (Wp + 1) + 1, Hp * Wp
-    off = 0
-    for sz in (R * cells * 16, R * HW * 4, R * HW * 4, R * HW * 4, R * 32, R * 8, 16, R * 24, R * 2 * HW * 4, R * HW * 4, R * HW * 4, R * cells * 16):
-        off = al(off + sz)
-    return off
-OFF = layout(bench.H, bench.W) + 2048 * 8
+OFF = int(_L.load().cmax_objective_probe_offset(obj.plan.handle))
 ws = obj._ws; base = obj._ws_ptr - ws.data_ptr()
 out = []
 for it in range(8):
     fb.copy_(flows[it % 4]); flush.zero_(); flush_rd.sum(); torch.cuda.synchronize(); dist.barrier()
+    flush.zero_(); flush_rd.sum(); obj._symm.barrier(channel=0)  # as bench.py: flush, then align the ranks in-stream
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); g.replay(); b.record(); torch.cuda.synchronize()
     st = ws[base + OFF: base + OFF + (148 + 64) * 64].view(torch.int64).cpu().numpy().reshape(148 + 64, 8).astype(np.float64)
     out.append((a.elapsed_time(b) * 1e3, st))
+gathered = [None] * world
+dist.all_gather_object(gathered, [(ms, st.tolist()) for ms, st in out[3:]])
 if rank == 0:
+    for r in range(world):  # per-rank summary of the last step: K1 end (pdl), flags seen, image end, exchange start/flags/end
+        ms, st = gathered[r][-1]
+        st = np.array(st); img, ex = st[:148], st[148:]; ex = ex[ex[:, 0] > 0]; t0 = img[:, 0].min()
+        f = lambda a: (np.median(a) - t0) / 1e3
+        print(f"rank {r}: step {ms:.1f} us | pdl {f(img[:,1]):.1f} fold {f(img[:,3]):.1f} flags {f(img[:,7]):.1f} barrier {f(img[:,4]):.1f} end {f(img[:,6]):.1f} | "
+              f"xchg start {f(ex[:,0]):.1f} flags {f(ex[:,1]):.1f} end {f(ex[:,2]):.1f}")
     names = ["start", "after pdl_wait (K1 done)", "after fold loop", "after fold (cta)", "after grid barrier", "after slot-reduce+combine", "end", "after wait_flags (peers' IWEs ready)"]
     order = [0, 1, 2, 3, 7, 4, 5, 6]
     for ms, st in out[3:]:

@@ -412,3 +412,25 @@ def test_strip_kernels_every_model_vs_oracle_and_run_kernels(B, dev, model, cost
     assert iwe.shape[0] == len(obj.ref_keys)
     for r, key in enumerate(obj.ref_keys):
         torch.testing.assert_close(iwe[r], images[key], rtol=1e-5, atol=2e-4)
+
+
+def test_very_dense_batch_runs_the_segmented_gradient_reduction(B, dev):
+    """>= 16 strips per source pixel (what a spatially compact shard of a multi-GPU run looks like): the strip K3 sums the flow
+    gradient over the strips of one pixel inside the warp before its reductions.  Same numbers as the oracle and as the run
+    kernels; a batch that covers only a band of the image (rows 8..23) exercises the row bookkeeping of the plan too."""
+    rng = np.random.default_rng(23)
+    H, W, n = 32, 40, 160_000
+    ev = np.stack([rng.integers(8, 24, n), rng.integers(0, W, n), np.sort(rng.uniform(0, 0.05, n)), rng.integers(0, 2, n)], 1).astype(np.float32)
+    ev = torch.from_numpy(ev)
+    flow = torch.from_numpy(rng.uniform(-5, 5, (2, H, W)).astype(np.float32))
+    obj = B.ContrastObjective(ev.to(dev), (H, W), cost="image_variance", motion_model="dense-flow")
+    assert obj.plan.n_strips >= 16 * 16 * W  # 250 events per pixel of the band -> the segmented path is on
+    v5, g5 = obj.value_and_grad(flow.to(dev))
+    obj.plan.set_variant(2, 2)
+    v2, g2 = obj.value_and_grad(flow.to(dev))
+    ref_v, ref_g = O.objective_value_and_grad(ev, flow, (H, W), motion_model="dense-flow", cost="image_variance")
+    ref_v64, _ = O.objective_value_and_grad(ev.double(), flow.double(), (H, W), motion_model="dense-flow", cost="image_variance")
+    assert _cost_close(v5, ref_v, ref_v64)
+    assert _rel(g5.cpu().numpy(), ref_g.numpy()) <= RTOL, _rel(g5.cpu().numpy(), ref_g.numpy())
+    assert _rel(g5.cpu().numpy(), g2.cpu().numpy()) <= RTOL
+    assert float(g5[:, :8].abs().max()) == 0.0 and float(g5[:, 24:].abs().max()) == 0.0  # no source pixels outside the band
