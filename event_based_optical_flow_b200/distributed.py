@@ -76,7 +76,7 @@ def reshard_events_by_pixel(events_shard: torch.Tensor, image_size, group=None) 
     targets = torch.tensor([(q * total) // world for q in range(1, world)], dtype=cum.dtype, device=cum.device)
     bounds = torch.searchsorted(cum, targets, right=False)  # first key index of rank q+1 = bounds[q] + 1
     dest = torch.searchsorted(bounds, key, right=False)      # key <= bounds[q] -> rank <= q
-    order = torch.sort(dest, stable=True).indices
+    order = torch.sort(dest.to(torch.uint8), stable=True).indices  # (8-bit keys: one radix pass instead of eight)
     send = events_shard.detach()[order].contiguous()
     send_counts = torch.bincount(dest, minlength=world)
     recv_counts = torch.empty_like(send_counts)
