@@ -450,6 +450,53 @@ def run_b200(args) -> None:
     h2d = int(host_motions[0].numel() * 4)
     d2h = int(out_host.numel() * 4)
 
+    # ---- the same batch driven by the patch grid the pyramid optimises (16x16 nodes, the shipped YAML's geometry): the tile-flow
+    # model evaluates the dense flow inside the event kernels, so the per-step host traffic is 2 KB each way instead of 720 KB
+    tile_leg = None
+    if world == 1 and args.config == "c2" and obj.plan.n_strips > 0:
+        from event_based_optical_flow_b200 import TileFlowObjective
+        tm_np = np.random.default_rng(7).uniform(-MAX_FLOW, MAX_FLOW, (N_FLOWS, 2, 16, 16)).astype(np.float32)
+        tm_host = [torch.from_numpy(tm_np[i]).pin_memory() for i in range(N_FLOWS)]
+        tm_dev = torch.zeros(2, 16, 16, dtype=torch.float32, device=dev)
+        t_out = torch.zeros(514, dtype=torch.float32, device=dev)
+        t_out_host = torch.empty(514, dtype=torch.float32).pin_memory()
+        t_grad, t_cost = t_out[:512].view(2, 16, 16), t_out[512:].view(torch.float64)
+        tile_leg = {"what": "same batch, motion = 16x16 patch grid (the shipped YAML's geometry); 'fused' = the tile-flow model (the event kernels "
+                            "evaluate interpolate(motion) themselves, no dense flow / gradient), 'composed' = up-sampling kernel + dense model + adjoint kernel"}
+        for tag, fused in (("fused", True), ("composed", False)):
+            tile = TileFlowObjective(obj, patch_size=(16, 21), sliding_window=(16, 21), patch_shift=(2, 5), t_scale=1.0, fused=fused)
+            for _ in range(3):
+                tile.step_into(tm_dev, t_cost, t_grad)
+            tg = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(tg):
+                tile.step_into(tm_dev, t_cost, t_grad)
+            dev_ms = []
+            for k in range(args.warmup + args.steps):
+                tm_dev.copy_(tm_host[k % N_FLOWS])
+                flush_l2()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                tg.replay()
+                b.record()
+                torch.cuda.synchronize()
+                if k >= args.warmup:
+                    dev_ms.append(a.elapsed_time(b))
+            wall = 0.0
+            for k in range(args.warmup + args.steps):
+                flush_l2()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                tm_dev.copy_(tm_host[k % N_FLOWS], non_blocking=True)
+                tg.replay()  # (the public step_into, captured: what a solver with a per-shape graph cache replays)
+                t_out_host.copy_(t_out, non_blocking=True)
+                torch.cuda.synchronize()
+                if k >= args.warmup:
+                    wall += time.perf_counter() - t0
+            tile_leg[tag] = {"ms_per_step": float(np.mean(dev_ms)), "value": n / (float(np.mean(dev_ms)) * 1e-3),
+                             "e2e": {"value": n * args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": 2048, "d2h_bytes_per_step": 2056}}
+            tg.reset()
+
     # ---- sharded vs single GPU: rank 0 gathers every shard, evaluates the whole batch on its own GPU and compares
     sharded_check = None
     if world > 1:
@@ -646,7 +693,7 @@ def run_b200(args) -> None:
                     "what": "host pinned motion -> device, step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
             "gpu_launches": per_step_kernels * args.steps if per_step_kernels else None,
             "plan_ms": plan_ms, "reshard_ms": reshard_ms, "events_this_rank": n_local, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
-            "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
+            "tile_flow": tile_leg, "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
         }
     if line is not None:
         print(json.dumps(line), flush=True)

@@ -289,8 +289,11 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
   constexpr uint32_t kTile = StripTileBytes<MODEL, NREF>::value;
   __shared__ TilePipe<kTile> pipes[kRunWarps];
   __shared__ double red2[2][kRunWarps];
-  // tile flow: dL/d(patch grid) of this CTA, accumulated in shared memory (the adjoint of the up-sampling: every source pixel
-  // hands its flow gradient to its <= 4 grid nodes) and added to the global gradient once per CTA
+  // tile flow: dL/d(patch grid) of this CTA (the adjoint of the up-sampling: every source pixel hands its flow gradient to
+  // its <= 4 grid nodes).  A CTA of this instantiation walks a CONTIGUOUS range of warp-tiles, i.e. a few neighbouring pixels'
+  // worth of strips, so it touches a handful of nodes: they are summed here and only the non-zero ones go to global memory.
+  // (The same reductions issued per pixel, or per CTA over strided tiles, serialise in the L2 at ~100 ns per same-address
+  // operation: 757 k of them onto 512 addresses made a 200 us kernel -- measured.)
   __shared__ float sgrad[MODEL == CMAX_MOTION_TILE ? 2 * kTileMaxNodes : 1];
   const RefRegs<NREF> rr = load_refs<NREF>(a.tp);
   const int HW = a.H * a.W;
@@ -304,8 +307,16 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
   }
   TilePipe<kTile>& pipe = pipes[threadIdx.x >> 5];
   pipe_init(pipe, lane);
-  const int64_t n_tiles = (a.n_strips + 31) / 32;
-  const int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  // warps stride over all tiles (dense / voxel / 2-dof), or over this CTA's contiguous range of tiles (tile flow)
+  int64_t n_tiles = (a.n_strips + 31) / 32;
+  int64_t warp0 = (int64_t)blockIdx.x * kRunWarps + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * kRunWarps;
+  if (MODEL == CMAX_MOTION_TILE) {
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t begin = (int64_t)blockIdx.x * per_cta;
+    n_tiles = min(n_tiles, begin + per_cta);
+    warp0 = begin + (threadIdx.x >> 5);
+    n_warps = kRunWarps;
+  }
   if (warp0 < n_tiles) pipe_issue(pipe, 0, a.strips, warp0, lane);  // the strips do not depend on the predecessor
   f32x2 f = 0ull;
   if (MODEL == CMAX_MOTION_2DOF) f = pk2(__ldg(a.motion), __ldg(a.motion + 1));
@@ -371,23 +382,65 @@ __global__ void __launch_bounds__(kRunThreads) grad_strips_kernel(FusedArgs a, c
         atomicAdd(gmotion + HW + h.src, g1);
       }
     } else if (MODEL == CMAX_MOTION_TILE) {
-      // dense[c] = -t_scale * sum_ab Wr[a] Wc[b] m[c,a,b]  =>  dL/dm[c,a,b] += -t_scale * Wr[a] Wc[b] * dL/ddense[c]
-      if (h.count > 0) {
-        float g0, g1;
-        upk2(st.g[0], g0, g1);
-        g0 *= -a.t_scale;
-        g1 *= -a.t_scale;
-        const float wr[2] = {1.0f - taps.lr, taps.lr}, wc[2] = {1.0f - taps.lc, taps.lc};
-        const int an[2] = {taps.a0, taps.a1}, bn[2] = {taps.b0, taps.b1};
+      // dense[c] = -t_scale * sum_ab Wr[a] Wc[b] m[c,a,b]  =>  dL/dm[c,a,b] += -t_scale * Wr[a] Wc[b] * dL/ddense[c].
+      // (1) the strips of one source pixel are consecutive lanes: segmented suffix sum of their flow gradients;
+      float g0, g1;
+      upk2(st.g[0], g0, g1);
+      const int key = h.count > 0 ? h.src : -1 - lane;  // padding strips never merge
+      const int prev = __shfl_up_sync(0xffffffffu, key, 1);
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+      for (int o = 1; o < 32; o <<= 1) {
+        const float u0 = __shfl_down_sync(0xffffffffu, g0, o), u1 = __shfl_down_sync(0xffffffffu, g1, o);
+        const int uk = __shfl_down_sync(0xffffffffu, key, o);
+        if (lane + o < 32 && uk == key) {
+          g0 += u0;
+          g1 += u1;
+        }
+      }
+      const bool head = h.count > 0 && (lane == 0 || prev != key);
+      // (2) the head of every pixel run turns the pixel's gradient into its 8 node contributions; the ~5 pixels of a warp-tile
+      // nearly always sit in ONE patch cell (same 4 nodes): then the 8 values are summed over the warp and one lane adds them
+      // to the CTA's accumulators (a float atomicAdd in shared memory is a compare-and-swap loop: keep it uncontended)
+      g0 *= -a.t_scale;
+      g1 *= -a.t_scale;
+      const float wr[2] = {1.0f - taps.lr, taps.lr}, wc[2] = {1.0f - taps.lc, taps.lc};
+      const int an[2] = {taps.a0, taps.a1}, bn[2] = {taps.b0, taps.b1};
+      float c[8];
+      int node[4];
 #pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            const float w = wr[u] * wc[v];
-            const int node = an[u] * a.tile.wp + bn[v];
-            atomicAdd(&sgrad[node], w * g0);
-            atomicAdd(&sgrad[np + node], w * g1);
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const float w = head ? wr[u] * wc[v] : 0.f;
+          node[2 * u + v] = an[u] * a.tile.wp + bn[v];
+          c[2 * u + v] = w * g0;
+          c[4 + 2 * u + v] = w * g1;
+        }
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      if (heads != 0u) {
+        const int first = __ffs(heads) - 1;
+        const int cell_key = (taps.a0 << 20) | (taps.a1 << 10) | 0;  // rows; columns compared separately (grids up to 1024 nodes)
+        const int col_key = (taps.b0 << 10) | taps.b1;
+        // (both shuffles unconditionally: a short-circuited && would leave lanes out of the second full-mask shuffle)
+        const int first_cell = __shfl_sync(0xffffffffu, cell_key, first), first_col = __shfl_sync(0xffffffffu, col_key, first);
+        const bool same = (cell_key == first_cell) & (col_key == first_col);
+        if (__all_sync(0xffffffffu, !head || same)) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) c[k] = warp_sum(c[k]);
+          if (lane == first) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              atomicAdd(&sgrad[node[k]], c[k]);
+              atomicAdd(&sgrad[np + node[k]], c[4 + k]);
+            }
           }
+        } else if (head) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            atomicAdd(&sgrad[node[k]], c[k]);
+            atomicAdd(&sgrad[np + node[k]], c[4 + k]);
+          }
+        }
       }
     } else if (MODEL == CMAX_MOTION_VOXEL) {
 #pragma unroll

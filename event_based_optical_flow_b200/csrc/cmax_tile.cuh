@@ -11,14 +11,15 @@ struct TileGeom {
   int sh, sw;        // integer up-sampling factors (the sliding window)
   int H, W;          // image
   int h1, w1;        // crop offsets inside the up-sampled padded grid
+  float inv_sh, inv_sw;  // 1.0f / sh, 1.0f / sw (IEEE fp32 division, done once on the host: the same value the device would compute)
 };
 
 // Source taps of output index `full` (coordinates of the up-sampled padded grid) along one axis, PyTorch bilinear
 // align_corners=false semantics: src = max(0, (full + 0.5) / s - 0.5); taps i0 = floor(src), i1 = min(i0 + 1, n_pad - 1)
 // with weights (1 - l, l); padded index p -> grid node clamp(p - pad, 0, n - 1) (replicate padding).
-__device__ __forceinline__ void axis_taps(int full, int s, int n, int pad, int* a0, int* a1, float* l1) {
+__device__ __forceinline__ void axis_taps(int full, float inv_s, int n, int pad, int* a0, int* a1, float* l1) {
   const int n_pad = n + 2 * pad;
-  float src = ((float)full + 0.5f) * (1.0f / (float)s) - 0.5f;
+  float src = ((float)full + 0.5f) * inv_s - 0.5f;
   src = fmaxf(src, 0.0f);
   const int i0 = (int)src;
   const int i1 = min(i0 + 1, n_pad - 1);
@@ -36,8 +37,8 @@ struct TileTaps {
 };
 __device__ __forceinline__ TileTaps tile_taps(const TileGeom& g, int i, int j) {
   TileTaps t;
-  axis_taps(i + g.h1, g.sh, g.hp, g.pad_h, &t.a0, &t.a1, &t.lr);
-  axis_taps(j + g.w1, g.sw, g.wp, g.pad_w, &t.b0, &t.b1, &t.lc);
+  axis_taps(i + g.h1, g.inv_sh, g.hp, g.pad_h, &t.a0, &t.a1, &t.lr);
+  axis_taps(j + g.w1, g.inv_sw, g.wp, g.pad_w, &t.b0, &t.b1, &t.lc);
   return t;
 }
 __device__ __forceinline__ float tile_value(const float* __restrict__ m, const TileGeom& g, const TileTaps& t) {

@@ -50,10 +50,10 @@ __global__ void __launch_bounds__(256) tile_flow_upsample_backward_kernel(const 
     int t0, t1;
     float l;
     if (t < nr) {
-      axis_taps(i_lo + t + g.h1, g.sh, g.hp, g.pad_h, &t0, &t1, &l);
+      axis_taps(i_lo + t + g.h1, g.inv_sh, g.hp, g.pad_h, &t0, &t1, &l);
       wr[t] = (t0 == a ? 1.0f - l : 0.f) + (t1 == a ? l : 0.f);
     } else {
-      axis_taps(j_lo + (t - nr) + g.w1, g.sw, g.wp, g.pad_w, &t0, &t1, &l);
+      axis_taps(j_lo + (t - nr) + g.w1, g.inv_sw, g.wp, g.pad_w, &t0, &t1, &l);
       wc[t - nr] = (t0 == b ? 1.0f - l : 0.f) + (t1 == b ? l : 0.f);
     }
   }
@@ -80,6 +80,8 @@ int make_tile_geom(const char* fn, int hp, int wp, int pad_h, int pad_w, int sh,
   TileGeom g;
   g.hp = hp; g.wp = wp; g.pad_h = pad_h; g.pad_w = pad_w; g.sh = sh; g.sw = sw; g.H = H; g.W = W;
   const int full_h = (hp + 2 * pad_h) * sh, full_w = (wp + 2 * pad_w) * sw;
+  g.inv_sh = 1.0f / (float)sh;
+  g.inv_sw = 1.0f / (float)sw;
   g.h1 = full_h / 2 - H / 2;
   g.w1 = full_w / 2 - W / 2;
   CMAX_REQUIRE(g.h1 >= 0 && g.w1 >= 0 && g.h1 + H <= full_h && g.w1 + W <= full_w,

@@ -419,10 +419,13 @@ class TileFlowObjective:
     interpolate(motion) * t_scale -> calculate_cost).  The gradient comes back on the patch grid (hp*wp*2 numbers), so
     the host round trip per optimiser step is a few KB.
 
-    `fused` (default: whenever the plan has strips): the event kernels evaluate the map at every source pixel themselves
-    (motion model "tile-flow", cmax_plan_set_tile_flow) -- no dense [2,H,W] flow or gradient exists, a CM iteration stays at
-    three launches, and a sharded objective exchanges 2*hp*wp floats instead of a dense gradient.  Otherwise the up-sampling
-    kernel, the dense objective and the adjoint kernel are composed (same numbers: both evaluate the same expression)."""
+    `fused=True`: the event kernels evaluate the map at every source pixel themselves (motion model "tile-flow",
+    cmax_plan_set_tile_flow) -- no dense [2,H,W] flow or gradient exists, a CM iteration stays at three launches, and a sharded
+    objective exchanges 2*hp*wp floats instead of a dense gradient.  `fused=False`: the up-sampling kernel, the dense objective
+    and the adjoint kernel are composed (same numbers: both evaluate the same expression).  Default: fused for SHARDED
+    objectives whose plan has strips (the 2 KB gradient exchange is what pays), composed otherwise -- on one GPU the per-strip
+    evaluation of the grid and the node reductions cost K1 / K3 slightly more (49.1 us) than the two small extra kernels of the
+    composition (46.4 us at config 2; bench.py `tile_flow`)."""
 
     def __init__(self, objective: ContrastObjective, patch_size, sliding_window, patch_shift=(0, 0), t_scale: float = 1.0,
                  fused: Optional[bool] = None):
@@ -437,7 +440,7 @@ class TileFlowObjective:
         can_fuse = objective.plan.n_strips > 0 and objective.plan.n > 0
         if fused and not can_fuse:
             raise ValueError("the fused tile-flow model needs a plan with strips (a pixel-ordered batch dense enough to be cut into strips)")
-        self.fused = can_fuse if fused is None else bool(fused)
+        self.fused = (can_fuse and objective.group is not None) if fused is None else bool(fused)
         self._geom = None
 
     def _set_geometry(self, grid) -> None:

@@ -137,6 +137,7 @@ class B200CostMixin:
     b200_event_order = "pixel"
     b200_process_group = None  # set to a torch.distributed group to shard the events of every rank
     b200_exchange = "nccl"     # "peer": the two sums over NVLink peer memory inside the kernels (needs symmetric memory)
+    b200_fuse_tile_flow = None  # None: TileFlowObjective's default (fused when sharded); True / False force the tile-flow model on / off
 
     b200_max_batches = 2  # resident event batches (the current one and its predecessor); older ones are closed
 
@@ -221,9 +222,10 @@ class B200CostMixin:
     def objective_scipy(self, motion_array, *args, **kw):
         """Same contract as `PyramidalPatchContrastMaximization.objective_scipy(motion_array, events, coarser_motion,
         suppress_log)` (src/solver/patch_contrast_pyramid.py:430-462).  For the configuration that method spends its time in --
-        CUDA events, bilinear patch interpolation, not time-aware -- the loss is evaluated from the patch motion directly: the
-        strip kernels compute interpolate(motion) * t_scale per source pixel and return dL/d(patch motion), so no dense flow
-        or dense gradient is ever built.  Anything else goes to the reference's own method."""
+        CUDA events, bilinear patch interpolation, not time-aware -- the loss is evaluated from the patch motion directly through
+        `TileFlowObjective`: fused, the strip kernels compute interpolate(motion) * t_scale per source
+        pixel and return dL/d(patch motion), no dense flow or dense gradient is ever built; composed, the up-sampling and its
+        adjoint are two small kernels around the dense model.  Anything else goes to the reference's own method."""
         events = args[0] if len(args) >= 1 else kw.get("events")
         pyramid_call = len(args) >= 2 and isinstance(args[1], dict) or "coarser_motion" in kw
         fast = (pyramid_call and isinstance(events, torch.Tensor) and events.is_cuda and isinstance(motion_array, torch.Tensor)
@@ -252,7 +254,10 @@ class B200CostMixin:
                 tile = batch.tile_objectives.get(key)
                 if tile is None:
                     from .objective import TileFlowObjective
-                    tile = TileFlowObjective(obj, geometry[0], geometry[1], geometry[2], t_scale)
+                    fuse = self.b200_fuse_tile_flow
+                    if fuse and obj.plan.n_strips == 0:
+                        fuse = False  # (a sparse batch has no strips: the composition is the only form)
+                    tile = TileFlowObjective(obj, geometry[0], geometry[1], geometry[2], t_scale, fused=fuse)
                     batch.tile_objectives[key] = tile
                 loss = tile(motion)
                 self._b200_register(cost, loss)

@@ -33,8 +33,8 @@ def _solvers(R, config_name):
     shape = (cfg["data"]["height"], cfg["data"]["width"])
     base = R.solver.PyramidalPatchContrastMaximization
 
-    class B200Pyramidal(B200CostMixin, base):  # INTEGRATION.md section 3, verbatim
-        pass
+    class B200Pyramidal(B200CostMixin, base):  # INTEGRATION.md section 3 (+ the tile-flow model forced on where the batch allows it)
+        b200_fuse_tile_flow = True
 
     with mock.patch("torch.cuda.is_available", return_value=False):  # the reference side stays on the CPU
         ref = base(shape, {}, cfg["solver"], cfg["optimizer"], cfg["output"], None)

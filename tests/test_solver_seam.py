@@ -299,7 +299,7 @@ def test_mixin_objective_scipy_runs_the_fused_tile_flow():
             raise AssertionError("the fused path must not fall through to the reference composition here")
 
     class Fast(B200CostMixin, PyramidLike):
-        pass
+        b200_fuse_tile_flow = True
 
     for cost_name, cw in (("image_variance", None), ("hybrid", {"multi_focal_normalized_gradient_magnitude": 1.0, "total_variation": 0.01})):
         slv = Fast(B, (H, W), cost_name, 1 if cost_name == "hybrid" else 0, cost_with_weight=cw)
