@@ -291,10 +291,11 @@ class ContrastObjective:
             raise ValueError(f"motion for {self.motion_model} must have shape {self.motion_shape}, got {tuple(motion.shape)}")
         return motion.detach().to(torch.float32).contiguous()
 
-    def _vote_and_fold(self, m: torch.Tensor, stream: int) -> None:
+    def _vote_and_fold(self, m: torch.Tensor, stream: int, model: Optional[int] = None) -> None:
         """K1 + fold: this rank's (partial) IWE stack is in `self._iwe_view` afterwards."""
         iwe_ptr = C.c_void_p()
-        _lib.call("cmax_objective_vote", self.plan.handle, _lib.MOTION[self.motion_model], m.data_ptr(), self._ws_ptr, stream)
+        _lib.call("cmax_objective_vote", self.plan.handle, _lib.MOTION[self.motion_model] if model is None else model, m.data_ptr(),
+                  self._ws_ptr, stream)
         _lib.call("cmax_objective_fold", self.plan.handle, self._ws_ptr, C.byref(iwe_ptr), stream)
         if self._iwe_view is None:
             off = iwe_ptr.value - self._ws.data_ptr()
@@ -315,7 +316,7 @@ class ContrastObjective:
             _lib.call("cmax_objective_sharded", self.plan.handle, model, m.data_ptr(), C.byref(self.spec), orig, self._ws_ptr,
                       C.byref(self._peers), cost.data_ptr(), gptr, stream)
         else:  # sharded, NCCL all-reduces between the stages (the baseline exchange)
-            self._vote_and_fold(m, stream)
+            self._vote_and_fold(m, stream, model)
             torch.distributed.all_reduce(self._iwe_view, group=self.group)
             _lib.call("cmax_objective_cost", self.plan.handle, C.byref(self.spec), orig, self._ws_ptr, 1 if grad is not None else 0,
                       cost.data_ptr(), gptr, grad.numel() if grad is not None else 0, stream)

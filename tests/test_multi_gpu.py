@@ -53,6 +53,25 @@ def _worker(rank, world, port, out):
                 both = [torch.zeros_like(g) for _ in range(world)]
                 dist.all_gather(both, g)
                 assert all(torch.equal(both[0], b) for b in both), (cost, exchange, reshard)
+        # the tile-flow model on a sharded objective: the gradient that crosses NVLink is 2 * hp * wp floats
+        grid, window = (6, 8), (16, 16)
+        motion = torch.from_numpy(rng.uniform(-5, 5, (2,) + grid).astype(np.float32)).to(dev)
+        full = B.ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow")
+        v_ref, g_ref = B.TileFlowObjective(full, window, window, (0, 0), 0.9, fused=False).value_and_grad(motion)
+        for exchange in ("nccl", "peer"):
+            mine = reshard_events_by_pixel(shard_events(ev, world, rank), (H, W))
+            obj = make_sharded_objective(mine, (H, W), cost="image_variance", motion_model="dense-flow", exchange=exchange)
+            tile = B.TileFlowObjective(obj, window, window, (0, 0), 0.9)
+            assert tile.fused, "sharded + strips -> the fused tile-flow model is the default"
+            for _ in range(3):
+                v, g = tile.value_and_grad(motion)
+            torch.cuda.synchronize()
+            rel_v = abs(float(v) - float(v_ref)) / abs(float(v_ref))
+            rel_g = float(torch.linalg.norm(g - g_ref) / torch.linalg.norm(g_ref))
+            results[("tile-flow", exchange, True)] = (rel_v, rel_g, 0.0)
+            both = [torch.zeros_like(g) for _ in range(world)]
+            dist.all_gather(both, g)
+            assert all(torch.equal(both[0], b) for b in both), ("tile-flow", exchange)
         out[rank] = results
     finally:
         dist.destroy_process_group()
