@@ -1,6 +1,7 @@
-// The per-iteration hot path: K1 (warp + bilinear vote of every event, all reference times in one pass),
-// the fold (per-corner accumulators -> IWE, with the variance sums fused in), K2 glue (blur / statistics / scalar
-// cost / per-corner gradient pictures) and K3 (re-warp, gather dL/dIWE, chain to dL/dmotion).
+// The event kernels that read the plan's PACKED copy: the per-event baselines (one thread per event) and the run kernels
+// (each thread walks 8 consecutive events), for K1 (warp + bilinear vote of every event, all reference times in one pass) and
+// K3 (re-warp, gather dL/dIWE, chain to dL/dmotion), plus the dispatch over motion model / reference times / variant.
+// The strip kernels (the default for dense batches) live in cmax_lean.cu, everything image-sized in cmax_mid.cu.
 //
 // Data layout in HBM / L2 (everything image-sized is L2 resident; only the event stream comes from HBM):
 //   events   float4[n]                       one 16-byte streamed load per event per pass
