@@ -442,15 +442,17 @@ class TileFlowObjective:
         if fused and not can_fuse:
             raise ValueError("the fused tile-flow model needs a plan with strips (a pixel-ordered batch dense enough to be cut into strips)")
         self.fused = (can_fuse and objective.group is not None) if fused is None else bool(fused)
-        self._geom = None
 
     def _set_geometry(self, grid) -> None:
+        """The geometry lives in the PLAN (host-side state of the C library), and several TileFlowObjectives may share one
+        plan: compare with what the plan currently holds, not with what this object set last."""
         geom = (int(grid[0]), int(grid[1]), int(self.pad[0]), int(self.pad[1]), self.window[0], self.window[1], self.t_scale)
-        if geom != self._geom:
+        plan = self.objective.plan
+        if geom != getattr(plan, "_tile_geom", None):
             if geom[0] * geom[1] > 1024:
                 raise ValueError(f"the fused tile-flow model supports patch grids of up to 1024 nodes, got {geom[0]}x{geom[1]}")
-            _lib.call("cmax_plan_set_tile_flow", self.objective.plan.handle, *geom)
-            self._geom = geom
+            _lib.call("cmax_plan_set_tile_flow", plan.handle, *geom)
+            plan._tile_geom = geom
 
     def _check(self, motion: torch.Tensor) -> None:
         _require_cuda(motion, "motion")
