@@ -171,7 +171,7 @@ class ContrastObjective:
                  motion_model: str = "dense-flow", sigma: float = 0.0, omit_boundary: bool = True, direction: str = "minimize",
                  outer_padding=0, n_bins: Optional[int] = None, order: str = "pixel", process_group=None,
                  t_range: Optional[Tuple[float, float]] = None, orig_events: Optional[torch.Tensor] = None,
-                 exchange: str = "nccl"):
+                 exchange: str = "nccl", cuda_graph: bool = False):
         if cost not in COST_TABLE:
             raise KeyError(f"cost {cost!r} has no fused CUDA form; available: {sorted(COST_TABLE)}")
         if motion_model not in _lib.MOTION or motion_model == "tile-flow":  # (the tile-flow model is reached through TileFlowObjective)
@@ -226,6 +226,10 @@ class ContrastObjective:
         with torch.cuda.device(self.device):
             _lib.call("cmax_objective_workspace_init", self.plan.handle, self._ws_ptr, _stream_ptr())
         self._cost = torch.zeros(1, dtype=torch.float64, device=self.device)
+        # small batches (the shipped YAMLs' 30 k events) are launch / host bound: with `cuda_graph` every evaluation replays a
+        # graph captured once per (value | value + gradient) into static buffers -- one launch, no per-call ctypes traffic
+        self.cuda_graph = bool(cuda_graph) and process_group is None
+        self._graphs: dict = {}
         self._orig_stat = None
         if form != "plain":
             self._orig_stat = self._orig_statistic(orig_events)
@@ -328,13 +332,42 @@ class ContrastObjective:
         """-> (cost: 0-dim float64 CUDA tensor, grad: fp32 tensor shaped like motion or None).  No host sync."""
         m = self._check_motion(motion)
         with torch.cuda.device(self.device):
-            cost = torch.empty(1, dtype=torch.float64, device=self.device)
-            grad = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device) if want_grad else None
-            self._evaluate(m, cost, grad, _stream_ptr())
+            if self.cuda_graph:
+                cost, grad = self._replay(m, want_grad)
+            else:
+                cost = torch.empty(1, dtype=torch.float64, device=self.device)
+                grad = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device) if want_grad else None
+                self._evaluate(m, cost, grad, _stream_ptr())
         if self._post_sign < 0:
             cost = -cost
             grad = -grad if grad is not None else None
         return cost[0], grad
+
+    def _replay(self, m: torch.Tensor, want_grad: bool):
+        """Graph-cached evaluation: capture `_evaluate` once per variant into static buffers, then copy-in / replay / copy-out."""
+        entry = self._graphs.get(want_grad)
+        if entry is None:
+            sm = torch.empty_like(m)
+            sc = torch.empty(1, dtype=torch.float64, device=self.device)
+            sg = torch.empty(self.motion_shape, dtype=torch.float32, device=self.device) if want_grad else None
+            sm.copy_(m)
+            self.plan.set_refs(self.directions, self.n_bins)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside the capture (first-use initialisation of the kernels)
+                for _ in range(2):
+                    self._evaluate(sm, sc, sg, side.cuda_stream)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._evaluate(sm, sc, sg, _stream_ptr())
+            entry = (graph, sm, sc, sg)
+            self._graphs[want_grad] = entry
+        graph, sm, sc, sg = entry
+        self.plan.set_refs(self.directions, self.n_bins)  # (no-op unless another objective re-packed the shared plan)
+        sm.copy_(m)
+        graph.replay()
+        return sc.clone(), (sg.clone() if want_grad else None)
 
     def value(self, motion: torch.Tensor) -> torch.Tensor:
         return self.value_and_grad(motion, want_grad=False)[0]

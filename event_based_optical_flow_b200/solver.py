@@ -137,6 +137,7 @@ class B200CostMixin:
     b200_event_order = "pixel"
     b200_process_group = None  # set to a torch.distributed group to shard the events of every rank
     b200_exchange = "nccl"     # "peer": the two sums over NVLink peer memory inside the kernels (needs symmetric memory)
+    b200_cuda_graph = False     # True: single-GPU objectives replay a CUDA graph per evaluation (small, launch-bound batches)
     b200_fuse_tile_flow = None  # None: TileFlowObjective's default (fused when sharded); True / False force the tile-flow model on / off
 
     b200_max_batches = 2  # resident event batches (the current one and its predecessor); older ones are closed
@@ -196,7 +197,7 @@ class B200CostMixin:
                 batch.plans[plan_key] = plan
             obj = ContrastObjective(plan, image_size, cost=cost_name, motion_model=motion_model, sigma=sigma, omit_boundary=True,
                                     direction=direction, n_bins=n_bins, orig_events=events, process_group=self.b200_process_group,
-                                    exchange=self.b200_exchange)
+                                    exchange=self.b200_exchange, cuda_graph=self.b200_cuda_graph)
             batch.objectives[key] = obj
         return obj
 

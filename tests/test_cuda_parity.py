@@ -434,3 +434,27 @@ def test_very_dense_batch_runs_the_segmented_gradient_reduction(B, dev):
     assert _rel(g5.cpu().numpy(), ref_g.numpy()) <= RTOL, _rel(g5.cpu().numpy(), ref_g.numpy())
     assert _rel(g5.cpu().numpy(), g2.cpu().numpy()) <= RTOL
     assert float(g5[:, :8].abs().max()) == 0.0 and float(g5[:, 24:].abs().max()) == 0.0  # no source pixels outside the band
+
+
+def test_cuda_graph_cached_evaluation(B, dev, golden_c1):
+    """`cuda_graph=True`: every evaluation replays a graph captured once per variant (config 1's regime: 30 k events, launch
+    bound).  Same numbers as the eager calls, for several motions in a row, value-only and value + gradient interleaved."""
+    g = golden_c1
+    ev = torch.from_numpy(g["events"]).float().to(dev)
+    eager = B.ContrastObjective(ev, (260, 346), cost="image_variance", motion_model="2d-translation")
+    graphed = B.ContrastObjective(ev, (260, 346), cost="image_variance", motion_model="2d-translation", cuda_graph=True)
+    rng = np.random.default_rng(3)
+    for k in range(6):
+        theta = torch.from_numpy(rng.uniform(-20, 20, 2).astype(np.float32)).to(dev)
+        v0, g0 = eager.value_and_grad(theta)
+        if k % 2:
+            v1 = graphed.value(theta)
+            assert abs(float(v1) - float(v0)) <= 1e-6 * abs(float(v0))
+        else:
+            v1, g1 = graphed.value_and_grad(theta)
+            assert abs(float(v1) - float(v0)) <= 1e-6 * abs(float(v0))
+            assert _rel(g1.cpu().numpy(), g0.cpu().numpy()) <= 1e-5
+    m = torch.tensor([3.0, -7.0], dtype=torch.float64, device=dev, requires_grad=True)
+    (ga,) = torch.autograd.grad(graphed(m), m)
+    (gb,) = torch.autograd.grad(eager(m), m)
+    assert _rel(ga.cpu().numpy(), gb.cpu().numpy()) <= 1e-5
