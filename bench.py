@@ -450,6 +450,25 @@ def run_b200(args) -> None:
     h2d = int(host_motions[0].numel() * 4)
     d2h = int(out_host.numel() * 4)
 
+    # ---- Hessian-vector product (what Newton-CG / trust-* of the shipped YAMLs ask for per inner CG step): device time per call
+    hvp_ms = None
+    if world == 1 and cfg["model"] != "time-aware" and not args.skip_cpu:
+        try:
+            vec = torch.randn(motion_shape, dtype=torch.float32, device=dev)
+            obj.hvp(motions[0], vec)
+            torch.cuda.synchronize()
+            t_h = []
+            for k in range(3):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                obj.hvp(motions[k % N_FLOWS], vec)
+                b.record()
+                torch.cuda.synchronize()
+                t_h.append(a.elapsed_time(b))
+            hvp_ms = float(np.mean(t_h))
+        except Exception as e:  # report, never fail the benchmark line over the second-order leg
+            hvp_ms = f"failed: {e!r}"
+
     # ---- the same batch driven by the patch grid the pyramid optimises (16x16 nodes, the shipped YAML's geometry): the tile-flow
     # model evaluates the dense flow inside the event kernels, so the per-step host traffic is 2 KB each way instead of 720 KB
     tile_leg = None
@@ -693,7 +712,7 @@ def run_b200(args) -> None:
                     "what": "host pinned motion -> device, step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
             "gpu_launches": per_step_kernels * args.steps if per_step_kernels else None,
             "plan_ms": plan_ms, "reshard_ms": reshard_ms, "events_this_rank": n_local, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
-            "tile_flow": tile_leg, "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
+            "hvp_ms": hvp_ms, "tile_flow": tile_leg, "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
         }
     if line is not None:
         print(json.dumps(line), flush=True)
