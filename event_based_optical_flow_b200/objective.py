@@ -394,22 +394,27 @@ class ContrastObjective:
     #    call each, every backward differentiable once more), so that torch can differentiate the gradient itself
     def modular_cost(self, motion: torch.Tensor) -> torch.Tensor:
         """The cost as a twice-differentiable function of `motion` (same value as `value(motion)` up to fp32 summation
-        order).  Composition and sign conventions of src/solver/patch_contrast_base.py:289-352 and src/costs/*.py."""
+        order).  Composition and sign conventions of src/solver/patch_contrast_base.py:289-352 and src/costs/*.py.
+        Sharded objectives: a collective call (every rank, same motion)."""
         from . import ops
-        if self.group is not None:
-            raise NotImplementedError("Hessian-vector products are not implemented for sharded objectives")
         if self._events_ref is None:
             raise NotImplementedError("Hessian-vector products need the event tensor: pass `orig_events=` when the objective is built from an EventPlan")
         ev = self._events_ref
         if ev.shape[1] == 3:
             ev = torch.cat([ev, ev.new_zeros(len(ev), 1)], dim=1)
         ev = ev[:, :4].to(torch.float32)
-        if self._modular_tp is None:
-            self._modular_tp = ops.time_params(ev, self.directions, self.n_bins)
+        if self._modular_tp is None:  # (sharded: reference time / period / bin edges from the GLOBAL time range, like the plan)
+            self._modular_tp = ops.time_params(ev, self.directions, self.n_bins, t_range=(self.plan.t_min, self.plan.t_max))
+        # sharded: every rank warps and votes ITS events; the partial IWEs are summed over the ranks (ops.SumPartials) and the
+        # replicated motion is put to local use (ops.UseReplicated) -- the two are each other's adjoint, so the recorded backward
+        # and its own backward (the Hessian-vector product) come out right on every rank
+        m_local = ops.UseReplicated.apply(motion, self.group) if self.group is not None else motion
         stats = []
         for r in range(len(self.directions)):
-            warped = ops.WarpFunction.apply(ev, motion, self.motion_model, self.image_size, self._modular_tp, r)
+            warped = ops.WarpFunction.apply(ev, m_local, self.motion_model, self.image_size, self._modular_tp, r)
             iwe = ops.VoteFunction.apply(warped, None, self.padded_size, self.plan.pad, "bilinear_vote")
+            if self.group is not None:
+                iwe = ops.SumPartials.apply(iwe, self.group)
             if self.sigma > 0:
                 iwe = ops.BlurFunction.apply(iwe, self.sigma)
             stats.append(ops.ImageStatFunction.apply(iwe, self.stat, self.omit_boundary).double())

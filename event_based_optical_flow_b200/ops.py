@@ -27,17 +27,56 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------ time
-def time_params(events: torch.Tensor, directions: Sequence, n_bins: int = 0, normalize_t: bool = True) -> torch.Tensor:
+def time_params(events: torch.Tensor, directions: Sequence, n_bins: int = 0, normalize_t: bool = True,
+                t_range: Optional[Tuple[float, float]] = None) -> torch.Tensor:
     """Device-resident cmax_time_params_t for these events (min/max of t taken from THIS batch, as the reference
-    does on every warp call, src/warp.py:201-259)."""
+    does on every warp call, src/warp.py:201-259; `t_range` = the GLOBAL range when the batch is one shard of a larger one)."""
     ev = _f32c(events)
     with torch.cuda.device(ev.device):
-        mm = torch.empty(2, dtype=torch.float32, device=ev.device)
-        _lib.call("cmax_time_range", ev.data_ptr(), ev.shape[0], ev.shape[1], mm.data_ptr(), _stream())
+        if t_range is not None:
+            mm = torch.tensor([float(t_range[0]), float(t_range[1])], dtype=torch.float32, device=ev.device)
+        else:
+            mm = torch.empty(2, dtype=torch.float32, device=ev.device)
+            _lib.call("cmax_time_range", ev.data_ptr(), ev.shape[0], ev.shape[1], mm.data_ptr(), _stream())
         tp = torch.empty(_lib.TIME_PARAMS_BYTES, dtype=torch.uint8, device=ev.device)
         _lib.call("cmax_time_params", mm.data_ptr(), _lib.refs_array(tuple(directions)), len(directions), int(n_bins),
                   1 if normalize_t else 0, tp.data_ptr(), _stream())
     return tp
+
+
+# ------------------------------------------------------------------------------------------------ sharded composition
+class SumPartials(torch.autograd.Function):
+    """y = sum over ranks of x (an all-reduce), every rank holding the result.  Dual of `UseReplicated`: under rank-local
+    autograd of REPLICATED scalars (every rank differentiates its own copy of the same cost) the cotangent of y is replicated
+    and each rank's x simply receives it -- but as an operation in the recorded backward it is a replicated value put to local
+    use, whose own adjoint is a sum over ranks again.  Making the two Functions each other's backward keeps derivatives of ANY
+    order correct (a Hessian-vector product needs the all-reduce of the tangent images sum_q J_q v; it appears here as the
+    backward of the `UseReplicated` in `SumPartials.backward`)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        y = x.detach().clone()
+        torch.distributed.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return UseReplicated.apply(g, ctx.group), None
+
+
+class UseReplicated(torch.autograd.Function):
+    """Identity on a value every rank holds identically and uses in its own partial computation (the motion; dL/dIWE);
+    its adjoint sums the ranks' contributions."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return SumPartials.apply(g, ctx.group), None
 
 
 # ------------------------------------------------------------------------------------------------ warp

@@ -176,6 +176,63 @@ def test_sharded_composition_gloo_world2():
         assert len(out) == world and out[0] == out[1]
 
 
+def _dual_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from event_based_optical_flow_b200.ops import SumPartials, UseReplicated
+        torch.manual_seed(0)
+        A = torch.randn(world, 7, 5, dtype=torch.float64)  # every rank draws the same numbers; rank r USES A[r]
+        m0 = torch.randn(5, dtype=torch.float64)
+        v = torch.randn(5, dtype=torch.float64)
+
+        def part(m, r):  # a nonlinear 'partial image' of rank r
+            return torch.sin(A[r] @ m) + (A[r] @ m) ** 2
+
+        def cost_of_image(img):
+            return (img ** 3).sum() + img.var()
+
+        def sharded(m):  # what every rank records: its own partial, summed over the ranks
+            return cost_of_image(SumPartials.apply(part(UseReplicated.apply(m, None), rank), None))
+
+        def whole(m):
+            return cost_of_image(sum(part(m, r) for r in range(world)))
+
+        m = m0.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(sharded(m), m, create_graph=True)
+        (hv,) = torch.autograd.grad(g, m, v)
+        mr = m0.clone().requires_grad_(True)
+        (gr,) = torch.autograd.grad(whole(mr), mr, create_graph=True)
+        (hvr,) = torch.autograd.grad(gr, mr, v)
+        torch.testing.assert_close(g.detach(), gr.detach(), rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(hv, hvr, rtol=1e-12, atol=1e-12)
+        # the path scipy_autograd takes (torch.autograd.functional.vhp), and a third derivative for good measure
+        _, hv2 = torch.autograd.functional.vhp(sharded, m0, v)
+        torch.testing.assert_close(hv2, hvr, rtol=1e-12, atol=1e-12)
+        m = m0.clone().requires_grad_(True)
+        (g,) = torch.autograd.grad(sharded(m), m, create_graph=True)
+        (h1,) = torch.autograd.grad(g, m, v, create_graph=True)
+        (t3,) = torch.autograd.grad(h1, m, v)
+        mr = m0.clone().requires_grad_(True)
+        (gr,) = torch.autograd.grad(whole(mr), mr, create_graph=True)
+        (h1r,) = torch.autograd.grad(gr, mr, v, create_graph=True)
+        (t3r,) = torch.autograd.grad(h1r, mr, v)
+        torch.testing.assert_close(t3, t3r, rtol=1e-11, atol=1e-11)
+        out[rank] = hv.tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", (2, 3))
+def test_sharded_second_order_autograd_pair_gloo(world):
+    """`ops.SumPartials` / `ops.UseReplicated` (each the other's backward): gradient, Hessian-vector product and a third
+    derivative recorded rank-locally on a sharded composition equal the single-process ones, and every rank holds the same."""
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_dual_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert len(out) == world and all(out[r] == out[0] for r in range(world))
+
+
 def test_cost_plugin_contract_on_the_host():
     """The plugin contract the reference's solvers rely on (src/costs/base.py:11-77, src/costs/hybrid.py:12-79), as far as it
     needs no GPU: KeyError for a missing arg-dict key, history bookkeeping, hybrid weights / 'inv' / member histories."""

@@ -72,6 +72,30 @@ def _worker(rank, world, port, out):
             both = [torch.zeros_like(g) for _ in range(world)]
             dist.all_gather(both, g)
             assert all(torch.equal(both[0], b) for b in both), ("tile-flow", exchange)
+        # second order on a sharded objective (a collective call): H v of the single-GPU objective, through `hvp` and through
+        # the path scipy_autograd takes (functional.vhp over obj(m)); ops.SumPartials / ops.UseReplicated carry the sums
+        vec = torch.from_numpy(rng.standard_normal((2, H, W)).astype(np.float32)).to(dev)
+        for cost, sigma in (("image_variance", 0.0), ("multi_focal_normalized_gradient_magnitude", 1.0)):
+            full = B.ContrastObjective(ev, (H, W), cost=cost, motion_model="dense-flow", sigma=sigma)
+            hv_ref = full.hvp(flow, vec)
+            mine = reshard_events_by_pixel(shard_events(ev, world, rank), (H, W))
+            obj = make_sharded_objective(mine, (H, W), cost=cost, motion_model="dense-flow", sigma=sigma, exchange="peer")
+            hv = obj.hvp(flow, vec)
+            _, hv_vhp = torch.autograd.functional.vhp(lambda m: obj(m), flow.double(), vec.double())
+            rel = lambda a, b: float(torch.linalg.norm(a.double() - b.double()) / torch.linalg.norm(b.double()))  # noqa: E731
+            results[("hvp", cost, "hvp")] = (0.0, rel(hv, hv_ref), 0.0)
+            results[("hvp", cost, "vhp")] = (0.0, rel(hv_vhp, hv_ref), 0.0)
+            both = [torch.zeros_like(hv) for _ in range(world)]
+            dist.all_gather(both, hv)
+            assert all(torch.equal(both[0], b) for b in both), ("hvp", cost)
+        pm = torch.from_numpy(rng.uniform(-5, 5, (2,) + grid)).to(dev)
+        pv = torch.from_numpy(rng.standard_normal((2,) + grid)).to(dev)
+        full = B.ContrastObjective(ev, (H, W), cost="image_variance", motion_model="dense-flow")
+        _, hv_ref = torch.autograd.functional.vhp(lambda m: B.TileFlowObjective(full, window, window, (0, 0), 0.9, fused=False)(m), pm, pv)
+        obj = make_sharded_objective(reshard_events_by_pixel(shard_events(ev, world, rank), (H, W)), (H, W), cost="image_variance",
+                                     motion_model="dense-flow", exchange="peer")
+        _, hv = torch.autograd.functional.vhp(lambda m: B.TileFlowObjective(obj, window, window, (0, 0), 0.9)(m), pm, pv)
+        results[("hvp", "tile-flow", "vhp")] = (0.0, float(torch.linalg.norm(hv - hv_ref) / torch.linalg.norm(hv_ref)), 0.0)
         out[rank] = results
     finally:
         dist.destroy_process_group()
@@ -88,5 +112,6 @@ def test_two_gpu_sharded_objective_matches_single_gpu():
         for rank in range(world):
             for key, (rel_v, rel_g, rel_vo) in out[rank].items():
                 assert rel_v <= 1e-5, (rank, key, rel_v)
-                assert rel_g <= 1e-5, (rank, key, rel_g)
+                print(rank, key, rel_v, rel_g)
+                assert rel_g <= (2e-5 if key[0] == "hvp" else 1e-5), (rank, key, rel_g)  # (H v: fp32 second differences of two summation orders)
                 assert rel_vo <= 1e-6, (rank, key, rel_vo)
