@@ -181,6 +181,73 @@ def reference_value_and_grad(R, cfg, ev, motion):
     return loss.detach(), grad
 
 
+def patch_init_leg(dev):
+    """The pyramid's per-patch initialiser at the shipped YAML's regime (30 000 events on 260x346, finest level: 16x16 patches of
+    16x21 pixels, one TPE trial of every patch per call = 256 candidate costs): device time and end-to-end time of one batched
+    call, next to the reference's own chain (src/solver/patch_contrast_pyramid.py:379-415: numpy warp / vote, scipy Gaussian,
+    cv2 Sobel) timed on a sample of the same evaluations.  An auxiliary leg: reported, never part of `value`."""
+    import torch
+    from event_based_optical_flow_b200.patch_init import PatchCandidateEvaluator
+    from oracle import patch_init_oracle as PO
+    rng = np.random.default_rng(3)
+    n, size, grid = 30_000, (16, 21), (16, 16)
+    ev = synth_events(n, 77).astype(np.float64)
+    rects = np.array([[i * size[0], (i + 1) * size[0], j * size[1], (j + 1) * size[1]] for i in range(grid[0]) for j in range(grid[1])])
+    t0 = time.perf_counter()
+    evaluator = PatchCandidateEvaluator(torch.from_numpy(ev).to(dev), rects, size, sigma=1.0)
+    torch.cuda.synchronize()
+    prepare_ms = (time.perf_counter() - t0) * 1e3
+    cand = rng.uniform(-20, 20, (len(rects), 1, 2))
+    loss = evaluator.evaluate(cand)
+    cand_dev = torch.from_numpy(cand).to(dev)
+    evaluator.losses(cand_dev)
+    torch.cuda.synchronize()
+    dev_us = []
+    for _ in range(20):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        evaluator.losses(cand_dev)
+        b.record()
+        torch.cuda.synchronize()
+        dev_us.append(a.elapsed_time(b) * 1e3)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        evaluator.evaluate(cand)
+    e2e_us = (time.perf_counter() - t0) / 20 * 1e6
+    # the CPU side: the unmodified reference operators composed as calculate_cost_for_small_patch composes them, else the port
+    sample = [int(i) for i in np.nonzero(evaluator.valid)[0][:48]]
+    kind, R = "port", None
+    try:
+        from oracle import reference_loader
+        R = reference_loader.load()
+    except Exception:
+        R = None
+    if R is not None:
+        kind = "reference"
+        warper = R.warp.Warp(size, calculate_feature=False, normalize_t=True)
+        imager = R.event_image_converter.EventImageConverter(size, outer_padding=0)
+        cost = R.costs.NormalizedGradientMagnitude(direction="minimize", store_history=False, precision="64", cuda_available=False)
+
+        def cpu_loss(f, c):
+            theta_c = np.array(c) * (f[:, 2].max() - f[:, 2].min())
+            warped, _ = warper.warp_event(f, theta_c, "2d-translation", direction="middle")
+            return cost.calculate({"omit_boundary": False, "clip": True, "orig_iwe": imager.create_iwe(f, "bilinear_vote", 1),
+                                   "iwe": imager.create_iwe(warped, "bilinear_vote", 1)})
+    else:
+        def cpu_loss(f, c):
+            return PO.candidate_loss(f, c, size, (0, 0), 1.0)
+    crops = {i: PO.crop_to_patch(ev, *rects[i]) for i in sample}
+    cpu_loss(crops[sample[0]], cand[sample[0], 0])
+    t0 = time.perf_counter()
+    ref = np.array([float(cpu_loss(crops[i], cand[i, 0])) for i in sample])
+    cpu_us = (time.perf_counter() - t0) / len(sample) * 1e6
+    rel = float(np.max(np.abs(loss[sample, 0] - ref) / np.abs(ref)))
+    return {"workload": f"{n} events, 260x346, {len(rects)} patches of {size[0]}x{size[1]}, 1 candidate per patch and call, sigma 1",
+            "evaluations_per_call": int(len(rects)), "prepare_ms": prepare_ms, "device_us_per_call": float(np.median(dev_us)),
+            "e2e_us_per_call": e2e_us, "cpu_us_per_evaluation": cpu_us, "cpu_kind": kind, "cpu_sample": len(sample),
+            "speedup_e2e_vs_cpu": cpu_us * len(rects) / e2e_us, "max_rel_vs_cpu": rel, "gpu_launches_per_call": 1}
+
+
 def load_reference_for(cfg):
     """The unmodified reference, when it is installed and this configuration is one it is composed for here; else None (the
     oracle port times instead)."""
@@ -469,6 +536,14 @@ def run_b200(args) -> None:
         except Exception as e:  # report, never fail the benchmark line over the second-order leg
             hvp_ms = f"failed: {e!r}"
 
+    # ---- the pyramid's per-patch initialiser, batched: one call = one TPE trial of all 256 patches
+    patch_init = None
+    if world == 1 and args.config == "c2" and not args.skip_cpu:
+        try:
+            patch_init = patch_init_leg(dev)
+        except Exception as e:
+            patch_init = f"failed: {e!r}"
+
     # ---- the same batch driven by the patch grid the pyramid optimises (16x16 nodes, the shipped YAML's geometry): the tile-flow
     # model evaluates the dense flow inside the event kernels, so the per-step host traffic is 2 KB each way instead of 720 KB
     tile_leg = None
@@ -712,7 +787,7 @@ def run_b200(args) -> None:
                     "what": "host pinned motion -> device, step_into (public API), gradient+cost -> pinned host in one copy, sync; events resident"},
             "gpu_launches": per_step_kernels * args.steps if per_step_kernels else None,
             "plan_ms": plan_ms, "reshard_ms": reshard_ms, "events_this_rank": n_local, "value_amortised_50_iters": world * n / (amortised_ms * 1e-3),
-            "hvp_ms": hvp_ms, "tile_flow": tile_leg, "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
+            "hvp_ms": hvp_ms, "patch_init": patch_init, "tile_flow": tile_leg, "roofline": roof, "parity": parity, "sharded_vs_single": sharded_check, "cpu_baseline": cpu, "clocks": clocks,
         }
     if line is not None:
         print(json.dumps(line), flush=True)

@@ -14,7 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libcmax_b200.so")
-SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_mid.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu")
+SOURCES = ("cmax_events.cu", "cmax_ops.cu", "cmax_cost.cu", "cmax_fused.cu", "cmax_mid.cu", "cmax_tileflow.cu", "cmax_flowvoxel.cu", "cmax_lean.cu", "cmax_patchinit.cu")
 HEADERS = ("cmax_common.cuh", "cmax_plan.cuh", "cmax_stats.cuh", "cmax_runs.cuh", "cmax_objective.cuh", "cmax_tile.cuh", os.path.join("..", "..", "include", "cmax_b200.h"))
 # `--measure` builds a SECOND library, lib/libcmax_b200_measure.so, with the measurement aids compiled in (-DCMAX_MEASURE:
 # partial stage masks, CMAX_PDL=0, phase stamps of the image / exchange kernels).  The release library has none of them and

@@ -11,6 +11,7 @@ import threading
 from . import _build
 
 ABI_VERSION = 2
+PATCH_GLOBAL_IMAGES, PATCH_KEEP_IMAGES = 1, 2  # flags of cmax_patch_candidates
 MAX_REFS = 4
 MAX_BINS = 64
 MAX_PEERS = 8
@@ -58,6 +59,8 @@ _SIGNATURES = {
     "cmax_blur3": (_i, [_p, _p, _i, _i, _i, _f, _i, _p]),
     "cmax_tile_flow_upsample": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "cmax_tile_flow_upsample_backward": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "cmax_patch_candidates_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "cmax_patch_candidates": (_i, [_p, _p, _i64, _i, _p, _p, _i, _i, _i, _i, _i, _f, _p, _i, _p, _sz, _p, _p]),
     "cmax_flow_voxel_workspace_bytes": (_sz, [_i, _i]),
     "cmax_flow_voxel": (_i, [_p, _i, _i, _i, _i, _i, _p, _p]),
     "cmax_flow_voxel_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),

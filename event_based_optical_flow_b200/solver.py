@@ -26,6 +26,7 @@ import logging
 from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import costs as b200_costs
@@ -173,6 +174,18 @@ class B200CostMixin:
         else:
             cache.move_to_end(id(events))
         return batch
+
+    # -- the per-patch initialiser of the pyramid (src/solver/patch_contrast_pyramid.py:320-362): same studies, same sampling
+    #    ranges, same candidate cost -- but trial t of ALL patches is evaluated by one batched CUDA call instead of one numpy /
+    #    scipy / cv2 chain per patch and trial
+    def initialize_guess_from_optuna_sampling(self, events, motion0):
+        from .patch_init import PatchCandidateEvaluator, n_trials_at, run_patch_studies
+        evaluator = PatchCandidateEvaluator(events, [self.patches[i] for i in range(self.n_patch)], self.scaled_patch_size[self.current_scale],
+                                            outer_padding=self.padding, sigma=float(self.iwe_config["blur_sigma"]),
+                                            normalize_t=self.normalize_t_in_batch)
+        n_iter = self.opt_config["n_iter"]
+        return run_patch_studies(evaluator, np.asarray(motion0, dtype=np.float64).reshape(2, -1), n_trials_at(n_iter, self.current_scale, self.coarest_scale),
+                                 min(10, n_iter // 5), suggest=lambda trial, key, m0: self.sampling_initial(trial, key, m0))
 
     def _b200_image_geometry(self) -> Tuple[Tuple[int, int], Tuple[int, int]]:
         pad = tuple(int(p) for p in getattr(self.imager, "outer_padding", (0, 0)))

@@ -158,6 +158,34 @@ int cmax_tile_flow_upsample(const float* motion, int hp, int wp, int pad_h, int 
 int cmax_tile_flow_upsample_backward(const float* grad_dense, int hp, int wp, int pad_h, int pad_w, int sh, int sw, int H, int W,
                                      float* grad_motion, cmax_stream_t stream);
 
+/* ------------------------------------------------------------------ per-patch initialiser   */
+/* K translation candidates for each of P patches in one call -- replaces P*K calls of
+ * PyramidalPatchContrastMaximization.calculate_cost_for_small_patch(events, theta, "2d-translation")
+ * (src/solver/patch_contrast_pyramid.py:379-415, driven per patch and per TPE trial by :320-377), the reference's numpy path:
+ * 2-dof warp to the middle of the patch's time span (src/warp.py:483-522), numpy bilinear vote
+ * (src/event_image_converter.py:257-312), scipy.ndimage.gaussian_filter(sigma) ('reflect' border, radius int(4 sigma + 0.5)),
+ * cv2.Sobel(ksize 3) / 8 (BORDER_REFLECT_101), mean(gx^2 + gy^2) over the whole (padded) patch image
+ * (src/costs/gradient_magnitude.py:78-95, omit_boundary = False).
+ *   patch_events [m,3] f32   the events of all patches, grouped by patch: (x - x_min, y - y_min, dt) with dt already
+ *                            (t - t_ref) / period of the PATCH's events (the host side prepares it once per frame and level)
+ *   patch_offsets [P+1] i64  device array; patch p owns rows [offsets[p], offsets[p+1]); max_patch_events = the largest count
+ *   candidates [P,K,2] f64   (trans_x, trans_y) as the sampler suggests them
+ *   theta_scale [P] f64      the patch's time span the reference multiplies a candidate by (pyramid.py:366-371); NULL = 1
+ *   orig_energy [P] f64      NULL: out [P,K] = mean squared gradient magnitude of the blurred image of warped events;
+ *                            else: out = orig_energy[p] / that (the reference's loss,
+ *                            src/costs/normalized_gradient_magnitude.py:90-94 with direction 'minimize'; NaN -> 0 as
+ *                            pyramid.py:374-375).  orig_energy is this entry point's own output for a zero candidate.
+ *   flags                    CMAX_PATCH_GLOBAL_IMAGES: never use the shared-memory kernel (it serves patch images of up to
+ *                            25 600 padded pixels); CMAX_PATCH_KEEP_IMAGES: leave the blurred images [P,K,Hp,Wp] f32 at the
+ *                            start of the workspace (always the case with global images).
+ * workspace: cmax_patch_candidates_workspace_bytes() bytes; may be NULL when the shared-memory kernel runs without KEEP_IMAGES. */
+enum { CMAX_PATCH_GLOBAL_IMAGES = 1, CMAX_PATCH_KEEP_IMAGES = 2 };
+size_t cmax_patch_candidates_workspace_bytes(int n_patches, int n_candidates, int h, int w, int pad_h, int pad_w);
+int cmax_patch_candidates(const float* patch_events, const int64_t* patch_offsets, int64_t max_patch_events, int n_patches,
+                          const double* candidates, const double* theta_scale, int n_candidates, int h, int w, int pad_h, int pad_w,
+                          float sigma, const double* orig_energy, int flags, void* workspace, size_t workspace_bytes, double* out,
+                          cmax_stream_t stream);
+
 /* ------------------------------------------------------------------ time-aware flow voxel   */
 typedef enum {
   CMAX_SCHEME_UPWIND = 0,  /* "upwind"   src/utils/flow_utils.py:439-493 */
