@@ -8,6 +8,7 @@ Layout:
   warp.py, event_image_converter.py, costs/   drop-in mirrors of the reference's duck-typed seam objects
   objective.py                  the fused per-iteration objective (EventPlan, ContrastObjective, cm_objective)
   solver.py                     the mixin that plugs the fused objective into the reference's solver seam
+  patch_init.py                 batched 2-dof candidate costs of the pyramid's per-patch (Optuna) initialiser
   distributed.py                event sharding + the two all-reduces per CM iteration
 """
 from . import _lib
