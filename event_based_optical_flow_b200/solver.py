@@ -141,6 +141,8 @@ class B200CostMixin:
     b200_cuda_graph = False     # True: single-GPU objectives replay a CUDA graph per evaluation (small, launch-bound batches)
     b200_fuse_tile_flow = None  # None: TileFlowObjective's default (fused when sharded); True / False force the tile-flow model on / off
 
+    b200_defer_history = True   # cost histories are materialised when read (get_history / clear_history), not with one .item() per call
+
     b200_max_batches = 2  # resident event batches (the current one and its predecessor); older ones are closed
 
     # -- cache, keyed on the IDENTITY of the event tensor (the reference hands the same tensor to every objective call of an
@@ -214,10 +216,46 @@ class B200CostMixin:
             batch.objectives[key] = obj
         return obj
 
-    @staticmethod
-    def _b200_register(cost, loss) -> None:
-        if getattr(cost, "store_history", False):
+    # -- cost history without a host sync per call (src/costs/base.py:42-56 does `loss.item()` inside
+    #    every `calculate`: three device round trips per objective call for a hybrid of two terms).  The losses stay on the device
+    #    until somebody asks: `get_history()` / `clear_history()` of every cost object that has deferred entries are wrapped (on the
+    #    INSTANCE) to materialise them first, in call order, with one D2H copy for all of them.
+    def _b200_register(self, cost, loss) -> None:
+        if not getattr(cost, "store_history", False):
+            return
+        if not (self.b200_defer_history and isinstance(loss, torch.Tensor)):
             cost.history["loss"].append(cost.get_item(loss))
+            return
+        self.__dict__.setdefault("_b200_pending", []).append((cost, loss.detach()))
+        if cost.__dict__.get("_b200_history_owner") is not self:
+            for name in ("get_history", "clear_history"):
+                def flushing(*a, _inner=getattr(cost, name), **k):
+                    self.b200_flush_history()
+                    return _inner(*a, **k)
+                setattr(cost, name, flushing)
+            cost._b200_history_owner = self
+
+    def b200_flush_history(self) -> None:
+        """Append the deferred losses to their cost objects' `history["loss"]` (one device -> host copy)."""
+        pending = self.__dict__.get("_b200_pending")
+        if not pending:
+            return
+        self._b200_pending = []
+        values = torch.stack([loss.double().reshape(()) for _, loss in pending]).cpu().tolist()
+        for (cost, _), value in zip(pending, values):
+            cost.history["loss"].append(value)
+
+    def _b200_unrecorded(self, cost, arg: dict):
+        """`cost.calculate(arg)` of a plugin that stays in torch (total variation) with ITS `.item()` deferred too."""
+        if not (self.b200_defer_history and getattr(cost, "store_history", False)):
+            return cost.calculate(arg)
+        cost.store_history = False
+        try:
+            loss = cost.calculate(arg)
+        finally:
+            cost.store_history = True
+        self._b200_register(cost, loss)
+        return loss
 
     def _b200_term(self, cost, events, warp, motion_model, coarse_flow):
         """One (non-hybrid) cost plugin evaluated for this call, or None if it has no fused form here."""
@@ -229,7 +267,7 @@ class B200CostMixin:
             self._b200_register(cost, loss)
             return loss
         if name == "total_variation":
-            return cost.calculate({"flow": coarse_flow, "omit_boundary": True})
+            return self._b200_unrecorded(cost, {"flow": coarse_flow, "omit_boundary": True})
         return None
 
     # -- the pyramid's objective with the tile-flow map INSIDE the event kernels
@@ -293,8 +331,8 @@ class B200CostMixin:
             loss = term(cost)
             if loss is None:
                 return super().objective_scipy(motion_array, *args, **kw)
-        if not (args[2] if len(args) >= 3 else kw.get("suppress_log", False)):
-            logger.info(f"{loss = }")
+        if not (args[2] if len(args) >= 3 else kw.get("suppress_log", False)) and logger.isEnabledFor(logging.INFO):
+            logger.info(f"{loss = }")  # (formatting a CUDA tensor is a host sync: only when somebody listens)
         return loss
 
     def interpolate_dense_flow_from_patch_tensor(self, motion_array: torch.Tensor) -> torch.Tensor:
@@ -335,7 +373,8 @@ class B200CostMixin:
         fusable = (isinstance(events, torch.Tensor) and events.is_cuda and isinstance(warp, torch.Tensor)
                    and self.iwe_config.get("method", "bilinear_vote") == "bilinear_vote"
                    and motion_model in ("dense-flow", "dense-flow-voxel", "2d-translation", "rigid-optical-flow"))
-        if not fusable:  # numpy callers (metrics, visualisation, the Optuna initialiser) keep the reference path
+        if not fusable:  # numpy callers (metrics, visualisation) keep the reference path -- which registers its history at once
+            self.b200_flush_history()
             return super().calculate_cost(events, warp, motion_model, coarse_flow, save_intermediate_result)
         if warp.device != events.device:
             warp = warp.to(events.device)
@@ -345,11 +384,13 @@ class B200CostMixin:
             for name, entry in cost.cost_func.items():
                 term = self._b200_term(entry["func"], events, warp, motion_model, coarse_flow)
                 if term is None:
+                    self.b200_flush_history()
                     return super().calculate_cost(events, warp, motion_model, coarse_flow, save_intermediate_result)
                 loss = loss + (1.0 / term if entry["weight"] == "inv" else entry["weight"] * term)
             self._b200_register(cost, loss)
             return loss
         loss = self._b200_term(cost, events, warp, motion_model, coarse_flow)
         if loss is None:
+            self.b200_flush_history()
             return super().calculate_cost(events, warp, motion_model, coarse_flow, save_intermediate_result)
         return loss

@@ -381,3 +381,44 @@ def test_reshard_events_by_pixel_gloo_world3():
         assert parts[r][2] < parts[r + 1][1], "key ranges must be disjoint and in rank order"
     counts = [len(p[0]) for p in parts]
     assert max(counts) - min(counts) <= 0.02 * n + 8, counts
+
+
+def test_mixin_defers_cost_history_until_it_is_read():
+    """SURVEY.md section 8f row 4 (drop the per-call `.item()`): losses registered through the mixin stay tensors until
+    `get_history()` / `clear_history()` of the cost object is called; order and values are those of immediate registration."""
+    from event_based_optical_flow_b200.costs import CostBase, HybridCost
+    from event_based_optical_flow_b200.solver import B200CostMixin
+
+    class Plain(CostBase):
+        name = "plain_for_test"
+
+        def _loss(self, arg):
+            return arg["x"]
+
+    mixin = B200CostMixin()
+    a, b = Plain(store_history=True), Plain(store_history=True)
+    hybrid = HybridCost("minimize", {"total_variation": 1.0}, store_history=True)
+    for k in range(3):
+        mixin._b200_register(a, torch.tensor(float(k)))
+        mixin._b200_register(b, torch.tensor(10.0 + k, dtype=torch.float64))
+        mixin._b200_register(hybrid, torch.tensor(100.0 + k))
+    assert a.history["loss"] == [] and len(mixin._b200_pending) == 9
+    assert a.get_history()["loss"] == [0.0, 1.0, 2.0]          # reading one flushes all (one copy)
+    assert b.history["loss"] == [10.0, 11.0, 12.0] and mixin._b200_pending == []
+    assert hybrid.get_history()["loss"] == [100.0, 101.0, 102.0]
+    mixin._b200_register(a, torch.tensor(7.0))
+    a.clear_history()                                           # pending entries belong to the history that is being cleared
+    assert a.get_history()["loss"] == [] and mixin._b200_pending == []
+    a.disable_history_register()
+    mixin._b200_register(a, torch.tensor(8.0))
+    assert a.get_history()["loss"] == []
+    # a plugin that stays in torch: its own bookkeeping is bypassed for the call and deferred as well
+    flow = torch.arange(5.0)[None, :, None].expand(2, 5, 5).contiguous()
+    tv = hybrid.cost_func["total_variation"]["func"]
+    loss = mixin._b200_unrecorded(tv, {"flow": flow, "omit_boundary": True})
+    assert tv.store_history and tv.history["loss"] == [] and tv.get_history()["loss"] == [float(loss)]
+    # switched off: immediate, like the reference
+    eager = B200CostMixin()
+    eager.b200_defer_history = False
+    eager._b200_register(b, torch.tensor(1.5))
+    assert b.history["loss"][-1] == 1.5
