@@ -180,6 +180,8 @@ def run_patch_studies(evaluator: PatchCandidateEvaluator, motion0: np.ndarray, n
             lo, hi = sampling_range(m0)[0 if key == "trans_x" else 1]
             return trial.suggest_uniform(key, lo, hi)
     live = [i for i in range(P) if evaluator.valid[i]]
+    if not live:
+        return motion0.copy()
     studies = {i: optuna.create_study(direction="minimize", sampler=optuna.samplers.TPESampler(n_startup_trials=n_startup_trials)) for i in live}
     cand = np.zeros((P, 1, 2))
     for _ in range(int(n_trials)):
