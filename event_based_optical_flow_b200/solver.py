@@ -131,6 +131,18 @@ class _Batch:
         self.plans.clear()
 
 
+def _weighted_sum(total, term, weight):
+    """total + weight * term as src/costs/hybrid.py:40-52 forms it ('inv' = the reciprocal), without the torch operators that
+    change nothing (0.0 + x, 1.0 * x): at the shipped batch size every operator is ~10 us of host time, forward and backward."""
+    if isinstance(weight, str):
+        if weight != "inv":
+            raise ValueError(f"unknown hybrid weight {weight!r}")
+        term = 1.0 / term
+    elif weight != 1.0:
+        term = weight * term
+    return term if total is None else total + term
+
+
 class B200CostMixin:
     """Mix in BEFORE a reference solver class.  Needs from the host class only what the reference's own
     `get_arg_for_cost` uses: `self.cost_func`, `self.iwe_config`, `self.imager`, `self.warper`."""
@@ -141,6 +153,7 @@ class B200CostMixin:
     b200_cuda_graph = False     # True: single-GPU objectives replay a CUDA graph per evaluation (small, launch-bound batches)
     b200_fuse_tile_flow = None  # None: TileFlowObjective's default (fused when sharded); True / False force the tile-flow model on / off
 
+    b200_fast_total_variation = True  # the hybrid's total-variation term through costs.total_variation.total_variation_loss
     b200_defer_history = True   # cost histories are materialised when read (get_history / clear_history), not with one .item() per call
 
     b200_max_batches = 2  # resident event batches (the current one and its predecessor); older ones are closed
@@ -257,6 +270,15 @@ class B200CostMixin:
         self._b200_register(cost, loss)
         return loss
 
+    def _b200_total_variation(self, cost, flow):
+        """The total-variation term of a hybrid cost for a tensor flow: value + analytic gradient in 8 torch operators
+        (costs/total_variation.py) instead of ~200 through the plugin's two Conv2d modules and autograd; same numbers."""
+        if not (self.b200_fast_total_variation and isinstance(flow, torch.Tensor) and flow.dim() in (3, 4) and flow.shape[-3] == 2):
+            return self._b200_unrecorded(cost, {"flow": flow, "omit_boundary": True})
+        loss = b200_costs.total_variation.total_variation_loss(flow, True, cost.direction)
+        self._b200_register(cost, loss)
+        return loss
+
     def _b200_term(self, cost, events, warp, motion_model, coarse_flow):
         """One (non-hybrid) cost plugin evaluated for this call, or None if it has no fused form here."""
         name = getattr(cost, "name", None)
@@ -267,7 +289,7 @@ class B200CostMixin:
             self._b200_register(cost, loss)
             return loss
         if name == "total_variation":
-            return self._b200_unrecorded(cost, {"flow": coarse_flow, "omit_boundary": True})
+            return self._b200_total_variation(cost, coarse_flow)
         return None
 
     # -- the pyramid's objective with the tile-flow map INSIDE the event kernels
@@ -315,17 +337,18 @@ class B200CostMixin:
                 self._b200_register(cost, loss)
                 return loss
             if name == "total_variation":
-                return cost.calculate({"flow": motion, "omit_boundary": True})
+                return self._b200_total_variation(cost, motion)
             return None
 
         cost = self.cost_func
         if getattr(cost, "name", None) == "hybrid":
-            loss = 0.0
+            loss = None
             for entry in cost.cost_func.values():
                 t = term(entry["func"])
                 if t is None:
+                    self.b200_flush_history()
                     return super().objective_scipy(motion_array, *args, **kw)
-                loss = loss + (1.0 / t if entry["weight"] == "inv" else entry["weight"] * t)
+                loss = _weighted_sum(loss, t, entry["weight"])
             self._b200_register(cost, loss)
         else:
             loss = term(cost)
@@ -380,13 +403,13 @@ class B200CostMixin:
             warp = warp.to(events.device)
         cost = self.cost_func
         if getattr(cost, "name", None) == "hybrid":
-            loss = 0.0
+            loss = None
             for name, entry in cost.cost_func.items():
                 term = self._b200_term(entry["func"], events, warp, motion_model, coarse_flow)
                 if term is None:
                     self.b200_flush_history()
                     return super().calculate_cost(events, warp, motion_model, coarse_flow, save_intermediate_result)
-                loss = loss + (1.0 / term if entry["weight"] == "inv" else entry["weight"] * term)
+                loss = _weighted_sum(loss, term, entry["weight"])
             self._b200_register(cost, loss)
             return loss
         loss = self._b200_term(cost, events, warp, motion_model, coarse_flow)

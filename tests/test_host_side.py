@@ -422,3 +422,21 @@ def test_mixin_defers_cost_history_until_it_is_read():
     eager.b200_defer_history = False
     eager._b200_register(b, torch.tensor(1.5))
     assert b.history["loss"][-1] == 1.5
+
+
+def test_total_variation_single_function_second_order_is_zero_like_autograd():
+    """The one-pass TV (value + analytic gradient in the forward) under a recorded backward: connected to the flow with a zero
+    Hessian, exactly what autograd through conv -> abs -> mean gives (torch.autograd.functional.vhp is what Newton-CG calls)."""
+    from event_based_optical_flow_b200.costs import functions
+    from event_based_optical_flow_b200.costs.total_variation import total_variation_loss
+    tv = functions["total_variation"](direction="minimize")
+    torch.manual_seed(1)
+    m0 = torch.randn(2, 9, 13, dtype=torch.float64)
+    v = torch.randn_like(m0)
+    val, hv = torch.autograd.functional.vhp(lambda x: tv.calculate({"flow": x, "omit_boundary": True}), m0, v)
+    assert float(hv.abs().max()) == 0.0
+    # inside a sum with a curved term the Hessian is the curved term's alone
+    _, hv2 = torch.autograd.functional.vhp(lambda x: total_variation_loss(x, True) * 3.0 + (x ** 3).sum(), m0, v)
+    torch.testing.assert_close(hv2, 6 * m0 * v)
+    assert float(total_variation_loss(m0, True, "maximize")) == -float(val)
+    assert not total_variation_loss(m0, True).requires_grad  # no graph, no saved gradient, when nothing asks for one
