@@ -311,7 +311,8 @@ class B200CostMixin:
         batch = self._b200_batch(events)
         if getattr(self, "normalize_t_in_batch", False):
             if batch.t_scale is None:  # events are constant over an optimize(): one host sync per batch instead of one per call
-                batch.t_scale = float(events[:, 2].max() - events[:, 2].min())
+                t = events.detach()[:, 2]
+                batch.t_scale = float(t.max() - t.min())
             t_scale = batch.t_scale
         else:
             t_scale = 1.0
