@@ -7,7 +7,6 @@ on the current CUDA stream; callers convert dtypes.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Sequence, Tuple
 
 import torch

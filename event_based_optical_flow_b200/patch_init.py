@@ -116,9 +116,9 @@ class PatchCandidateEvaluator:
         self.orig_energy = self._run(torch.zeros(P, 1, 2, dtype=torch.float64, device=self.device), None, None, keep_images=False)[:, 0].contiguous()
 
     def _run(self, cand: torch.Tensor, scale, orig, keep_images: bool) -> torch.Tensor:
+        if cand.ndim != 3 or cand.shape[0] != self.n_patches or cand.shape[1] < 1 or cand.shape[2] != 2:
+            raise ValueError(f"candidates must be [{self.n_patches}, K >= 1, 2], got {tuple(cand.shape)}")
         P, K = int(cand.shape[0]), int(cand.shape[1])
-        if cand.ndim != 3 or P != self.n_patches or cand.shape[2] != 2:
-            raise ValueError(f"candidates must be [{self.n_patches}, K, 2], got {tuple(cand.shape)}")
         cand = cand.detach().to(device=self.device, dtype=torch.float64).contiguous()
         flags = self.flags | (_lib.PATCH_KEEP_IMAGES if keep_images else 0)
         with torch.cuda.device(self.device):
