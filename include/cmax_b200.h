@@ -262,7 +262,7 @@ int cmax_plan_set_compact(cmax_plan_t* plan, int enable, int32_t* h_compact, cma
  * Bit 0 = the memsets, bit 1 = the event kernels, bit 2 = the image-sized kernels. */
 int cmax_plan_set_stage_mask(cmax_plan_t* plan, int mask);
 
-/* What one CM evaluation computes: cost = form(stat(blur(iwe_r)))   src/costs/*.py, src/solver/patch_contrast_base.py:289-352 */
+/* What one CM evaluation computes: cost = form(stat(blur(iwe_r)))   src/costs/<cost>.py, src/solver/patch_contrast_base.py:289-352 */
 typedef struct {
   int32_t stat;           /* cmax_stat */
   int32_t form;           /* cmax_cost_form */

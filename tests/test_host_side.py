@@ -440,3 +440,63 @@ def test_total_variation_single_function_second_order_is_zero_like_autograd():
     torch.testing.assert_close(hv2, 6 * m0 * v)
     assert float(total_variation_loss(m0, True, "maximize")) == -float(val)
     assert not total_variation_loss(m0, True).requires_grad  # no graph, no saved gradient, when nothing asks for one
+
+
+def test_binding_constants_equal_the_header():
+    """Every enum value / limit `_lib.py` hard-codes is the one include/cmax_b200.h declares (the binding a maintainer would
+    write from the header alone must agree with the one shipped)."""
+    from event_based_optical_flow_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "cmax_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    values = {k: int(v) for k, v in re.findall(r"\b(CMAX_[A-Z0-9_]+)\s*=\s*(\d+)", header)}
+    values.update({k: int(v) for k, v in re.findall(r"#define\s+(CMAX_[A-Z0-9_]+)\s+(\d+)", header)})
+    assert values["CMAX_ABI_VERSION"] == _lib.ABI_VERSION
+    assert (values["CMAX_MAX_REFS"], values["CMAX_MAX_BINS"], values["CMAX_MAX_PEERS"]) == (_lib.MAX_REFS, _lib.MAX_BINS, _lib.MAX_PEERS)
+    assert [values[k] for k in ("CMAX_OK", "CMAX_ERR_ARG", "CMAX_ERR_CUDA", "CMAX_ERR_SOURCE_OOB", "CMAX_ERR_WORKSPACE")] == \
+        [_lib.OK, _lib.ERR_ARG, _lib.ERR_CUDA, _lib.ERR_SOURCE_OOB, _lib.ERR_WORKSPACE]
+    assert _lib.MOTION == {"dense-flow": values["CMAX_MOTION_DENSE"], "dense-flow-voxel": values["CMAX_MOTION_VOXEL"],
+                           "2d-translation": values["CMAX_MOTION_2DOF"], "rigid-optical-flow": values["CMAX_MOTION_2DOF"],
+                           "tile-flow": values["CMAX_MOTION_TILE"]}
+    assert _lib.STAT == {"variance": values["CMAX_STAT_VARIANCE"], "gradmag": values["CMAX_STAT_GRADMAG"]}
+    assert _lib.FORM == {"plain": values["CMAX_COST_PLAIN"], "normalized": values["CMAX_COST_NORMALIZED"], "multifocal": values["CMAX_COST_MULTIFOCAL"]}
+    assert _lib.ORDER == {"asis": values["CMAX_ORDER_ASIS"], "tile": values["CMAX_ORDER_TILE"], "pixel": values["CMAX_ORDER_PIXEL"]}
+    assert _lib.SCHEME == {"upwind": values["CMAX_SCHEME_UPWIND"], "burgers": values["CMAX_SCHEME_BURGERS"]}
+    assert (_lib.PATCH_GLOBAL_IMAGES, _lib.PATCH_KEEP_IMAGES) == (values["CMAX_PATCH_GLOBAL_IMAGES"], values["CMAX_PATCH_KEEP_IMAGES"])
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/cmax_b200.h compiles as C (gcc, no CUDA headers: what a cgo / JNI / ctypes binding sees), and the structs the
+    Python binding mirrors have the C compiler's sizes and field offsets."""
+    import shutil
+    import subprocess
+    from event_based_optical_flow_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "layout.c"
+    src.write_text(r"""
+#include <stddef.h>
+#include <stdio.h>
+#include "cmax_b200.h"
+int main(void) {
+  printf("ref %zu %zu %zu\n", sizeof(cmax_ref), offsetof(cmax_ref, mode), offsetof(cmax_ref, fraction));
+  printf("spec %zu %zu %zu %zu %zu %zu %zu\n", sizeof(cmax_cost_spec), offsetof(cmax_cost_spec, stat), offsetof(cmax_cost_spec, form),
+         offsetof(cmax_cost_spec, direction_sign), offsetof(cmax_cost_spec, omit_boundary), offsetof(cmax_cost_spec, sigma),
+         offsetof(cmax_cost_spec, weights));
+  printf("peers %zu %zu %zu %zu %zu %zu\n", sizeof(cmax_peers), offsetof(cmax_peers, n_peers), offsetof(cmax_peers, rank),
+         offsetof(cmax_peers, iwe), offsetof(cmax_peers, grad), offsetof(cmax_peers, flags));
+  printf("time %zu\n", sizeof(cmax_time_params_t));
+  return 0;
+}
+""")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = dict((line.split()[0], [int(v) for v in line.split()[1:]]) for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+
+    def layout(struct):
+        return [ctypes.sizeof(struct)] + [getattr(struct, name).offset for name, _ in struct._fields_]
+
+    assert out["ref"] == layout(_lib.Ref)
+    assert out["spec"] == layout(_lib.CostSpec)
+    assert out["peers"] == layout(_lib.Peers)
+    assert out["time"] == [_lib.TIME_PARAMS_BYTES]
