@@ -500,3 +500,24 @@ int main(void) {
     assert out["spec"] == layout(_lib.CostSpec)
     assert out["peers"] == layout(_lib.Peers)
     assert out["time"] == [_lib.TIME_PARAMS_BYTES]
+
+
+def test_every_entry_point_rejects_null_arguments_without_a_gpu():
+    """Argument validation comes before any CUDA call: with NULL pointers and zero sizes every status-returning entry point of
+    the C ABI answers CMAX_ERR_ARG and names itself in cmax_last_error() -- on a machine without a GPU, without crashing."""
+    from event_based_optical_flow_b200 import _lib
+    lib = _lib.load()
+    scalars = {ctypes.c_int: 0, ctypes.c_int32: 0, ctypes.c_int64: 0, ctypes.c_size_t: 0, ctypes.c_float: 0.0, ctypes.c_double: 0.0}
+    checked = 0
+    for name, (restype, argtypes) in _lib._SIGNATURES.items():
+        if restype is not ctypes.c_int or not argtypes:
+            continue
+        args = [scalars.get(t) for t in argtypes]  # None = NULL for every pointer type
+        status = getattr(lib, name)(*args)
+        message = lib.cmax_last_error().decode()
+        assert status == _lib.ERR_ARG, (name, status, message)
+        assert message.startswith(name), (name, message)
+        checked += 1
+    assert checked >= 25
+    with pytest.raises(ValueError, match="cmax_vote"):  # the mapping of the status to the reference's exception type
+        _lib.call("cmax_vote", *[scalars.get(t) for t in _lib._SIGNATURES["cmax_vote"][1]])
