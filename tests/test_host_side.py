@@ -75,6 +75,10 @@ def test_no_cpu_fallback():
         B.EventImageConverter((8, 8)).create_iwe(ev)
     with pytest.raises(RuntimeError):
         B.cost_functions["image_variance"]().calculate({"iwe": torch.zeros(8, 8), "omit_boundary": True})
+    if not torch.cuda.is_available():
+        from event_based_optical_flow_b200.patch_init import PatchCandidateEvaluator
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            PatchCandidateEvaluator(ev, [(0, 8, 0, 8)], (8, 8))
 
 
 def test_product_never_imports_the_oracle():
